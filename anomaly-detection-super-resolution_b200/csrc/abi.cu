@@ -1,0 +1,104 @@
+// extern "C" entry points that only marshal arguments (the kernels live in the other .cu files).
+#include "adsr_kernels.h"
+
+using namespace adsr;
+
+extern "C" int adsr_abi_version(void) { return ADSR_ABI_VERSION; }
+
+extern "C" const char* adsr_status_string(int status) {
+    switch (status) {
+        case ADSR_OK: return "ok";
+        case ADSR_ERR_BAD_SHAPE: return "unsupported shape";
+        case ADSR_ERR_BAD_ALIGN: return "misaligned pointer or pitch";
+        case ADSR_ERR_LAUNCH: return "kernel launch failed";
+        case ADSR_ERR_CUDA: return "CUDA runtime call failed";
+        case ADSR_ERR_ARCH: return "device is not sm_100";
+    }
+    return "unknown status";
+}
+
+extern "C" int adsr_device_check(int* host_num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return ADSR_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return ADSR_ERR_CUDA;
+    if (host_num_sms) *host_num_sms = prop.multiProcessorCount;
+    return prop.major == 10 ? ADSR_OK : ADSR_ERR_ARCH;
+}
+
+extern "C" int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* w_packed, const float* bias_padded,
+                                 int N, int BN, int n_tiles, int act, float slope, float alpha, const void* res,
+                                 int64_t ldres, void* out, int64_t ldo, int ocol0, int n_store, int num_sms, void* stream) {
+    if (K <= 0 || N <= 0 || n_store > n_tiles * BN || lda < ((K + 7) & ~7)) return ADSR_ERR_BAD_SHAPE;
+    TcGemmParams p{};
+    p.A = static_cast<const __nv_bfloat16*>(A);
+    p.lda = lda;
+    p.M = M;
+    p.K8 = (K + 7) & ~7;
+    p.k16_total = (K + 15) / 16;
+    p.num_k_stages = (K + 63) / 64;
+    p.conv = 0;
+    p.Hin = p.Win = p.Hout = p.Wout = 1;
+    p.stride = 1;
+    p.stages_per_tap = 1;
+    p.k16_per_tap = 0;
+    p.Bp = static_cast<const uint8_t*>(w_packed);
+    p.n_tiles = n_tiles;
+    p.BN = BN;
+    p.m_tiles = (M + 127) / 128;
+    p.bias = bias_padded;
+    p.N = N;
+    p.n_store = n_store;
+    p.act = act;
+    p.slope = slope;
+    p.alpha = alpha;
+    p.res = static_cast<const __nv_bfloat16*>(res);
+    p.ldres = ldres;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo;
+    p.ocol0 = ocol0;
+    p.out_mode = ADSR_OUT_ROWS;
+    return launch_tc_gemm(p, num_sms, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int Hin, int Win, int Cin, int stride,
+                                       const void* w_packed, const float* bias_padded, int N, int BN, int n_tiles, int act,
+                                       float slope, float alpha, const void* res, int64_t ldres, void* out, int64_t ldo,
+                                       int out_mode, int n_store, int num_sms, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (Cin <= 0 || N <= 0 || (stride != 1 && stride != 2) || n_store > n_tiles * BN || ld_in < ((Cin + 7) & ~7))
+        return ADSR_ERR_BAD_SHAPE;
+    if (out_mode == ADSR_OUT_PIXEL_SHUFFLE2 && ((N % 4) || stride != 1 || res != nullptr)) return ADSR_ERR_BAD_SHAPE;
+    TcGemmParams p{};
+    p.A = static_cast<const __nv_bfloat16*>(in);
+    p.lda = ld_in;
+    p.Hin = Hin;
+    p.Win = Win;
+    p.stride = stride;
+    p.Hout = (Hin + 2 - 3) / stride + 1;
+    p.Wout = (Win + 2 - 3) / stride + 1;
+    p.M = B * p.Hout * p.Wout;
+    p.K8 = (Cin + 7) & ~7;
+    p.conv = 1;
+    p.stages_per_tap = (Cin + 63) / 64;
+    p.k16_per_tap = (Cin + 15) / 16;
+    p.num_k_stages = 9 * p.stages_per_tap;
+    p.k16_total = 0;
+    p.Bp = static_cast<const uint8_t*>(w_packed);
+    p.n_tiles = n_tiles;
+    p.BN = BN;
+    p.m_tiles = (p.M + 127) / 128;
+    p.bias = bias_padded;
+    p.N = N;
+    p.n_store = n_store;
+    p.act = act;
+    p.slope = slope;
+    p.alpha = alpha;
+    p.res = static_cast<const __nv_bfloat16*>(res);
+    p.ldres = ldres;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo;
+    p.ocol0 = 0;
+    p.out_mode = out_mode;
+    return launch_tc_gemm(p, num_sms, static_cast<cudaStream_t>(stream));
+}

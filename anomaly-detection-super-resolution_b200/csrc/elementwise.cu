@@ -1,0 +1,390 @@
+// Bandwidth-bound kernels of the DRCT path: LayerNorm, window index maps / shuffles, the 3-channel
+// head convolution fused with patch_embed LayerNorm, the 3-channel tail convolution fused with the
+// evaluator's uint8 truncation.  All are coalesced, 16-byte vectorised where the layout allows and
+// use warp-shuffle reductions.
+#include "adsr_kernels.h"
+#include "ptx.cuh"
+
+namespace adsr {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the first C columns of a bf16 row; one warp per row, row held in registers.
+// Two-pass statistics (mean, then centred variance) in fp32 like ATen's native_layer_norm.
+// MAXV = 16-byte chunks per lane (C <= 256*MAXV).
+// `src_row` lets the same body serve the plain and the shift+partition variants.
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>
+__device__ __forceinline__ void ln_row(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, int C,
+                                       float eps, int lane) {
+    const int cpad = (C + 15) & ~15;        // columns written (zeros beyond C)
+    float x[MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c0 = (lane + 32 * i) * 8;
+        if (c0 < C) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + c0));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                x[i][2 * j] = (c0 + 2 * j < C) ? bf16_lo(w[j]) : 0.f;
+                x[i][2 * j + 1] = (c0 + 2 * j + 1 < C) ? bf16_hi(w[j]) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[i][j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += x[i][j];
+    }
+    const float mean = warp_sum(sum) / static_cast<float>(C);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c0 = (lane + 32 * i) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = (c0 + j < C) ? x[i][j] - mean : 0.f;
+            var += d * d;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(var) / static_cast<float>(C) + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c0 = (lane + 32 * i) * 8;
+        if (c0 < cpad) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                y[j] = (c < C) ? (x[i][j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) : 0.f;
+            }
+            *reinterpret_cast<uint4*>(out + c0) =
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+    }
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16* __restrict__ in, long long ldi,
+                                                              __nv_bfloat16* __restrict__ out, long long ldo,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int M, int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < M;
+         row += static_cast<long long>(gridDim.x) * warps_per_block)
+        ln_row<MAXV>(in + row * ldi, out + row * ldo, gamma, beta, C, eps, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// window index maps (closed form of torch.roll + window_partition and of calculate_mask's regions)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int region_1d(int t, int L, int ws, int shift) {
+    return (t >= L - ws ? 1 : 0) + (t >= L - shift ? 1 : 0);
+}
+__device__ __forceinline__ int window_src_pixel(int w, int n, int H, int W, int ws, int shift, int* region) {
+    const int nwx = W / ws;
+    const int ys = (w / nwx) * ws + n / ws;
+    const int xs = (w % nwx) * ws + n % ws;
+    if (region) *region = shift > 0 ? 3 * region_1d(ys, H, ws, shift) + region_1d(xs, W, ws, shift) : 0;
+    return ((ys + shift) % H) * W + (xs + shift) % W;
+}
+
+__global__ void window_index_map_kernel(int H, int W, int ws, int shift, int32_t* src, int32_t* region) {
+    const int N = ws * ws, total = (H / ws) * (W / ws) * N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int r;
+        const int s = window_src_pixel(i / N, i % N, H, W, ws, shift, &r);
+        if (src) src[i] = s;
+        if (region) region[i] = r;
+    }
+}
+
+// LayerNorm + cyclic shift + window partition: windows[(b*nW + w)*N + n, :] = LN(x[b, src(w, n), :])
+template <int MAXV>
+__global__ void __launch_bounds__(256) ln_shift_partition_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                                  __nv_bfloat16* __restrict__ win, long long ldw,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float eps, int B, int H,
+                                                                  int W, int C, int ws, int shift) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int N = ws * ws, L = H * W;
+    const long long total = static_cast<long long>(B) * L;
+    for (long long g = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); g < total;
+         g += static_cast<long long>(gridDim.x) * warps_per_block) {
+        const int b = static_cast<int>(g / L);
+        const int rem = static_cast<int>(g - static_cast<long long>(b) * L);
+        const int src = window_src_pixel(rem / N, rem % N, H, W, ws, shift, nullptr);
+        ln_row<MAXV>(x + (static_cast<long long>(b) * L + src) * ldx, win + g * ldw, gamma, beta, C, eps, lane);
+    }
+}
+
+// inverse: x[b, src(w, n), :C] = windows[(b*nW + w)*N + n, :C]   (8-byte vectors: C % 4 == 0)
+__global__ void window_reverse_unshift_kernel(const __nv_bfloat16* __restrict__ win, long long ldw,
+                                              __nv_bfloat16* __restrict__ x, long long ldx, int B, int H, int W, int C,
+                                              int ws, int shift) {
+    const int N = ws * ws, L = H * W;
+    const int vec_per_row = C / 4;
+    const long long total = static_cast<long long>(B) * L * vec_per_row;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long g = i / vec_per_row;
+        const int v = static_cast<int>(i - g * vec_per_row);
+        const int b = static_cast<int>(g / L);
+        const int rem = static_cast<int>(g - static_cast<long long>(b) * L);
+        const int src = window_src_pixel(rem / N, rem % N, H, W, ws, shift, nullptr);
+        const uint2 val = __ldg(reinterpret_cast<const uint2*>(win + g * ldw + v * 4));
+        *reinterpret_cast<uint2*>(x + (static_cast<long long>(b) * L + src) * ldx + v * 4) = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DRCT head: (x - mean) * img_range -> 3x3 conv (nc -> C) + bias -> x0 (bf16) and LayerNorm -> slab.
+// One warp per pixel; lane owns channels lane, lane+32, ...  (C <= 256).  Weights live in shared
+// memory as [C][nc*9] (odd row length 9 or 27: bank-conflict free).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) drct_head_kernel(const float* __restrict__ x, int B, int nc, int H, int W,
+                                                         const float* __restrict__ weight, const float* __restrict__ bias,
+                                                         const float* __restrict__ mean, float img_range,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float eps, int C, __nv_bfloat16* __restrict__ x0, long long ld0,
+                                                         __nv_bfloat16* __restrict__ slab, long long lds) {
+    extern __shared__ float sw[];                 // [C][nc*9] then bias[C], gamma[C], beta[C]
+    const int kk = nc * 9;
+    float* sb = sw + C * kk;
+    float* sg = sb + C;
+    float* sbt = sg + C;
+    for (int i = threadIdx.x; i < C * kk; i += blockDim.x) sw[i] = weight[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { sb[i] = bias[i]; sg[i] = gamma[i]; sbt[i] = beta[i]; }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long total = static_cast<long long>(B) * H * W;
+    const int cpad = (C + 15) & ~15;
+    for (long long pix = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); pix < total;
+         pix += static_cast<long long>(gridDim.x) * warps_per_block) {
+        const int b = static_cast<int>(pix / (H * W));
+        const int rem = static_cast<int>(pix - static_cast<long long>(b) * H * W);
+        const int y = rem / W, xx = rem - y * W;
+        // lanes 0..kk-1 fetch one input tap each, then broadcast by shuffle
+        float tapv = 0.f;
+        if (lane < kk) {
+            const int c = lane / 9, t = lane - c * 9;
+            const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                tapv = (__ldg(x + ((static_cast<long long>(b) * nc + c) * H + iy) * W + ix) - __ldg(mean + c)) * img_range;
+        }
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = lane + 32 * j;
+            acc[j] = ch < C ? sb[ch] : 0.f;
+        }
+        for (int k = 0; k < kk; ++k) {
+            const float v = __shfl_sync(0xffffffffu, tapv, k);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ch = lane + 32 * j;
+                if (ch < C) acc[j] = fmaf(v, sw[ch * kk + k], acc[j]);
+            }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += (lane + 32 * j < C) ? acc[j] : 0.f;
+        const float mu = warp_sum(sum) / static_cast<float>(C);
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = (lane + 32 * j < C) ? acc[j] - mu : 0.f;
+            var += d * d;
+        }
+        const float rstd = rsqrtf(warp_sum(var) / static_cast<float>(C) + eps);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = lane + 32 * j;
+            if (ch < cpad) {
+                const bool ok = ch < C;
+                x0[pix * ld0 + ch] = __float2bfloat16(ok ? acc[j] : 0.f);
+                slab[pix * lds + ch] = __float2bfloat16(ok ? (acc[j] - mu) * rstd * sg[ch] + sbt[ch] : 0.f);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DRCT tail: conv_last 3x3 (Cin -> nc<=4) on NHWC bf16, + x/img_range + mean, optional fp32 NCHW store
+// and the evaluator's uint8 truncation (HWC).  One thread per output pixel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) conv_last_quant_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, int B,
+                                                               int H, int W, int Cin, const float* __restrict__ weight,
+                                                               const float* __restrict__ bias, int nc,
+                                                               const float* __restrict__ mean, float inv_img_range,
+                                                               float u8_scale, float* __restrict__ out,
+                                                               uint8_t* __restrict__ out_u8) {
+    extern __shared__ float swl[];                // [9][Cin][4]
+    for (int i = threadIdx.x; i < 9 * Cin * 4; i += blockDim.x) {
+        const int o = i & 3, c = (i >> 2) % Cin, t = (i >> 2) / Cin;
+        swl[i] = o < nc ? weight[(o * Cin + c) * 9 + t] : 0.f;
+    }
+    __syncthreads();
+    const long long total = static_cast<long long>(B) * H * W;
+    const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= total) return;
+    const int b = static_cast<int>(pix / (H * W));
+    const int rem = static_cast<int>(pix - static_cast<long long>(b) * H * W);
+    const int y = rem / W, x = rem - y * W;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < 9; ++t) {
+        const int iy = y + t / 3 - 1, ix = x + t % 3 - 1;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        const __nv_bfloat16* src = in + ((static_cast<long long>(b) * H + iy) * W + ix) * ld_in;
+        const float4* wt = reinterpret_cast<const float4*>(swl + t * Cin * 4);
+        for (int c0 = 0; c0 < Cin; c0 += 8) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c0));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a0 = bf16_lo(w[j]), a1 = bf16_hi(w[j]);
+                const float4 w0 = wt[c0 + 2 * j], w1 = wt[c0 + 2 * j + 1];
+                acc[0] = fmaf(a0, w0.x, acc[0]); acc[1] = fmaf(a0, w0.y, acc[1]);
+                acc[2] = fmaf(a0, w0.z, acc[2]); acc[3] = fmaf(a0, w0.w, acc[3]);
+                acc[0] = fmaf(a1, w1.x, acc[0]); acc[1] = fmaf(a1, w1.y, acc[1]);
+                acc[2] = fmaf(a1, w1.z, acc[2]); acc[3] = fmaf(a1, w1.w, acc[3]);
+            }
+        }
+    }
+    for (int o = 0; o < nc; ++o) {
+        const float v = (acc[o] + __ldg(bias + o)) * inv_img_range + __ldg(mean + o);
+        if (out) out[((static_cast<long long>(b) * nc + o) * H + y) * W + x] = v;
+        if (out_u8) {
+            const float q = fminf(fmaxf(v * u8_scale, 0.f), 255.f);
+            out_u8[pix * nc + o] = static_cast<uint8_t>(q);   // truncation, as torch .byte()
+        }
+    }
+}
+
+__global__ void quantize_u8_kernel(const float* __restrict__ x, int B, int nc, int H, int W, float u8_scale,
+                                   uint8_t* __restrict__ out) {
+    const long long total = static_cast<long long>(B) * H * W;
+    for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total;
+         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = pix / (H * W);
+        const long long rem = pix - b * H * W;
+        for (int c = 0; c < nc; ++c) {
+            const float q = fminf(fmaxf(__ldg(x + (b * nc + c) * H * W + rem) * u8_scale, 0.f), 255.f);
+            out[pix * nc + c] = static_cast<uint8_t>(q);
+        }
+    }
+}
+
+inline int grid_for(long long work_items, int per_block, int cap = 148 * 16) {
+    long long g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    return static_cast<int>(g < cap ? g : cap);
+}
+inline int check_launch() { return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH; }
+
+}  // namespace
+}  // namespace adsr
+
+using namespace adsr;
+
+extern "C" int adsr_layernorm_rows(const void* in, int64_t ldi, void* out, int64_t ldo, const float* gamma,
+                                   const float* beta, int M, int C, float eps, void* stream) {
+    if (M <= 0) return ADSR_OK;
+    if (C <= 0 || C > 1024 || (ldi % 8) || (ldo % 8) || ldi < C || ldo < ((C + 15) & ~15)) return ADSR_ERR_BAD_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return ADSR_ERR_BAD_ALIGN;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = grid_for(M, 8);
+    auto a = static_cast<const __nv_bfloat16*>(in);
+    auto o = static_cast<__nv_bfloat16*>(out);
+    if (C <= 256) layernorm_rows_kernel<1><<<grid, 256, 0, st>>>(a, ldi, o, ldo, gamma, beta, M, C, eps);
+    else if (C <= 512) layernorm_rows_kernel<2><<<grid, 256, 0, st>>>(a, ldi, o, ldo, gamma, beta, M, C, eps);
+    else layernorm_rows_kernel<4><<<grid, 256, 0, st>>>(a, ldi, o, ldo, gamma, beta, M, C, eps);
+    return check_launch();
+}
+
+extern "C" int adsr_window_index_map(int H, int W, int ws, int shift, int32_t* src_index, int32_t* region_id, void* stream) {
+    if (ws <= 0 || H % ws || W % ws || shift < 0 || shift >= ws) return ADSR_ERR_BAD_SHAPE;
+    window_index_map_kernel<<<grid_for(static_cast<long long>(H) * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        H, W, ws, shift, src_index, region_id);
+    return check_launch();
+}
+
+extern "C" int adsr_ln_shift_partition(const void* x, int64_t ldx, void* windows, int64_t ldw, const float* gamma,
+                                       const float* beta, float eps, int B, int H, int W, int C, int ws, int shift,
+                                       void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (ws <= 0 || H % ws || W % ws || shift < 0 || shift >= ws) return ADSR_ERR_BAD_SHAPE;
+    if (C <= 0 || C > 1024 || (ldx % 8) || (ldw % 8) || ldx < C || ldw < ((C + 15) & ~15)) return ADSR_ERR_BAD_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(windows) & 15)) return ADSR_ERR_BAD_ALIGN;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = grid_for(static_cast<long long>(B) * H * W, 8);
+    auto a = static_cast<const __nv_bfloat16*>(x);
+    auto o = static_cast<__nv_bfloat16*>(windows);
+    if (C <= 256) ln_shift_partition_kernel<1><<<grid, 256, 0, st>>>(a, ldx, o, ldw, gamma, beta, eps, B, H, W, C, ws, shift);
+    else if (C <= 512) ln_shift_partition_kernel<2><<<grid, 256, 0, st>>>(a, ldx, o, ldw, gamma, beta, eps, B, H, W, C, ws, shift);
+    else ln_shift_partition_kernel<4><<<grid, 256, 0, st>>>(a, ldx, o, ldw, gamma, beta, eps, B, H, W, C, ws, shift);
+    return check_launch();
+}
+
+extern "C" int adsr_window_reverse_unshift(const void* windows, int64_t ldw, void* x, int64_t ldx, int B, int H, int W,
+                                           int C, int ws, int shift, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (ws <= 0 || H % ws || W % ws || shift < 0 || shift >= ws || (C % 4) || (ldw % 4) || (ldx % 4)) return ADSR_ERR_BAD_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(x) & 7) || (reinterpret_cast<uintptr_t>(windows) & 7)) return ADSR_ERR_BAD_ALIGN;
+    const long long items = static_cast<long long>(B) * H * W * (C / 4);
+    window_reverse_unshift_kernel<<<grid_for(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(windows), ldw, static_cast<__nv_bfloat16*>(x), ldx, B, H, W, C, ws, shift);
+    return check_launch();
+}
+
+extern "C" int adsr_drct_head(const float* x_nchw, int B, int nc, int H, int W, const float* weight, const float* bias,
+                              const float* mean, float img_range, const float* ln_gamma, const float* ln_beta, float eps,
+                              int C, void* x0, int64_t ld0, void* slab, int64_t lds, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (nc < 1 || nc > 3 || C <= 0 || C > 256) return ADSR_ERR_BAD_SHAPE;
+    const int cpad = (C + 15) & ~15;
+    if (ld0 < cpad || lds < cpad) return ADSR_ERR_BAD_SHAPE;
+    const size_t smem = (static_cast<size_t>(C) * nc * 9 + 3 * C) * sizeof(float);
+    if (smem > 48 * 1024) return ADSR_ERR_BAD_SHAPE;
+    drct_head_kernel<<<grid_for(static_cast<long long>(B) * H * W, 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        x_nchw, B, nc, H, W, weight, bias, mean, img_range, ln_gamma, ln_beta, eps, C, static_cast<__nv_bfloat16*>(x0), ld0,
+        static_cast<__nv_bfloat16*>(slab), lds);
+    return check_launch();
+}
+
+extern "C" int adsr_conv_last_quant(const void* in, int64_t ld_in, int B, int H, int W, int Cin, const float* weight,
+                                    const float* bias, int nc, const float* mean, float img_range, float rgb_range,
+                                    float* out_nchw, uint8_t* out_u8_hwc, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (nc < 1 || nc > 4 || Cin <= 0 || (Cin % 8) || (ld_in % 8)) return ADSR_ERR_BAD_SHAPE;
+    if (reinterpret_cast<uintptr_t>(in) & 15) return ADSR_ERR_BAD_ALIGN;
+    const size_t smem = static_cast<size_t>(9) * Cin * 4 * sizeof(float);
+    if (smem > 48 * 1024) return ADSR_ERR_BAD_SHAPE;
+    const long long total = static_cast<long long>(B) * H * W;
+    const int grid = static_cast<int>((total + 127) / 128);
+    conv_last_quant_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), ld_in, B, H, W, Cin, weight, bias, nc, mean, 1.0f / img_range,
+        static_cast<float>(255.0 / static_cast<double>(rgb_range)), out_nchw, out_u8_hwc);
+    return check_launch();
+}
+
+extern "C" int adsr_quantize_u8(const float* x_nchw, int B, int nc, int H, int W, float rgb_range, uint8_t* out_u8_hwc,
+                                void* stream) {
+    if (B <= 0) return ADSR_OK;
+    quantize_u8_kernel<<<grid_for(static_cast<long long>(B) * H * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_nchw, B, nc, H, W, static_cast<float>(255.0 / static_cast<double>(rgb_range)), out_u8_hwc);
+    return check_launch();
+}

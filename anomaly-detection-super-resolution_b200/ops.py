@@ -1,0 +1,140 @@
+"""Thin torch-tensor wrappers over the C ABI (one Python function per entry point).
+
+Tensors are only carriers of device memory; every function enqueues exactly one kernel on the
+current CUDA stream and returns immediately.  `LAUNCHES` counts kernels launched through this
+module (bench.py reports it as `gpu_launches`).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _abi
+from ._abi import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, OUT_PIXEL_SHUFFLE2, OUT_ROWS, check, lib, ptr, stream_ptr
+from .pack import PackedWeight
+
+LAUNCHES = 0
+
+
+def _count() -> None:
+    global LAUNCHES
+    LAUNCHES += 1
+
+
+def _cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: this package has no CPU fallback")
+
+
+def tc_gemm(a: torch.Tensor, k: int, w: PackedWeight, out: torch.Tensor, *, act: int = ACT_NONE, slope: float = 0.0,
+            alpha: float = 1.0, res: Optional[torch.Tensor] = None, ocol0: int = 0, n_store: Optional[int] = None,
+            m: Optional[int] = None) -> None:
+    """out[:, ocol0:ocol0+n_store] = alpha * act(a[:, :k] @ W^T + b) (+ res[:, :N])."""
+    _cuda(a, "a")
+    m = a.shape[0] if m is None else m
+    n_store = (w.N + 15) // 16 * 16 if n_store is None else n_store
+    check(lib().adsr_tc_gemm_bf16(ptr(a), a.stride(0), m, k, ptr(w.data), ptr(w.bias), w.N, w.BN, w.n_tiles, act, slope,
+                                  alpha, ptr(res), res.stride(0) if res is not None else 0, ptr(out), out.stride(0), ocol0,
+                                  n_store, _abi.num_sms(), stream_ptr()), "adsr_tc_gemm_bf16")
+    _count()
+
+
+def conv3x3(x: torch.Tensor, b: int, h: int, wd: int, cin: int, w: PackedWeight, out: torch.Tensor, *, stride: int = 1,
+            act: int = ACT_NONE, slope: float = 0.0, alpha: float = 1.0, res: Optional[torch.Tensor] = None,
+            out_mode: int = OUT_ROWS, n_store: Optional[int] = None) -> None:
+    """x: [b*h*wd, ld] NHWC bf16 -> out rows (b*ho*wo) or pixel-shuffled [b, 2h, 2w, N/4]."""
+    _cuda(x, "x")
+    n_store = (w.N + 15) // 16 * 16 if n_store is None else n_store
+    check(lib().adsr_conv3x3_igemm_bf16(ptr(x), x.stride(0), b, h, wd, cin, stride, ptr(w.data), ptr(w.bias), w.N, w.BN,
+                                        w.n_tiles, act, slope, alpha, ptr(res), res.stride(0) if res is not None else 0,
+                                        ptr(out), out.stride(0), out_mode, n_store, _abi.num_sms(), stream_ptr()),
+          "adsr_conv3x3_igemm_bf16")
+    _count()
+
+
+def layernorm_rows(x: torch.Tensor, out: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, c: int, eps: float = 1e-5,
+                   m: Optional[int] = None) -> None:
+    _cuda(x, "x")
+    m = x.shape[0] if m is None else m
+    check(lib().adsr_layernorm_rows(ptr(x), x.stride(0), ptr(out), out.stride(0), ptr(gamma), ptr(beta), m, c, eps,
+                                    stream_ptr()), "adsr_layernorm_rows")
+    _count()
+
+
+def window_attention(qkv: torch.Tensor, out: torch.Tensor, table: torch.Tensor, b: int, h: int, w: int, ws: int,
+                     shift: int, heads: int, hd: int, hdp: int) -> None:
+    _cuda(qkv, "qkv")
+    check(lib().adsr_window_attention(ptr(qkv), qkv.stride(0), ptr(out), out.stride(0), ptr(table), b, h, w, ws, shift,
+                                      heads, hd, hdp, stream_ptr()), "adsr_window_attention")
+    _count()
+
+
+def window_index_map(h: int, w: int, ws: int, shift: int, device) -> tuple[torch.Tensor, torch.Tensor]:
+    n = (h // ws) * (w // ws) * ws * ws
+    src = torch.empty(n, dtype=torch.int32, device=device)
+    reg = torch.empty(n, dtype=torch.int32, device=device)
+    check(lib().adsr_window_index_map(h, w, ws, shift, ptr(src), ptr(reg), stream_ptr()), "adsr_window_index_map")
+    _count()
+    return src, reg
+
+
+def ln_shift_partition(x: torch.Tensor, windows: torch.Tensor, gamma, beta, b, h, w, c, ws, shift, eps=1e-5) -> None:
+    _cuda(x, "x")
+    check(lib().adsr_ln_shift_partition(ptr(x), x.stride(0), ptr(windows), windows.stride(0), ptr(gamma), ptr(beta), eps, b,
+                                        h, w, c, ws, shift, stream_ptr()), "adsr_ln_shift_partition")
+    _count()
+
+
+def window_reverse_unshift(windows: torch.Tensor, x: torch.Tensor, b, h, w, c, ws, shift) -> None:
+    _cuda(x, "x")
+    check(lib().adsr_window_reverse_unshift(ptr(windows), windows.stride(0), ptr(x), x.stride(0), b, h, w, c, ws, shift,
+                                            stream_ptr()), "adsr_window_reverse_unshift")
+    _count()
+
+
+def drct_head(x: torch.Tensor, weight, bias, mean, img_range: float, gamma, beta, c: int, x0: torch.Tensor,
+              slab: torch.Tensor, eps: float = 1e-5) -> None:
+    _cuda(x, "x")
+    b, nc, h, w = x.shape
+    check(lib().adsr_drct_head(ptr(x), b, nc, h, w, ptr(weight), ptr(bias), ptr(mean), img_range, ptr(gamma), ptr(beta), eps,
+                               c, ptr(x0), x0.stride(0), ptr(slab), slab.stride(0), stream_ptr()), "adsr_drct_head")
+    _count()
+
+
+def conv_last_quant(x: torch.Tensor, b: int, h: int, w: int, cin: int, weight, bias, nc: int, mean, img_range: float,
+                    rgb_range: float, out: Optional[torch.Tensor], out_u8: Optional[torch.Tensor]) -> None:
+    _cuda(x, "x")
+    check(lib().adsr_conv_last_quant(ptr(x), x.stride(0), b, h, w, cin, ptr(weight), ptr(bias), nc, ptr(mean), img_range,
+                                     rgb_range, ptr(out), ptr(out_u8), stream_ptr()), "adsr_conv_last_quant")
+    _count()
+
+
+def quantize_u8(x: torch.Tensor, rgb_range: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 NCHW in [0, rgb_range] -> uint8 NHWC, truncating (src/evaluate.py:214-215)."""
+    _cuda(x, "x")
+    x = x.contiguous().float()
+    b, nc, h, w = x.shape
+    if out is None:
+        out = torch.empty(b, h, w, nc, dtype=torch.uint8, device=x.device)
+    check(lib().adsr_quantize_u8(ptr(x), b, nc, h, w, rgb_range, ptr(out), stream_ptr()), "adsr_quantize_u8")
+    _count()
+    return out
+
+
+def score_images(sr_u8: torch.Tensor, hr_u8: torch.Tensor, window_sizes: Sequence[int],
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 NHWC pairs -> fp64 [B, n_ws + 2] = SSIM per window size, MSE, PSNR."""
+    _cuda(sr_u8, "sr_u8")
+    assert sr_u8.shape == hr_u8.shape and sr_u8.dtype == torch.uint8 and hr_u8.dtype == torch.uint8
+    sr_u8, hr_u8 = sr_u8.contiguous(), hr_u8.contiguous()
+    b, h, w, c = sr_u8.shape
+    n_ws = len(window_sizes)
+    if out is None:
+        out = torch.empty(b, n_ws + 2, dtype=torch.float64, device=sr_u8.device)
+    arr = (ctypes.c_int32 * max(n_ws, 1))(*window_sizes)
+    check(lib().adsr_score_images(ptr(sr_u8), ptr(hr_u8), b, h, w, c, arr, n_ws, ptr(out), stream_ptr()),
+          "adsr_score_images")
+    _count()
+    return out

@@ -1,0 +1,126 @@
+/* adsr_b200 -- C ABI of the B200-native DRCT / DRN super-resolution + anomaly-scoring hot path.
+ *
+ * The reference (Benedict3007/anomaly-detection-super-resolution) has NO FFI / operator layer: its
+ * seams are Python symbols.  Each entry point below therefore cites the reference
+ * Python call site(s) whose device work it replaces.  The Python host side
+ * (anomaly-detection-super-resolution_b200/{drct,drn,metrics,evaluate}.py) binds these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer unless named host_*; bf16 tensors are passed as void*
+ *   - nothing is allocated here: outputs and workspaces are caller-owned
+ *   - `stream` is a cudaStream_t passed as void*; every call only ENQUEUES work on it, never syncs
+ *   - return value: 0 = ok, otherwise one of ADSR_ERR_* (never aborts, never prints)
+ *   - stateless and re-entrant (the only cached state is the per-process max-shared-memory opt-in)
+ *   - activations are token-major ("NHWC") bf16: row m = (b*H + y)*W + x, `ld*` = row pitch in elements
+ */
+#ifndef ADSR_B200_H_
+#define ADSR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADSR_ABI_VERSION 1
+
+#define ADSR_OK 0
+#define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
+#define ADSR_ERR_BAD_ALIGN 2   /* pointer / pitch alignment requirement violated */
+#define ADSR_ERR_LAUNCH 3      /* kernel launch failed (cudaGetLastError) */
+#define ADSR_ERR_CUDA 4        /* a CUDA runtime call failed */
+#define ADSR_ERR_ARCH 5        /* device is not sm_100 */
+
+#define ADSR_ACT_NONE 0
+#define ADSR_ACT_LRELU 1
+#define ADSR_ACT_GELU 2        /* exact erf GELU (nn.GELU default, src/drct.py:175) */
+#define ADSR_ACT_RELU 3
+
+#define ADSR_OUT_ROWS 0            /* out[m*ldo + ocol0 + n] */
+#define ADSR_OUT_PIXEL_SHUFFLE2 1  /* nn.PixelShuffle(2): n = c*4+i*2+j -> out[b,2y+i,2x+j,c] */
+
+int adsr_abi_version(void);
+const char* adsr_status_string(int status);
+/* 0 if the current device is compute capability 10.x, ADSR_ERR_ARCH otherwise; *num_sms receives the SM count */
+int adsr_device_check(int* host_num_sms);
+
+/* ---- tcgen05 GEMM: out = alpha * act(A[M,K] * W^T + bias) + res ------------------------------------
+ * replaces nn.Linear qkv / proj / fc1 / fc2 (src/drct.py:278, 300, 185-188) and the 1x1 `adjust` convs
+ * with their LeakyReLU / 0.2*x5 + x epilogues (src/drct.py:334-374, 389-396).
+ * w_packed / bias_padded come from pack.pack_gemm_weight(): n_tiles tiles of BN rows, K padded to 64. */
+int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K,
+                      const void* w_packed, const float* bias_padded, int N, int BN, int n_tiles,
+                      int act, float slope, float alpha,
+                      const void* res, int64_t ldres,
+                      void* out, int64_t ldo, int ocol0, int n_store,
+                      int num_sms, void* stream);
+
+/* ---- tcgen05 implicit-GEMM 3x3 convolution (pad 1, stride 1|2) on NHWC bf16 -------------------------
+ * replaces conv_after_body / conv_before_upsample(+LeakyReLU) / Upsample convs + nn.PixelShuffle(2)
+ * (src/drct.py:837, 844-845, 702-705, 893-895) and DRN's default_conv / DownBlock convs
+ * (src/drn.py:29-32, 83-119).  out_mode selects plain rows or the fused PixelShuffle(2) store. */
+int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int Hin, int Win, int Cin, int stride,
+                            const void* w_packed, const float* bias_padded, int N, int BN, int n_tiles,
+                            int act, float slope, float alpha,
+                            const void* res, int64_t ldres,
+                            void* out, int64_t ldo, int out_mode, int n_store,
+                            int num_sms, void* stream);
+
+/* ---- LayerNorm over the first C columns of each row (eps, affine); writes round16(C) columns ---------
+ * replaces nn.LayerNorm norm1 / norm2 / final norm (src/drct.py:432, 438, 833, 881). */
+int adsr_layernorm_rows(const void* in, int64_t ldi, void* out, int64_t ldo,
+                        const float* gamma, const float* beta, int M, int C, float eps, void* stream);
+
+/* ---- fused (shifted-)window multi-head attention ------------------------------------------------------
+ * replaces torch.roll + window_partition + WindowAttention.forward (q*scale, q@k^T, +relative position
+ * bias, +shift mask (-100), softmax, @v) + window_reverse + roll back
+ * (src/drct.py:482-505, 193-220, 271-299, 449-470).
+ * qkv: [B*H*W, ldq] with q|k|v blocks of nH heads, each head padded to hdp (multiple of 16) columns;
+ * out: [B*H*W, ldo], head h at column h*hdp, written at the ORIGINAL (un-shifted) token position.
+ * bias_table: fp32 [(2ws-1)^2, nH] = relative_position_bias_table. */
+int adsr_window_attention(const void* qkv, int64_t ldq, void* out, int64_t ldo, const float* bias_table,
+                          int B, int H, int W, int ws, int shift, int nH, int hd, int hdp, void* stream);
+
+/* ---- index maps (bit-exact objects): gather map of roll+partition and region ids of calculate_mask ------
+ * src/drct.py:193-204, 449-463, 482-489.  src_index / region_id: int32 [ (H/ws)*(W/ws) * ws*ws ]. */
+int adsr_window_index_map(int H, int W, int ws, int shift, int32_t* src_index, int32_t* region_id, void* stream);
+
+/* ---- standalone LayerNorm + cyclic shift + window partition, and its inverse (first parity slice) -------
+ * src/drct.py:481-489 and 497-505.  windows: [B*nW*N, ldw]. */
+int adsr_ln_shift_partition(const void* x, int64_t ldx, void* windows, int64_t ldw,
+                            const float* gamma, const float* beta, float eps,
+                            int B, int H, int W, int C, int ws, int shift, void* stream);
+int adsr_window_reverse_unshift(const void* windows, int64_t ldw, void* x, int64_t ldx,
+                                int B, int H, int W, int C, int ws, int shift, void* stream);
+
+/* ---- DRCT head: (x - mean)*img_range -> conv_first 3x3 -> x0 (long skip) and LayerNorm(x0) -> slab -------
+ * src/drct.py:887-892, 650-654 (patch_embed.norm).  x: fp32 NCHW, weights fp32 [C, nc, 3, 3]. */
+int adsr_drct_head(const float* x_nchw, int B, int nc, int H, int W,
+                   const float* weight, const float* bias, const float* mean, float img_range,
+                   const float* ln_gamma, const float* ln_beta, float eps, int C,
+                   void* x0, int64_t ld0, void* slab, int64_t lds, void* stream);
+
+/* ---- DRCT tail: conv_last 3x3 (Cin -> nc) + x/img_range + mean, fused uint8 truncation ------------------
+ * src/drct.py:895-897 and the quantisation of src/evaluate.py:212-215
+ * (u8 = trunc(clamp(sr * 255/rgb_range, 0, 255)), HWC).  Either output pointer may be NULL. */
+int adsr_conv_last_quant(const void* in, int64_t ld_in, int B, int H, int W, int Cin,
+                         const float* weight, const float* bias, int nc, const float* mean, float img_range,
+                         float rgb_range, float* out_nchw, uint8_t* out_u8_hwc, void* stream);
+
+/* ---- uint8 truncation of an fp32 NCHW image batch (HR side of src/evaluate.py:215) ----------------------- */
+int adsr_quantize_u8(const float* x_nchw, int B, int nc, int H, int W, float rgb_range, uint8_t* out_u8_hwc,
+                     void* stream);
+
+/* ---- per-image anomaly scores ---------------------------------------------------------------------------------
+ * replaces ssim_numpy (src/metrics.py:26-67) for every window size of the sweep (src/evaluate.py:233-248),
+ * MSE (src/evaluate.py:259-260) and psnr_numpy (src/metrics.py:15-23) on uint8 HWC pairs.
+ * host_ws_list: int32 [n_ws <= 64] in HOST memory (odd window sizes, ws/2 < min(H,W));
+ * scores: fp64 [B, n_ws + 2] = ssim(ws_0..), mse, psnr (+inf when mse == 0). */
+int adsr_score_images(const uint8_t* sr_u8_hwc, const uint8_t* hr_u8_hwc, int B, int H, int W, int C,
+                      const int32_t* host_ws_list, int n_ws, double* scores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADSR_B200_H_ */

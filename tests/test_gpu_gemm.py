@@ -1,0 +1,126 @@
+"""GPU parity of the tcgen05 GEMM / implicit-GEMM conv kernel against fp32 torch on bf16-rounded inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_common import bf16_round, mod, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _gemm_case(M, K, N, act="none", res=False, alpha=1.0, ocol0=0, n_store=None, seed=0):
+    ops, pack = mod("ops"), mod("pack")
+    torch.manual_seed(seed)
+    lda = (K + 63) // 64 * 64 + 64
+    a = torch.full((M, lda), 9.0, device=DEV, dtype=torch.bfloat16)          # poison beyond K
+    a[:, :K] = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    k8 = (K + 7) // 8 * 8
+    a[:, K:k8] = 3.0                                                          # finite junk in the K tail
+    w = torch.randn(N, K, device=DEV) * 0.1
+    bias = torch.randn(N, device=DEV)
+    pw = pack.pack_gemm_weight(w, bias)
+    ldo = 1024
+    out = torch.full((M, ldo), -7.0, device=DEV, dtype=torch.bfloat16)
+    r = torch.randn(M, 512, device=DEV).to(torch.bfloat16) if res else None
+    code = {"none": ops.ACT_NONE, "gelu": ops.ACT_GELU, "lrelu": ops.ACT_LRELU, "relu": ops.ACT_RELU}[act]
+    ops.tc_gemm(a, K, pw, out, act=code, slope=0.2, alpha=alpha, res=r, ocol0=ocol0, n_store=n_store)
+    torch.cuda.synchronize()
+    v = a[:, :K].float() @ bf16_round(w).t() + bias
+    v = {"none": lambda t: t, "gelu": F.gelu, "lrelu": lambda t: F.leaky_relu(t, 0.2), "relu": F.relu}[act](v) * alpha
+    if res:
+        v = v + r[:, :N].float()
+    ns = (N + 15) // 16 * 16 if n_store is None else n_store
+    got = out[:, ocol0:ocol0 + N].float()
+    err = rel_err(got, v)
+    assert err < 0.012, f"M={M} K={K} N={N} act={act} res={res}: rel err {err}"
+    if ns > N:
+        assert float(out[:, ocol0 + N:ocol0 + ns].float().abs().max()) == 0.0, "padded columns must be exact zeros"
+    assert float((out[:, ocol0 + ns:].float() + 7.0).abs().max()) == 0.0, "wrote past n_store"
+    if ocol0:
+        assert float((out[:, :ocol0].float() + 7.0).abs().max()) == 0.0, "wrote before ocol0"
+
+
+def test_gemm_single_tile_k64():
+    _gemm_case(128, 64, 64)
+
+
+def test_gemm_k16_steps():
+    _gemm_case(128, 16, 16)
+    _gemm_case(128, 48, 32)
+
+
+@pytest.mark.parametrize("K", [180, 212, 244, 276, 308, 488])
+def test_gemm_k_tails(K):
+    _gemm_case(256, K, 192, seed=K)
+
+
+@pytest.mark.parametrize("N", [32, 180, 360, 576, 768, 864, 960])
+def test_gemm_n_tiles(N):
+    _gemm_case(384, 180, N, seed=N)
+
+
+def test_gemm_row_tail_and_many_tiles():
+    _gemm_case(128 * 301 + 77, 212, 424, act="gelu", seed=5)     # > 148 tiles: persistent loop + TMEM double buffer
+
+
+def test_gemm_epilogues():
+    _gemm_case(300, 244, 244, act="none", res=True, seed=6)
+    _gemm_case(300, 308, 180, act="none", res=True, alpha=0.2, seed=7)
+    _gemm_case(300, 180, 32, act="lrelu", ocol0=180, n_store=32, seed=8)     # slab slice at an 8-byte aligned column
+    _gemm_case(300, 276, 276, act="relu", seed=9)
+
+
+def _conv_case(B, H, W, Cin, Cout, stride=1, act="none", res=False, ps=False, seed=0):
+    ops, pack = mod("ops"), mod("pack")
+    torch.manual_seed(seed)
+    ld = (Cin + 15) // 16 * 16
+    x = torch.zeros(B * H * W, ld, device=DEV, dtype=torch.bfloat16)
+    x[:, :Cin] = torch.randn(B * H * W, Cin, device=DEV).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV) * 0.05
+    bias = torch.randn(Cout, device=DEV)
+    pw = pack.pack_conv3x3_weight(w, bias)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    xin = x[:, :Cin].float().view(B, H, W, Cin).permute(0, 3, 1, 2)
+    want = F.conv2d(xin, bf16_round(w), bias, stride=stride, padding=1)
+    code = {"none": ops.ACT_NONE, "lrelu": ops.ACT_LRELU}[act]
+    if act == "lrelu":
+        want = F.leaky_relu(want, 0.01)
+    r = None
+    if res:
+        r = torch.randn(B * Ho * Wo, (Cout + 15) // 16 * 16, device=DEV).to(torch.bfloat16)
+        want = want + r[:, :Cout].float().view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
+    if ps:
+        want = F.pixel_shuffle(want, 2)
+        out = torch.zeros(B * 4 * Ho * Wo, Cout // 4, device=DEV, dtype=torch.bfloat16)
+        ops.conv3x3(x, B, H, W, Cin, pw, out, out_mode=ops.OUT_PIXEL_SHUFFLE2)
+        got = out.float().view(B, 2 * Ho, 2 * Wo, Cout // 4).permute(0, 3, 1, 2)
+    else:
+        out = torch.zeros(B * Ho * Wo, (Cout + 15) // 16 * 16, device=DEV, dtype=torch.bfloat16)
+        ops.conv3x3(x, B, H, W, Cin, pw, out, stride=stride, act=code, slope=0.01, res=r)
+        got = out[:, :Cout].float().view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    err = rel_err(got, want)
+    assert err < 0.012, f"conv B={B} H={H} Cin={Cin} Cout={Cout} s={stride} ps={ps}: rel err {err}"
+
+
+def test_conv_64_to_64():
+    _conv_case(1, 16, 16, 64, 64)
+
+
+def test_conv_after_body_shape():
+    _conv_case(2, 32, 32, 180, 180, res=True, seed=1)
+
+
+def test_conv_before_upsample_shape():
+    _conv_case(2, 32, 32, 180, 64, act="lrelu", seed=2)
+
+
+def test_conv_upsample_pixelshuffle():
+    _conv_case(2, 32, 32, 64, 256, ps=True, seed=3)
+    _conv_case(1, 64, 64, 64, 256, ps=True, seed=4)
+
+
+def test_conv_stride2_and_odd_sizes():
+    _conv_case(2, 32, 32, 80, 80, stride=2, seed=5)
+    _conv_case(3, 20, 12, 16, 32, seed=6)        # M not a multiple of 128, tiles straddle images
