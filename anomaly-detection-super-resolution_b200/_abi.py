@@ -42,6 +42,9 @@ _SIGNATURES = {
     "adsr_quantize_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "adsr_score_images": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int32), c_int, c_void_p,
                                   c_void_p]),
+    "adsr_score_images_strided": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_int64),
+                                          POINTER(c_int64), c_float, c_int, c_int, c_double, c_double, c_double,
+                                          POINTER(c_int32), c_int, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -28,64 +28,94 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {        // np.pad(mode
     return i;
 }
 
-// gray value in [0,1] exactly as the reference builds it: u8 -> fp32 / 255, then dot with the fp32
-// (65.738, 129.057, 25.064)/256 coefficients (src/metrics.py:37-39); single channel: value / 255.
-__device__ __forceinline__ float gray01(const uint8_t* __restrict__ px, int C) {
-    if (C == 1) return static_cast<float>(px[0]) / 255.0f;
+// How a pixel is fetched.  Element strides let one kernel serve uint8 HWC (the evaluator), fp32 HWC
+// (generic ssim_numpy / psnr_numpy callers) and cropped fp32 NCHW views (psnr_torch / ssim_torch).
+struct PixelView {
+    const void* base;
+    long long sb, sr, sc, sch;   // element strides: image, row, column, channel
+    int is_f32;                  // 0 = uint8, 1 = float
+    float div;                   // value / div  (255 for uint8 -> [0,1]; rgb_range for ssim_torch; 1 otherwise)
+    int clamp01;                 // clamp to [0,1] after the division (ssim_torch, src/metrics.py:86-87)
+};
+
+__device__ __forceinline__ float fetch(const PixelView& v, long long off) {
+    float x = v.is_f32 ? __ldg(static_cast<const float*>(v.base) + off)
+                       : static_cast<float>(__ldg(static_cast<const uint8_t*>(v.base) + off));
+    if (v.div != 1.0f) x = x / v.div;
+    if (v.clamp01) x = fminf(fmaxf(x, 0.f), 1.f);
+    return x;
+}
+
+// gray value exactly as the reference builds it: channels dotted with the fp32
+// (65.738, 129.057, 25.064)/256 coefficients (src/metrics.py:37-39, :93-96); single channel: as is.
+__device__ __forceinline__ float gray_at(const PixelView& v, long long off, int C) {
+    if (C == 1) return fetch(v, off);
     const float c0 = 65.738f / 256.0f, c1 = 129.057f / 256.0f, c2 = 25.064f / 256.0f;
-    const float r = static_cast<float>(px[0]) / 255.0f, g = static_cast<float>(px[1]) / 255.0f,
-                b = static_cast<float>(px[2]) / 255.0f;
+    const float r = fetch(v, off), g = fetch(v, off + v.sch), b = fetch(v, off + 2 * v.sch);
     return fmaf(b, c2, fmaf(g, c1, r * c0));
 }
 
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 
-__global__ void __launch_bounds__(1024) score_images_kernel(const uint8_t* __restrict__ sr, const uint8_t* __restrict__ hr,
-                                                             int H, int W, int C, WsList wl, int n_ws,
-                                                             double* __restrict__ scores) {
+struct ScoreParams {
+    PixelView sr, hr;
+    int H, W, C, n_ws;
+    int zero_pad;               // 0 = np.pad(mode="reflect") (ssim_numpy), 1 = zero padding (F.conv2d, ssim_torch)
+    double C1, C2, psnr_peak2;  // SSIM constants and data_range^2 of the PSNR
+    double* scores;
+    WsList wl;
+};
+
+__global__ void __launch_bounds__(1024) score_images_kernel(const ScoreParams p) {
+    const int H = p.H, W = p.W, C = p.C, n_ws = p.n_ws;
+    double* __restrict__ scores = p.scores;
     extern __shared__ double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int b = blockIdx.y, j = blockIdx.x;
-    const uint8_t* srb = sr + static_cast<long long>(b) * H * W * C;
-    const uint8_t* hrb = hr + static_cast<long long>(b) * H * W * C;
+    const long long srb = static_cast<long long>(b) * p.sr.sb, hrb = static_cast<long long>(b) * p.hr.sb;
     double* red = sm;                                   // [32] block reduction scratch
 
     if (j == n_ws) {
         // ---------------- MSE / PSNR over all pixels and channels of u8/255 images ---------------
         const long long n = static_cast<long long>(H) * W * C;
-        unsigned long long acc = 0;
+        double acc = 0.0;
         for (long long i = tid; i < n; i += blockDim.x) {
-            const int d = static_cast<int>(srb[i]) - static_cast<int>(hrb[i]);
-            acc += static_cast<unsigned long long>(d * d);
+            const int ch = static_cast<int>(i % C);
+            const long long px = i / C;
+            const int r = static_cast<int>(px / W), c = static_cast<int>(px - static_cast<long long>(r) * W);
+            const float d = fetch(p.sr, srb + r * p.sr.sr + c * p.sr.sc + ch * p.sr.sch) -
+                            fetch(p.hr, hrb + r * p.hr.sr + c * p.hr.sc + ch * p.hr.sch);
+            acc += static_cast<double>(d * d);          // (ref - out) ** 2 on float32 arrays
         }
-        double v = static_cast<double>(acc);
+        double v = acc;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) red[warp] = v;
         __syncthreads();
         if (tid == 0) {
             double t = 0;
             for (int w = 0; w < nwarps; ++w) t += red[w];
-            const double mse = t / (65025.0 * static_cast<double>(n));
+            const double mse = t / static_cast<double>(n);
             scores[static_cast<long long>(b) * (n_ws + 2) + n_ws] = mse;
             scores[static_cast<long long>(b) * (n_ws + 2) + n_ws + 1] =
-                mse == 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : 10.0 * log10(1.0 / mse);
+                mse == 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : 10.0 * log10(p.psnr_peak2 / mse);
         }
         return;
     }
 
     // ---------------- SSIM for window size ws --------------------------------------------------
-    const int ws = wl.ws[j], pad = ws / 2;
+    const int ws = p.wl.ws[j], pad = ws / 2;
     const int col = tid;                                 // one column per thread (blockDim.x >= W)
     const bool active = col < W;
     double* wtot = sm + 32;                              // [2][5][32] per-warp totals (double buffered)
     double* pref = wtot + 2 * 5 * 32;                    // [2][5][W + 1] prefix sums (double buffered)
     const double inv_n = 1.0 / (static_cast<double>(ws) * ws);
-    const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03;
+    const double C1 = p.C1, C2 = p.C2;
+    const bool zp = p.zero_pad != 0;
 
     double v[5] = {0, 0, 0, 0, 0};
     auto add_row = [&](int r, double sign) {
-        const long long off = (static_cast<long long>(r) * W + col) * C;
-        const float x = gray01(hrb + off, C), y = gray01(srb + off, C);      // x = reference (HR), y = SR
+        const float x = gray_at(p.hr, hrb + r * p.hr.sr + col * p.hr.sc, C);   // x = reference (HR)
+        const float y = gray_at(p.sr, srb + r * p.sr.sr + col * p.sr.sc, C);   // y = SR
         v[0] += sign * static_cast<double>(x);
         v[1] += sign * static_cast<double>(y);
         v[2] += sign * static_cast<double>(x * x);      // products are formed in fp32 like `ref * ref`
@@ -93,14 +123,22 @@ __global__ void __launch_bounds__(1024) score_images_kernel(const uint8_t* __res
         v[4] += sign * static_cast<double>(x * y);
     };
     if (active)
-        for (int r = -pad; r <= pad; ++r) add_row(reflect_idx(r, H), 1.0);
+        for (int r = -pad; r <= pad; ++r) {
+            if (zp) { if (r >= 0 && r < H) add_row(r, 1.0); }
+            else add_row(reflect_idx(r, H), 1.0);
+        }
 
     double acc = 0.0;
     for (int i = 0; i < H; ++i) {
         const int bufi = i & 1;
         if (i > 0 && active) {
-            add_row(reflect_idx(i + pad, H), 1.0);
-            add_row(reflect_idx(i - pad - 1, H), -1.0);
+            if (zp) {
+                if (i + pad < H) add_row(i + pad, 1.0);
+                if (i - pad - 1 >= 0) add_row(i - pad - 1, -1.0);
+            } else {
+                add_row(reflect_idx(i + pad, H), 1.0);
+                add_row(reflect_idx(i - pad - 1, H), -1.0);
+            }
         }
         // inclusive scan of the 5 column sums across the row
         double s[5];
@@ -133,8 +171,10 @@ __global__ void __launch_bounds__(1024) score_images_kernel(const uint8_t* __res
             for (int q = 0; q < 5; ++q) {
                 const double* Pq = P + q * (W + 1);
                 double t = Pq[a1 + 1] - Pq[a0];
-                if (lo < 0) t += Pq[-lo + 1] - Pq[1];                       // reflected columns 1 .. -lo
-                if (hi > W - 1) t += Pq[W - 1] - Pq[2 * (W - 1) - hi];      // reflected columns 2(W-1)-hi .. W-2
+                if (!zp) {
+                    if (lo < 0) t += Pq[-lo + 1] - Pq[1];                       // reflected columns 1 .. -lo
+                    if (hi > W - 1) t += Pq[W - 1] - Pq[2 * (W - 1) - hi];      // reflected columns 2(W-1)-hi .. W-2
+                }
                 box[q] = t * inv_n;
             }
             const double mu1 = box[0], mu2 = box[1];
@@ -156,25 +196,53 @@ __global__ void __launch_bounds__(1024) score_images_kernel(const uint8_t* __res
 }  // namespace
 }  // namespace adsr
 
-extern "C" int adsr_score_images(const uint8_t* sr_u8_hwc, const uint8_t* hr_u8_hwc, int B, int H, int W, int C,
-                                 const int32_t* host_ws_list, int n_ws, double* scores, void* stream) {
+namespace {
+int launch_score(adsr::ScoreParams& p, int B, const int32_t* host_ws_list, int n_ws, cudaStream_t st) {
     using namespace adsr;
     if (B <= 0) return ADSR_OK;
-    if (n_ws < 0 || n_ws > kMaxWs || (C != 1 && C != 3) || W > 1024 || W < 2 || H < 2) return ADSR_ERR_BAD_SHAPE;
-    WsList wl;
-    for (int i = 0; i < kMaxWs; ++i) wl.ws[i] = 1;
+    if (n_ws < 0 || n_ws > kMaxWs || (p.C != 1 && p.C != 3) || p.W > 1024 || p.W < 2 || p.H < 2) return ADSR_ERR_BAD_SHAPE;
+    for (int i = 0; i < kMaxWs; ++i) p.wl.ws[i] = 1;
     for (int i = 0; i < n_ws; ++i) {
         const int ws = host_ws_list[i];
-        if (ws < 1 || (ws % 2) == 0 || ws / 2 >= H || ws / 2 >= W) return ADSR_ERR_BAD_SHAPE;
-        wl.ws[i] = ws;
+        if (ws < 1 || (ws % 2) == 0 || ws / 2 >= p.H || ws / 2 >= p.W) return ADSR_ERR_BAD_SHAPE;
+        p.wl.ws[i] = ws;
     }
-    const int threads = ((W + 31) / 32) * 32;
-    const size_t smem = (32 + 2 * 5 * 32 + 2 * 5 * static_cast<size_t>(W + 1)) * sizeof(double);
+    p.n_ws = n_ws;
+    const int threads = ((p.W + 31) / 32) * 32;
+    const size_t smem = (32 + 2 * 5 * 32 + 2 * 5 * static_cast<size_t>(p.W + 1)) * sizeof(double);
     if (smem > 48 * 1024) {
         if (cudaFuncSetAttribute(score_images_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
             return ADSR_ERR_CUDA;
     }
     dim3 grid(n_ws + 1, B);
-    score_images_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(sr_u8_hwc, hr_u8_hwc, H, W, C, wl, n_ws, scores);
+    score_images_kernel<<<grid, threads, smem, st>>>(p);
     return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
+}
+}  // namespace
+
+extern "C" int adsr_score_images(const uint8_t* sr_u8_hwc, const uint8_t* hr_u8_hwc, int B, int H, int W, int C,
+                                 const int32_t* host_ws_list, int n_ws, double* scores, void* stream) {
+    adsr::ScoreParams p{};
+    const long long sb = static_cast<long long>(H) * W * C;
+    p.sr = {sr_u8_hwc, sb, static_cast<long long>(W) * C, C, 1, 0, 255.0f, 0};
+    p.hr = {hr_u8_hwc, sb, static_cast<long long>(W) * C, C, 1, 0, 255.0f, 0};
+    p.H = H; p.W = W; p.C = C;
+    p.zero_pad = 0;
+    p.C1 = 0.01 * 0.01; p.C2 = 0.03 * 0.03; p.psnr_peak2 = 1.0;
+    p.scores = scores;
+    return launch_score(p, B, host_ws_list, n_ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int adsr_score_images_strided(const void* sr, const void* hr, int is_f32, int B, int H, int W, int C,
+                                         const int64_t* host_strides_sr, const int64_t* host_strides_hr, float div,
+                                         int clamp01, int zero_pad, double c1, double c2, double psnr_peak,
+                                         const int32_t* host_ws_list, int n_ws, double* scores, void* stream) {
+    adsr::ScoreParams p{};
+    p.sr = {sr, host_strides_sr[0], host_strides_sr[1], host_strides_sr[2], host_strides_sr[3], is_f32, div, clamp01};
+    p.hr = {hr, host_strides_hr[0], host_strides_hr[1], host_strides_hr[2], host_strides_hr[3], is_f32, div, clamp01};
+    p.H = H; p.W = W; p.C = C;
+    p.zero_pad = zero_pad;
+    p.C1 = c1; p.C2 = c2; p.psnr_peak2 = psnr_peak * psnr_peak;
+    p.scores = scores;
+    return launch_score(p, B, host_ws_list, n_ws, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,326 @@
+"""Drop-in for the reference's `src.evaluate` (/root/reference/src/evaluate.py): same CLI flags, same
+`evaluate_on_test(opt, checkpoint_model_path, output_dir, save_images)` entry point and the same final line
+`Test AUCs - SSIM(best ws=..): .., MSE: .., PSNR: ..` -- but batched and on the GPU end to end:
+
+  reference (src/evaluate.py:204-265)                    here
+  ----------------------------------------------------   ---------------------------------------------------
+  batch_size forced to 1, one D2H copy per image          images run in batches (--batch-size, default 64)
+  SR -> uint8 via 5 tiny kernels + numpy                  truncation fused into the SR model's last kernel
+  ssim_numpy Python loop, 14 calls per image (~12 s)      ONE scoring launch per batch: all window sizes + MSE + PSNR
+  roc_auc_score on the host                               unchanged (N_img scalars), after an all_gather when sharded
+
+Deviation (documented in DESIGN.md): the model runs with evaluation semantics (DropPath off); the reference
+never calls model.eval() on this path, which makes its AUC nondeterministic.
+With --workers / torchrun the images shard by index across ranks and only the [n_img, n_ws+2] score
+table is gathered (NCCL), as SURVEY.md section 8e prescribes.
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import os
+import re
+import sys
+from pathlib import Path
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import metrics, ops
+from .main import DRCT as DRCTOpt
+from .main import DRN as DRNOpt
+from .main import setup_opt_drct, setup_opt_drn
+
+
+# ------------------------------------------------------------------------------------------ CLI (src/evaluate.py:20-45)
+def parse_args(argv=None):
+    pre = argparse.ArgumentParser(add_help=False)
+    pre.add_argument('--config', type=str, default=None)
+    pre_args, _ = pre.parse_known_args(argv)
+    p = argparse.ArgumentParser(description='Evaluation entrypoint', parents=[pre])
+    p.add_argument('--model-type', type=str, default='drct', choices=['drct', 'drn-l'])
+    p.add_argument('--dataset', type=str, default='mvtec', choices=['mvtec'])
+    p.add_argument('--classe', type=str, default='grid')
+    p.add_argument('--scale', type=int, default=4)
+    p.add_argument('--resolution', type=int, default=128)
+    p.add_argument('--device', type=str, default='auto', choices=['auto', 'cuda', 'mps', 'cpu'])
+    p.add_argument('--data-root', type=str, default='auto')
+    p.add_argument('--run-dir', type=str, default='')
+    p.add_argument('--checkpoint', type=str, default='')
+    p.add_argument('--batch-size', type=int, default=64)
+    p.add_argument('--output-dir', type=str, default='')
+    p.add_argument('--save-images', action='store_true', default=True)
+    p.add_argument('--workers', type=int, default=0 if sys.platform == 'darwin' else 4)
+    if pre_args.config and os.path.isfile(pre_args.config):
+        import yaml
+
+        with open(pre_args.config, 'r') as f:
+            cfg = yaml.safe_load(f) or {}
+        p.set_defaults(**{k.replace('-', '_'): v for k, v in cfg.items()})
+    return p.parse_args(argv)
+
+
+def infer_from_run_dir(run_dir: str):
+    """src/evaluate.py:48-122: path-name pattern first, then config.txt overrides."""
+    result = {'model_type': None, 'dataset': None, 'classe': None, 'resolution': None, 'scale': None}
+    for seg in Path(run_dir).parts:
+        if seg in ('drct', 'drn-l'):
+            result['model_type'] = seg
+            break
+    m = re.match(r"(?P<ds>\w+)_(?P<cls>\w+)_(?P<res>\d+)_X(?P<scale>\d+)", Path(run_dir).name)
+    if m:
+        result['dataset'], result['classe'] = m.group('ds'), m.group('cls')
+        result['resolution'], result['scale'] = int(m.group('res')), int(m.group('scale'))
+    cfg_path = Path(run_dir) / 'config.txt'
+    if cfg_path.exists():
+        try:
+            lines = cfg_path.read_text().splitlines()
+
+            def read_val(key):
+                for line in lines:
+                    if line.strip().startswith(f"{key}:"):
+                        return line.split(':', 1)[1].strip()
+                return None
+
+            for key, field in (('model_name', 'model_type'), ('dataset', 'dataset'), ('classe', 'classe')):
+                v = read_val(key)
+                if v:
+                    result[field] = v
+            res = read_val('patch_size')
+            if res and res.isdigit():
+                result['resolution'] = int(res)
+            scale_val = read_val('upscale') or read_val('scale')
+            if scale_val:
+                ms = re.findall(r"\d+", scale_val)
+                if ms:
+                    result['scale'] = int(ms[-1])
+        except Exception:
+            pass
+    return result
+
+
+def resolve_checkpoint(args):
+    if args.checkpoint:
+        return args.checkpoint
+    if args.run_dir:
+        for name in ('model_best.pt', 'model_latest.pt'):
+            cand = os.path.join(args.run_dir, 'model', name)
+            if os.path.isfile(cand):
+                return cand
+    raise FileNotFoundError('Please provide --checkpoint or a valid --run-dir containing model/*.pt')
+
+
+# ------------------------------------------------------------------------------------------ data (src/data.py, test mode)
+def _rgb_to_y(img: np.ndarray) -> np.ndarray:
+    """skimage.color.rgb2ycbcr(img)[..., 0] for uint8 RGB (used by src/data.py:59 when n_colors == 1)."""
+    f = img.astype(np.float64) / 255.0
+    return 16.0 + 65.481 * f[..., 0] + 128.553 * f[..., 1] + 24.966 * f[..., 2]
+
+
+def _set_channel(img: np.ndarray, n_colors: int) -> np.ndarray:
+    if img.ndim == 2:
+        img = img[:, :, None]
+    c = img.shape[2]
+    if n_colors == 1 and c == 3:
+        img = _rgb_to_y(img)[:, :, None]
+    elif n_colors == 3 and c == 1:
+        img = np.concatenate([img] * 3, 2)
+    return img
+
+
+def scan_split(data_dir: str, scale: int) -> Tuple[List[str], List[str]]:
+    """HR/*.png sorted + matching LR file, same candidate order as src/data.py:109-134."""
+    names_hr = sorted(glob.glob(os.path.join(data_dir, 'HR', '*.png')))
+    names_lr = []
+    for f in names_hr:
+        stem = os.path.splitext(os.path.basename(f))[0]
+        cands = [os.path.join(data_dir, 'LR_bicubic', f'X{scale}', f'{stem}x{scale}.png'),
+                 os.path.join(data_dir, f'LR_{scale}', f'{stem}.png'), os.path.join(data_dir, 'LR', f'{stem}.png')]
+        for c in cands:
+            if os.path.exists(c):
+                names_lr.append(c)
+                break
+        else:
+            raise FileNotFoundError(f"LR image not found for {stem} at scale {scale}: tried {', '.join(cands)}")
+    return names_hr, names_lr
+
+
+def load_pair(f_hr: str, f_lr: str, scale: int, n_colors: int, rgb_range: float):
+    """-> (lr [nc,h,w] float32, hr [nc,H,W] float32) in [0, rgb_range] (src/data.py:11-19, 84-92, 176-183)."""
+    from PIL import Image
+
+    hr = _set_channel(np.array(Image.open(f_hr)), n_colors)
+    lr = _set_channel(np.array(Image.open(f_lr)), n_colors)
+    ih, iw = lr.shape[:2]
+    hr = hr[0:ih * scale, 0:iw * scale]
+    to_t = lambda a: torch.from_numpy(np.ascontiguousarray(a.transpose(2, 0, 1))).float().mul_(rgb_range / 255)
+    return to_t(lr), to_t(hr)
+
+
+# ------------------------------------------------------------------------------------------ batched device path
+class BatchedEvaluator:
+    """SR forward + uint8 truncation + per-image scores for batches of (lr, hr) pairs.
+
+    `step(lr, hr)` takes what the reference's loader yields (float tensors in [0, rgb_range], on the host or
+    already on the device) and returns the fp64 score table [B, n_ws + 2] on the device; nothing else leaves
+    the GPU.  Host tensors are copied with non_blocking=True (pin them for overlap)."""
+
+    def __init__(self, model, rgb_range: float, window_sizes: Optional[Sequence[int]] = None):
+        self.model = model
+        self.rgb_range = float(rgb_range)
+        self.window_sizes = list(window_sizes) if window_sizes is not None else None
+        self.device = torch.device('cuda')
+        self.last_sr_u8: Optional[torch.Tensor] = None
+
+    def step(self, lr: torch.Tensor, hr: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        lr_d = lr.to(self.device, non_blocking=True)
+        hr_d = hr.to(self.device, non_blocking=True)
+        if hr_d.dtype == torch.uint8:                         # already quantised NHWC
+            hr_u8 = hr_d
+        else:
+            hr_u8 = ops.quantize_u8(hr_d, self.rgb_range)
+        h, w = hr_u8.shape[1], hr_u8.shape[2]
+        target = self.model.model if hasattr(self.model, 'model') else self.model
+        _, sr_u8 = target.run(lr_d, want_float=False, want_u8=True)
+        if sr_u8.shape[1] != h or sr_u8.shape[2] != w:        # sr = sr[..., :h, :w]  (src/evaluate.py:212-213)
+            sr_u8 = sr_u8[:, :h, :w, :].contiguous()
+        if self.window_sizes is None:
+            self.window_sizes = metrics.window_sizes_for(min(h, w))
+        self.last_sr_u8 = sr_u8
+        return metrics.score_batch(sr_u8, hr_u8, self.window_sizes, out)
+
+
+def _dist_info():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def gather_scores(local_scores: torch.Tensor, local_ids: torch.Tensor, n_total: int) -> Optional[np.ndarray]:
+    """all_gather of the per-rank score rows (NCCL over NVLink when sharded); rank 0 returns the table ordered by
+    image id, other ranks None.  <= 8*(n_ws+2)+8 bytes per image: latency only."""
+    import torch.distributed as dist
+
+    rank, world = _dist_info()
+    if world == 1:
+        out = np.empty((n_total, local_scores.shape[1]), dtype=np.float64)
+        out[local_ids.cpu().numpy()] = local_scores.cpu().numpy()
+        return out
+    n_max = (n_total + world - 1) // world
+    pad = n_max - local_scores.shape[0]
+    s = torch.cat([local_scores, local_scores.new_zeros(pad, local_scores.shape[1])]) if pad else local_scores
+    i = torch.cat([local_ids, local_ids.new_full((pad,), -1)]) if pad else local_ids
+    all_s = [torch.empty_like(s) for _ in range(world)]
+    all_i = [torch.empty_like(i) for _ in range(world)]
+    dist.all_gather(all_s, s.contiguous())
+    dist.all_gather(all_i, i.contiguous())
+    if rank != 0:
+        return None
+    out = np.empty((n_total, local_scores.shape[1]), dtype=np.float64)
+    for ss, ii in zip(all_s, all_i):
+        ii = ii.cpu().numpy()
+        keep = ii >= 0
+        out[ii[keep]] = ss.cpu().numpy()[keep]
+    return out
+
+
+def save_sr_image(sr_u8_hwc: np.ndarray, output_dir: str, name: str, split: str, scale_value: int) -> None:
+    from PIL import Image
+
+    out_dir = Path(output_dir) / split / f"x{scale_value}"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    img = Image.fromarray(sr_u8_hwc[:, :, 0] if sr_u8_hwc.shape[2] == 1 else sr_u8_hwc)
+    img.save(str(out_dir / f"{name}.png"))
+
+
+def evaluate_on_test(opt, checkpoint_model_path, output_dir: str, save_images: bool, batch_size: Optional[int] = None):
+    """src/evaluate.py:138-267 with the loops batched.  Returns dict(best_ws, auc_ssim, auc_mse, auc_psnr, n)."""
+    from .model import Model
+
+    scale = opt.scale[-1] if isinstance(opt.scale, list) else int(opt.scale)
+    rank, world = _dist_info()
+    entries = []                                             # (label, split, hr path, lr path): good first, then bad
+    for label, split in ((0, 'good'), (1, 'bad')):
+        d = f'{opt.data_root}/{opt.classe}/test/{split}'
+        hr_files, lr_files = scan_split(d, scale)
+        entries += [(label, split, h, l) for h, l in zip(hr_files, lr_files)]
+    y_true = [e[0] for e in entries]
+    if len(set(y_true)) < 2:
+        print('Test set lacks both classes; AUC not available')
+        return None
+
+    opt.pre_train = checkpoint_model_path
+    model = Model(opt, None)
+    ev = BatchedEvaluator(model, opt.rgb_range)
+    bs = batch_size or getattr(opt, 'eval_batch_size', None) or 64
+    mine = list(range(rank, len(entries), world))            # image index i -> rank i mod R
+    rows, ids = [], []
+    with torch.no_grad():
+        for s in range(0, len(mine), bs):
+            idx = mine[s:s + bs]
+            pairs = [load_pair(entries[i][2], entries[i][3], scale, opt.n_colors, opt.rgb_range) for i in idx]
+            shapes = {(tuple(p[0].shape), tuple(p[1].shape)) for p in pairs}
+            groups = [list(range(len(idx)))] if len(shapes) == 1 else [[j] for j in range(len(idx))]
+            for g in groups:                                  # mixed sizes fall back to one image per launch
+                lr = torch.stack([pairs[j][0] for j in g]).pin_memory()
+                hr = torch.stack([pairs[j][1] for j in g]).pin_memory()
+                rows.append(ev.step(lr, hr))
+                ids += [idx[j] for j in g]
+                if save_images:
+                    sr_np = ev.last_sr_u8.cpu().numpy()
+                    for k, j in enumerate(g):
+                        name = os.path.splitext(os.path.basename(entries[idx[j]][2]))[0]
+                        save_sr_image(sr_np[k], output_dir, name, entries[idx[j]][1], scale)
+    n_cols = len(ev.window_sizes) + 2 if ev.window_sizes else 3
+    local = torch.cat(rows) if rows else torch.empty(0, n_cols, dtype=torch.float64, device='cuda')
+    table = gather_scores(local, torch.tensor(ids, dtype=torch.int64, device='cuda'), len(entries))
+    if table is None:
+        return None
+    best_ws, auc_ssim, auc_mse, auc_psnr = metrics.aucs_from_scores(y_true, table, ev.window_sizes)
+    print(f"Test AUCs - SSIM(best ws={best_ws}): {auc_ssim:.4f}, MSE: {auc_mse:.4f}, PSNR: {auc_psnr:.4f}")
+    return dict(best_ws=best_ws, auc_ssim=auc_ssim, auc_mse=auc_mse, auc_psnr=auc_psnr, n=len(entries), scores=table)
+
+
+def main(argv=None):
+    """src/evaluate.py:270-344."""
+    args = parse_args(argv)
+    model_type, ds, class_name = args.model_type, args.dataset, args.classe
+    img_resolution, scale = args.resolution, args.scale
+    if args.run_dir:
+        inferred = infer_from_run_dir(args.run_dir)
+        model_type = inferred.get('model_type') or model_type
+        ds = inferred.get('dataset') or ds
+        class_name = inferred.get('classe') or class_name
+        img_resolution = inferred.get('resolution') or img_resolution
+        scale = inferred.get('scale') or scale
+    if args.device in ('cpu', 'mps'):
+        raise RuntimeError(f"--device {args.device}: the B200 build has no CPU/MPS path; use the reference for that")
+    n_colors = 3 if (ds == 'mvtec' and class_name == 'carpet') else 1
+    data_root = args.data_root if args.data_root != 'auto' else f"data/mvtec_{img_resolution}"
+    data_dir = f"{data_root}/{class_name}/train/good"
+    ckpt_path = resolve_checkpoint(args)
+    common = dict(best_auc=0.0, ssim_window_size=11, dataset=ds, classe=class_name, slurm=False, scale=scale,
+                  no_augment=True, n_colors=n_colors, epochs=1, batch_size=args.batch_size, patch_size=img_resolution)
+    if model_type == 'drn-l':
+        opt = setup_opt_drn(DRNOpt(), common['best_auc'], 11, ds, class_name, False, scale, True, n_colors, 1,
+                            args.batch_size, img_resolution, data_dir, './workspace/eval', '', 1, 1, 1, 0.0, args.workers,
+                            ckpt_path, '.', '1*L1')
+    else:
+        opt = setup_opt_drct(DRCTOpt(), common['best_auc'], 11, ds, class_name, False, scale, True, n_colors, 1,
+                             args.batch_size, img_resolution, img_resolution // scale, data_dir, './workspace/eval', '', 1,
+                             1, 1, 0.0, args.workers, ckpt_path, '1*L1')
+    opt.model_name, opt.data_root, opt.test_only = model_type, data_root, True
+    if 'LOCAL_RANK' in os.environ and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+        dist.init_process_group('nccl')
+    out_dir = args.output_dir or (os.path.join(args.run_dir, 'eval_results') if args.run_dir else './workspace/eval_results')
+    return evaluate_on_test(opt, ckpt_path, out_dir, args.save_images, batch_size=args.batch_size)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,11 +16,24 @@ from ._abi import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, OUT_PIXEL_SHUFFLE2, O
 from .pack import PackedWeight
 
 LAUNCHES = 0
+PROFILE = None      # set to a list to collect (kind, algorithmic_flops, start_event, end_event) per launch (bench.py)
 
 
-def _count() -> None:
+def _count(kind: str = "", flops: float = 0.0, start=None) -> None:
     global LAUNCHES
     LAUNCHES += 1
+    if start is not None:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        PROFILE.append((kind, flops, start, end))
+
+
+def _begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
 
 
 def _cuda(t: torch.Tensor, name: str) -> None:
@@ -35,10 +48,11 @@ def tc_gemm(a: torch.Tensor, k: int, w: PackedWeight, out: torch.Tensor, *, act:
     _cuda(a, "a")
     m = a.shape[0] if m is None else m
     n_store = (w.N + 15) // 16 * 16 if n_store is None else n_store
+    _t = _begin()
     check(lib().adsr_tc_gemm_bf16(ptr(a), a.stride(0), m, k, ptr(w.data), ptr(w.bias), w.N, w.BN, w.n_tiles, act, slope,
                                   alpha, ptr(res), res.stride(0) if res is not None else 0, ptr(out), out.stride(0), ocol0,
                                   n_store, _abi.num_sms(), stream_ptr()), "adsr_tc_gemm_bf16")
-    _count()
+    _count("tc_gemm", 2.0 * m * k * w.N, _t)
 
 
 def conv3x3(x: torch.Tensor, b: int, h: int, wd: int, cin: int, w: PackedWeight, out: torch.Tensor, *, stride: int = 1,
@@ -47,68 +61,76 @@ def conv3x3(x: torch.Tensor, b: int, h: int, wd: int, cin: int, w: PackedWeight,
     """x: [b*h*wd, ld] NHWC bf16 -> out rows (b*ho*wo) or pixel-shuffled [b, 2h, 2w, N/4]."""
     _cuda(x, "x")
     n_store = (w.N + 15) // 16 * 16 if n_store is None else n_store
+    _t = _begin()
     check(lib().adsr_conv3x3_igemm_bf16(ptr(x), x.stride(0), b, h, wd, cin, stride, ptr(w.data), ptr(w.bias), w.N, w.BN,
                                         w.n_tiles, act, slope, alpha, ptr(res), res.stride(0) if res is not None else 0,
                                         ptr(out), out.stride(0), out_mode, n_store, _abi.num_sms(), stream_ptr()),
           "adsr_conv3x3_igemm_bf16")
-    _count()
+    _count("conv3x3", 2.0 * b * (-(-h // stride)) * (-(-wd // stride)) * 9 * cin * w.N, _t)
 
 
 def layernorm_rows(x: torch.Tensor, out: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, c: int, eps: float = 1e-5,
                    m: Optional[int] = None) -> None:
     _cuda(x, "x")
     m = x.shape[0] if m is None else m
+    _t = _begin()
     check(lib().adsr_layernorm_rows(ptr(x), x.stride(0), ptr(out), out.stride(0), ptr(gamma), ptr(beta), m, c, eps,
                                     stream_ptr()), "adsr_layernorm_rows")
-    _count()
+    _count("layernorm", 0.0, _t)
 
 
 def window_attention(qkv: torch.Tensor, out: torch.Tensor, table: torch.Tensor, b: int, h: int, w: int, ws: int,
                      shift: int, heads: int, hd: int, hdp: int) -> None:
     _cuda(qkv, "qkv")
+    _t = _begin()
     check(lib().adsr_window_attention(ptr(qkv), qkv.stride(0), ptr(out), out.stride(0), ptr(table), b, h, w, ws, shift,
                                       heads, hd, hdp, stream_ptr()), "adsr_window_attention")
-    _count()
+    _count("window_attention", 4.0 * b * h * w * ws * ws * heads * hd, _t)
 
 
 def window_index_map(h: int, w: int, ws: int, shift: int, device) -> tuple[torch.Tensor, torch.Tensor]:
     n = (h // ws) * (w // ws) * ws * ws
     src = torch.empty(n, dtype=torch.int32, device=device)
     reg = torch.empty(n, dtype=torch.int32, device=device)
+    _t = _begin()
     check(lib().adsr_window_index_map(h, w, ws, shift, ptr(src), ptr(reg), stream_ptr()), "adsr_window_index_map")
-    _count()
+    _count("index_map", 0.0, _t)
     return src, reg
 
 
 def ln_shift_partition(x: torch.Tensor, windows: torch.Tensor, gamma, beta, b, h, w, c, ws, shift, eps=1e-5) -> None:
     _cuda(x, "x")
+    _t = _begin()
     check(lib().adsr_ln_shift_partition(ptr(x), x.stride(0), ptr(windows), windows.stride(0), ptr(gamma), ptr(beta), eps, b,
                                         h, w, c, ws, shift, stream_ptr()), "adsr_ln_shift_partition")
-    _count()
+    _count("ln_shift_partition", 0.0, _t)
 
 
 def window_reverse_unshift(windows: torch.Tensor, x: torch.Tensor, b, h, w, c, ws, shift) -> None:
     _cuda(x, "x")
+    _t = _begin()
     check(lib().adsr_window_reverse_unshift(ptr(windows), windows.stride(0), ptr(x), x.stride(0), b, h, w, c, ws, shift,
                                             stream_ptr()), "adsr_window_reverse_unshift")
-    _count()
+    _count("window_reverse", 0.0, _t)
 
 
 def drct_head(x: torch.Tensor, weight, bias, mean, img_range: float, gamma, beta, c: int, x0: torch.Tensor,
               slab: torch.Tensor, eps: float = 1e-5) -> None:
     _cuda(x, "x")
     b, nc, h, w = x.shape
+    _t = _begin()
     check(lib().adsr_drct_head(ptr(x), b, nc, h, w, ptr(weight), ptr(bias), ptr(mean), img_range, ptr(gamma), ptr(beta), eps,
                                c, ptr(x0), x0.stride(0), ptr(slab), slab.stride(0), stream_ptr()), "adsr_drct_head")
-    _count()
+    _count("drct_head", 2.0 * b * h * w * 9 * nc * c, _t)
 
 
 def conv_last_quant(x: torch.Tensor, b: int, h: int, w: int, cin: int, weight, bias, nc: int, mean, img_range: float,
                     rgb_range: float, out: Optional[torch.Tensor], out_u8: Optional[torch.Tensor]) -> None:
     _cuda(x, "x")
+    _t = _begin()
     check(lib().adsr_conv_last_quant(ptr(x), x.stride(0), b, h, w, cin, ptr(weight), ptr(bias), nc, ptr(mean), img_range,
                                      rgb_range, ptr(out), ptr(out_u8), stream_ptr()), "adsr_conv_last_quant")
-    _count()
+    _count("conv_last", 2.0 * b * h * w * 9 * cin * nc, _t)
 
 
 def quantize_u8(x: torch.Tensor, rgb_range: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -118,8 +140,9 @@ def quantize_u8(x: torch.Tensor, rgb_range: float, out: Optional[torch.Tensor] =
     b, nc, h, w = x.shape
     if out is None:
         out = torch.empty(b, h, w, nc, dtype=torch.uint8, device=x.device)
+    _t = _begin()
     check(lib().adsr_quantize_u8(ptr(x), b, nc, h, w, rgb_range, ptr(out), stream_ptr()), "adsr_quantize_u8")
-    _count()
+    _count("quantize_u8", 0.0, _t)
     return out
 
 
@@ -134,7 +157,33 @@ def score_images(sr_u8: torch.Tensor, hr_u8: torch.Tensor, window_sizes: Sequenc
     if out is None:
         out = torch.empty(b, n_ws + 2, dtype=torch.float64, device=sr_u8.device)
     arr = (ctypes.c_int32 * max(n_ws, 1))(*window_sizes)
+    _t = _begin()
     check(lib().adsr_score_images(ptr(sr_u8), ptr(hr_u8), b, h, w, c, arr, n_ws, ptr(out), stream_ptr()),
           "adsr_score_images")
-    _count()
+    _count("score_images", 0.0, _t)
+    return out
+
+
+def score_images_strided(sr: torch.Tensor, hr: torch.Tensor, layout: str, window_sizes: Sequence[int], *, div: float = 1.0,
+                         clamp01: bool = False, zero_pad: bool = False, c1: float = 1e-4, c2: float = 9e-4,
+                         psnr_peak: float = 1.0) -> torch.Tensor:
+    """Generic scorer behind psnr/ssim_numpy (float or uint8 HWC) and psnr/ssim_torch (fp32 NCHW views).
+    layout: "hwc" -> tensors [B, H, W, C]; "chw" -> [B, C, H, W] (any strides, e.g. a shaved crop)."""
+    _cuda(sr, "sr")
+    assert sr.shape == hr.shape and sr.dtype == hr.dtype and sr.dtype in (torch.uint8, torch.float32)
+    if layout == "hwc":
+        b, h, w, c = sr.shape
+        st = lambda t: (t.stride(0), t.stride(1), t.stride(2), t.stride(3))
+    else:
+        b, c, h, w = sr.shape
+        st = lambda t: (t.stride(0), t.stride(2), t.stride(3), t.stride(1))
+    n_ws = len(window_sizes)
+    out = torch.empty(b, n_ws + 2, dtype=torch.float64, device=sr.device)
+    arr = (ctypes.c_int32 * max(n_ws, 1))(*window_sizes)
+    s_sr, s_hr = (ctypes.c_int64 * 4)(*st(sr)), (ctypes.c_int64 * 4)(*st(hr))
+    _t = _begin()
+    check(lib().adsr_score_images_strided(ptr(sr), ptr(hr), int(sr.dtype == torch.float32), b, h, w, c, s_sr, s_hr, div,
+                                          int(clamp01), int(zero_pad), c1, c2, psnr_peak, arr, n_ws, ptr(out), stream_ptr()),
+          "adsr_score_images_strided")
+    _count("score_images", 0.0, _t)
     return out

@@ -120,6 +120,16 @@ int adsr_quantize_u8(const float* x_nchw, int B, int nc, int H, int W, float rgb
 int adsr_score_images(const uint8_t* sr_u8_hwc, const uint8_t* hr_u8_hwc, int B, int H, int W, int C,
                       const int32_t* host_ws_list, int n_ws, double* scores, void* stream);
 
+/* Same kernel behind the reference's generic metric signatures: psnr_numpy / ssim_numpy on float arrays
+ * (src/metrics.py:15-67) and psnr_torch / ssim_torch (src/metrics.py:70-108: zero-padded box filter, /rgb_range,
+ * clamp, 255^2-scaled constants).  sr/hr: uint8 (is_f32=0) or fp32 (is_f32=1) with element strides
+ * host_strides_* = {image, row, column, channel}; value = clamp?(raw / div); zero_pad selects F.conv2d-style
+ * padding instead of np.pad reflect; c1/c2 are the SSIM constants, psnr_peak the PSNR data range. */
+int adsr_score_images_strided(const void* sr, const void* hr, int is_f32, int B, int H, int W, int C,
+                              const int64_t* host_strides_sr, const int64_t* host_strides_hr, float div,
+                              int clamp01, int zero_pad, double c1, double c2, double psnr_peak,
+                              const int32_t* host_ws_list, int n_ws, double* scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,10 @@ import torch
 
 PKG = "anomaly-detection-super-resolution_b200"
 
+# the torch side of every comparison must be true fp32 (no TF32 in cuDNN / cuBLAS)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 
 def mod(name):
     return importlib.import_module(f"{PKG}.{name}")

@@ -45,8 +45,10 @@ def test_layernorm_rows(C):
     want = F.layer_norm(x[:, :C].float(), (C,), g, b, 1e-5)
     assert (out[:, :C].float() - want).abs().max() < 0.03
     cpad = (C + 15) // 16 * 16
-    assert float(out[:, C:cpad].float().abs().max()) == 0.0 if cpad > C else True
-    assert float((out[:, cpad:].float() - 5.0).abs().max()) == 0.0
+    if cpad > C:
+        assert float(out[:, C:cpad].float().abs().max()) == 0.0
+    if ld > cpad:
+        assert float((out[:, cpad:].float() - 5.0).abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("H,ws,shift", [(32, 8, 0), (32, 8, 4), (16, 4, 2)])
@@ -104,7 +106,7 @@ def test_conv_last_quant(nc, rgb_range):
     ops.conv_last_quant(x, B, H, H, Cin, w, bias, nc, mean, 1.0, rgb_range, out, u8)
     xin = x.float().view(B, H, H, Cin).permute(0, 3, 1, 2)
     want = F.conv2d(xin, w, bias, padding=1) + mean.view(1, nc, 1, 1)
-    assert (out - want).abs().max() < 2e-3 * rgb_range
+    assert (out - want).abs().max() < 1e-4 * float(want.abs().max())
     # the uint8 image must be the truncation of the kernel's own fp32 output (src/evaluate.py:214)
     want_u8 = S.quantize_u8(out.cpu().numpy(), rgb_range)
     assert np.array_equal(u8.cpu().numpy(), want_u8)
