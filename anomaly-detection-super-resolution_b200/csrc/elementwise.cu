@@ -73,11 +73,96 @@ __device__ __forceinline__ void ln_row(const __nv_bfloat16* __restrict__ in, __n
     }
 }
 
-template <int MAXV>
+// Plain LayerNorm kernel: one warp normalises RPW rows at a time so that RPW independent 16-byte loads per
+// lane are in flight (the single-row version was latency bound at ~25 % of HBM bandwidth).
+template <int RPW, int CPL>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const __nv_bfloat16* __restrict__ in, long long ldi,
                                                               __nv_bfloat16* __restrict__ out, long long ldo,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int M, int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int cpad = (C + 15) & ~15;
+    const float inv_c = 1.0f / static_cast<float>(C);
+    for (long long row = (static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5)) * RPW; row < M;
+         row += static_cast<long long>(gridDim.x) * warps_per_block * RPW) {
+        uint4 u[RPW][CPL];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int c0 = (lane + 32 * k) * 8;
+                u[r][k] = (c0 < C && row + r < M) ? __ldg(reinterpret_cast<const uint4*>(in + (row + r) * ldi + c0))
+                                                  : make_uint4(0, 0, 0, 0);
+            }
+        float x[RPW][CPL][8], mean[RPW], rstd[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int c0 = (lane + 32 * k) * 8;
+                const uint32_t w[4] = {u[r][k].x, u[r][k].y, u[r][k].z, u[r][k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    x[r][k][2 * j] = (c0 + 2 * j < C) ? bf16_lo(w[j]) : 0.f;
+                    x[r][k][2 * j + 1] = (c0 + 2 * j + 1 < C) ? bf16_hi(w[j]) : 0.f;
+                    s += x[r][k][2 * j] + x[r][k][2 * j + 1];
+                }
+            }
+            mean[r] = s;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            mean[r] *= inv_c;
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = ((lane + 32 * k) * 8 + j < C) ? x[r][k][j] - mean[r] : 0.f;
+                    v += d * d;
+                }
+            rstd[r] = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const int c0 = (lane + 32 * k) * 8;
+            if (c0 >= cpad) continue;
+            float g[8], bt[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                g[j] = (c0 + j < C) ? __ldg(gamma + c0 + j) : 0.f;
+                bt[j] = (c0 + j < C) ? __ldg(beta + c0 + j) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                if (row + r >= M) continue;
+                const float rs = rsqrtf(rstd[r] * inv_c + eps);
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = (c0 + j < C) ? (x[r][k][j] - mean[r]) * rs * g[j] + bt[j] : 0.f;
+                *reinterpret_cast<uint4*>(out + (row + r) * ldo + c0) =
+                    make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            }
+        }
+    }
+}
+
+// generic fallback (C > 256): one row per warp, MAXV chunks per lane
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_rows_wide_kernel(const __nv_bfloat16* __restrict__ in, long long ldi,
+                                                                   __nv_bfloat16* __restrict__ out, long long ldo,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, int M, int C, float eps) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < M;
@@ -309,9 +394,9 @@ extern "C" int adsr_layernorm_rows(const void* in, int64_t ldi, void* out, int64
     const int grid = grid_for(M, 8);
     auto a = static_cast<const __nv_bfloat16*>(in);
     auto o = static_cast<__nv_bfloat16*>(out);
-    if (C <= 256) layernorm_rows_kernel<1><<<grid, 256, 0, st>>>(a, ldi, o, ldo, gamma, beta, M, C, eps);
-    else if (C <= 512) layernorm_rows_kernel<2><<<grid, 256, 0, st>>>(a, ldi, o, ldo, gamma, beta, M, C, eps);
-    else layernorm_rows_kernel<4><<<grid, 256, 0, st>>>(a, ldi, o, ldo, gamma, beta, M, C, eps);
+    if (C <= 256) layernorm_rows_kernel<4, 1><<<grid_for(M, 32), 256, 0, st>>>(a, ldi, o, ldo, gamma, beta, M, C, eps);
+    else if (C <= 512) layernorm_rows_kernel<2, 2><<<grid_for(M, 16), 256, 0, st>>>(a, ldi, o, ldo, gamma, beta, M, C, eps);
+    else layernorm_rows_wide_kernel<4><<<grid, 256, 0, st>>>(a, ldi, o, ldo, gamma, beta, M, C, eps);
     return check_launch();
 }
 

@@ -25,9 +25,13 @@ namespace {
 constexpr int kStages = 4;
 constexpr int kAStageBytes = 128 * 128;       // 128 rows x 64 bf16
 constexpr int kBStageBytes = 256 * 128;       // up to 256 rows x 64 bf16
-constexpr int kNumThreads = 384;              // 12 warps
+constexpr int kNumThreads = 512;              // 16 warps: B loader, MMA, TMEM alloc, spare, 8 epilogue, 4 producers
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTmemCols = 512;                // 2 accumulator buffers x 256 fp32 columns
-constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 256;
+constexpr int kStageOutBytes = 32 * 64;       // per epilogue warp: 32 rows x 32 bf16 staging tile
+constexpr int kRingBytes = kStages * (kAStageBytes + kBStageBytes);
+constexpr int kSmemBytes = kRingBytes + kEpiWarps * kStageOutBytes + 2 * 256 * 4 + 256;
 
 struct __align__(8) RingBarriers {
     uint64_t full[kStages];
@@ -37,18 +41,57 @@ struct __align__(8) RingBarriers {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act, float slope) {
-    if (act == ADSR_ACT_LRELU) return v > 0.f ? v : v * slope;
-    if (act == ADSR_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-    if (act == ADSR_ACT_RELU) return fmaxf(v, 0.f);
+// exact-erf GELU to 8e-7 absolute: erf(z) = 1 - 2^-p(z) with a degree-5 fit of p (z = |x|/sqrt 2 folded
+// into the coefficients), so gelu(x) = 0.5 * (x + |x| - |x| * 2^-q(|x|)): 5 FMA + 1 MUFU + 3.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float a = fabsf(x);
+    float q = 4.88103149e-4f;                    // c5 / 2^2.5
+    q = fmaf(q, a, -7.19872210e-3f);             // c4 / 4
+    q = fmaf(q, a, 5.21466284e-2f);              // c3 / 2^1.5
+    q = fmaf(q, a, 4.59595859e-1f);              // c2 / 2
+    q = fmaf(q, a, 1.15100050e+0f);              // c1 / sqrt 2
+    const float e = exp2f(-q * a);
+    return 0.5f * (x + fmaf(-a, e, a));
+}
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v, float slope) {
+    if constexpr (ACT == ADSR_ACT_LRELU) return v > 0.f ? v : v * slope;
+    if constexpr (ACT == ADSR_ACT_GELU) return gelu_erf(v);
+    if constexpr (ACT == ADSR_ACT_RELU) return fmaxf(v, 0.f);
     return v;
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t add_bf16x2_f32(uint32_t a, uint32_t b, bool lo_ok, bool hi_ok) {
+    const float l = bf16_lo(a) + (lo_ok ? bf16_lo(b) : 0.f);
+    const float h = bf16_hi(a) + (hi_ok ? bf16_hi(b) : 0.f);
+    return pack_bf16x2(l, h);
+}
+
+template <int ACT>
 __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const TcGemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kAStageBytes;
-    RingBarriers* bars = reinterpret_cast<RingBarriers*>(smem + kStages * (kAStageBytes + kBStageBytes));
+    uint8_t* smem_out = smem + kRingBytes;                                   // [8 warps][32 rows][64 B]
+    float* smem_bias = reinterpret_cast<float*>(smem_out + kEpiWarps * kStageOutBytes);   // [2][256]
+    RingBarriers* bars = reinterpret_cast<RingBarriers*>(smem_bias + 2 * 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -63,7 +106,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const TcGemmPar
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->tmem_full[b], 1);
-            mbar_init(&bars->tmem_empty[b], 128);  // 128 epilogue threads
+            mbar_init(&bars->tmem_empty[b], kEpiThreads);
         }
         fence_barrier_init();
     }
@@ -127,94 +170,146 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const TcGemmPar
                 umma_commit(&bars->tmem_full[buf]);            // accumulator complete -> epilogue
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ================================ epilogue: TMEM -> registers -> global ======================
-        const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
+    } else if (warp >= 4 && warp < 4 + kEpiWarps) {
+        // ================================ epilogue: TMEM -> regs -> smem staging -> coalesced global ==
+        // 8 warps: quadrant q = warp & 3 owns TMEM lanes / tile rows 32q..32q+31, the two warps of a
+        // quadrant take alternate 32-column chunks.  Values are staged as bf16 in a per-warp 32x32
+        // swizzled tile so that global stores (and residual loads) are row-contiguous 64 B segments.
+        const int ew = warp - 4;
+        const int quad = warp & 3;
+        const int half = ew >> 2;
+        const int et = threadIdx.x - 4 * 32;                   // 0..255 inside the epilogue group
+        uint8_t* stg = smem_out + ew * kStageOutBytes;
+        const uint32_t stg_w = smem_u32(stg) + static_cast<uint32_t>(lane * 64);     // my row when writing
+        const int wsw = (lane >> 1) & 3;
+        const int n_chunks = (p.BN + 31) >> 5;
+        const bool st16 = (p.ocol0 & 7) == 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_tile = tile / p.n_tiles;
             const int n_tile = tile % p.n_tiles;
             const int buf = it & 1;
             const uint32_t use = static_cast<uint32_t>(it >> 1);
+            const int n_base = n_tile * p.BN;
+            const int n_lim = min(p.n_store, n_base + p.BN);   // never write into the next N tile's columns
+            float* bias_s = smem_bias + buf * 256;
+            if (et < p.BN) bias_s[et] = __ldg(p.bias + n_base + et);
+            named_bar_sync(1, kEpiThreads);
             mbar_wait(&bars->tmem_full[buf], use & 1);
             tc_fence_after_sync();
-            const int row = m_tile * 128 + quad * 32 + lane;
-            const bool row_ok = row < p.M;
+            const int row0 = m_tile * 128 + quad * 32;
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(buf * 256) + (static_cast<uint32_t>(quad * 32) << 16);
-            const int n_base = n_tile * p.BN;
 
-            // pixel-shuffle destination (out_mode 1): this row is input pixel (b, y, x)
-            long long ps_base = 0;
-            if (p.out_mode == ADSR_OUT_PIXEL_SHUFFLE2 && row_ok) {
-                const int hw = p.Hout * p.Wout;
-                const int b = row / hw;
-                const int rem = row - b * hw;
-                const int y = rem / p.Wout;
-                const int x = rem - y * p.Wout;
-                ps_base = ((static_cast<long long>(b) * (2 * p.Hout) + 2 * y) * (2 * p.Wout) + 2 * x) * p.ldo;
-            }
-
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                uint32_t raw[16];
-                __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge first
-                tmem_ld16(taddr + static_cast<uint32_t>(c0), raw);
-                tmem_ld_wait();
+            for (int ch = half; ch < n_chunks; ch += 2) {
+                const int c0 = ch * 32;
                 const int n0 = n_base + c0;
-                if (row_ok && n0 < p.n_store) {
-                float v[16];
+                const bool wide = c0 + 32 <= p.BN;             // BN % 32 == 16: last chunk is 16 columns
+                const bool do_store = n0 < n_lim;              // warp-uniform
+                // ---- residual prefetch in the coalesced (write-out) mapping: 4 rows-of-8 x 4 chunks
+                uint4 rres[4];
+                if (p.res != nullptr && do_store) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float a = __uint_as_float(raw[j]) + __ldg(p.bias + n0 + j);
-                    v[j] = apply_act(a, p.act, p.slope) * p.alpha;
-                }
-                if (p.res != nullptr) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + static_cast<long long>(row) * p.ldres + n0);
-                    uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (n0 + 2 * j < p.N) v[2 * j] += bf16_lo(rr[j]);
-                        if (n0 + 2 * j + 1 < p.N) v[2 * j + 1] += bf16_hi(rr[j]);
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = row0 + i * 8 + (lane >> 2);
+                        const int col = n0 + (lane & 3) * 8;
+                        rres[i] = (r < p.M && col < n_lim)
+                                      ? __ldg(reinterpret_cast<const uint4*>(p.res + static_cast<long long>(r) * p.ldres + col))
+                                      : make_uint4(0, 0, 0, 0);
                     }
                 }
-                if (p.out_mode == ADSR_OUT_ROWS) {
-                    uint32_t o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-                    __nv_bfloat16* dst = p.out + static_cast<long long>(row) * p.ldo + p.ocol0 + n0;
-                    if ((p.ocol0 & 7) == 0) {
-                        uint4* d4 = reinterpret_cast<uint4*>(dst);
-                        d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                    } else {                                    // slab slices start at 8-byte aligned columns
-                        uint2* d2 = reinterpret_cast<uint2*>(dst);
-                        d2[0] = make_uint2(o[0], o[1]);
-                        d2[1] = make_uint2(o[2], o[3]);
-                        d2[2] = make_uint2(o[4], o[5]);
-                        d2[3] = make_uint2(o[6], o[7]);
-                    }
+                uint32_t raw[32];
+                __syncwarp();                                   // tcgen05.ld is .sync.aligned
+                if (wide) {
+                    tmem_ld32(taddr + static_cast<uint32_t>(c0), raw);
                 } else {
-                    // PixelShuffle(2): column n = c*4 + i*2 + j  ->  out[b, 2y+i, 2x+j, c]
-                    const int ch0 = n0 >> 2;
+                    uint32_t lo[16];
+                    tmem_ld16(taddr + static_cast<uint32_t>(c0), lo);
 #pragma unroll
-                    for (int sub = 0; sub < 4; ++sub) {
-                        const int i = sub >> 1, j = sub & 1;
-                        uint2 o;
-                        o.x = pack_bf16x2(v[0 * 4 + sub], v[1 * 4 + sub]);
-                        o.y = pack_bf16x2(v[2 * 4 + sub], v[3 * 4 + sub]);
-                        __nv_bfloat16* dst = p.out + ps_base + (static_cast<long long>(i) * (2 * p.Wout) + j) * p.ldo + ch0;
-                        *reinterpret_cast<uint2*>(dst) = o;
+                    for (int j = 0; j < 16; ++j) { raw[j] = lo[j]; raw[16 + j] = 0; }
+                }
+                tmem_ld_wait();
+                if (!do_store) continue;                        // warp-uniform
+                // ---- bias + activation + alpha, pack to bf16, stage
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
+                    const float v0 = apply_act<ACT>(__uint_as_float(raw[4 * j + 0]) + bb.x, p.slope) * p.alpha;
+                    const float v1 = apply_act<ACT>(__uint_as_float(raw[4 * j + 1]) + bb.y, p.slope) * p.alpha;
+                    const float v2 = apply_act<ACT>(__uint_as_float(raw[4 * j + 2]) + bb.z, p.slope) * p.alpha;
+                    const float v3 = apply_act<ACT>(__uint_as_float(raw[4 * j + 3]) + bb.w, p.slope) * p.alpha;
+                    if (p.out_mode == ADSR_OUT_ROWS) {
+                        pk[2 * j] = pack_bf16x2(v0, v1);
+                        pk[2 * j + 1] = pack_bf16x2(v2, v3);
+                    } else {
+                        // PixelShuffle(2): column 4c+sub -> staging position sub*8 + c  (8 channels per chunk)
+                        // handled below from the float values: keep them in raw[]
+                        raw[4 * j + 0] = __float_as_uint(v0); raw[4 * j + 1] = __float_as_uint(v1);
+                        raw[4 * j + 2] = __float_as_uint(v2); raw[4 * j + 3] = __float_as_uint(v3);
                     }
                 }
+                if (p.out_mode != ADSR_OUT_ROWS) {
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            pk[sub * 4 + c] = pack_bf16x2(__uint_as_float(raw[(2 * c) * 4 + sub]),
+                                                          __uint_as_float(raw[(2 * c + 1) * 4 + sub]));
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_w + static_cast<uint32_t>((j ^ wsw) << 4)),
+                                 "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                                 : "memory");
+                }
+                __syncwarp();
+                // ---- coalesced write-out: lane -> (row = i*8 + lane/4, 16-byte chunk = lane%4)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = i * 8 + (lane >> 2);
+                    const int cc = lane & 3;
+                    const uint4 val = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((cc ^ ((rl >> 1) & 3)) << 4));
+                    const int r = row0 + rl;
+                    if (r >= p.M) continue;
+                    if (p.out_mode == ADSR_OUT_ROWS) {
+                        const int col = n0 + cc * 8;
+                        if (col >= n_lim) continue;
+                        uint4 o = val;
+                        if (p.res != nullptr) {
+                            o.x = add_bf16x2_f32(val.x, rres[i].x, col + 0 < p.N, col + 1 < p.N);
+                            o.y = add_bf16x2_f32(val.y, rres[i].y, col + 2 < p.N, col + 3 < p.N);
+                            o.z = add_bf16x2_f32(val.z, rres[i].z, col + 4 < p.N, col + 5 < p.N);
+                            o.w = add_bf16x2_f32(val.w, rres[i].w, col + 6 < p.N, col + 7 < p.N);
+                        }
+                        __nv_bfloat16* dst = p.out + static_cast<long long>(r) * p.ldo + p.ocol0 + col;
+                        if (st16) {
+                            *reinterpret_cast<uint4*>(dst) = o;
+                        } else {                                // slab slices start at 8-byte aligned columns
+                            reinterpret_cast<uint2*>(dst)[0] = make_uint2(o.x, o.y);
+                            reinterpret_cast<uint2*>(dst)[1] = make_uint2(o.z, o.w);
+                        }
+                    } else {
+                        // staging chunk cc = sub-pixel (i2, j2); 8 channels n0/4 .. n0/4+7
+                        const int hw = p.Hout * p.Wout;
+                        const int b = r / hw;
+                        const int rem = r - b * hw;
+                        const int y = rem / p.Wout;
+                        const int x = rem - y * p.Wout;
+                        const int i2 = cc >> 1, j2 = cc & 1;
+                        __nv_bfloat16* dst = p.out +
+                            ((static_cast<long long>(b) * (2 * p.Hout) + 2 * y + i2) * (2 * p.Wout) + 2 * x + j2) * p.ldo + (n0 >> 2);
+                        *reinterpret_cast<uint4*>(dst) = val;
+                    }
+                }
+                __syncwarp();                                   // staging tile is reused by the next chunk
             }
             __syncwarp();
             tc_fence_before_sync();
             mbar_arrive(&bars->tmem_empty[buf]);
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 4 + kEpiWarps) {
         // ================================ A producers (4 warps, 128 threads) =========================
-        const int pw = warp - 8;
+        const int pw = warp - (4 + kEpiWarps);
         const int chunk = lane & 7;                            // 16-byte chunk inside the 128 B row
         const int rsub = pw * 4 + (lane >> 3);                 // row inside each 16-row step
         const uint32_t sw_off = static_cast<uint32_t>(rsub * 128 + ((chunk ^ (rsub & 7)) << 4));
@@ -303,16 +398,23 @@ int launch_tc_gemm(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
         ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldo % 8) != 0))
         return ADSR_ERR_BAD_ALIGN;
     if (p.num_k_stages <= 0 || p.n_tiles <= 0) return ADSR_ERR_BAD_SHAPE;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) return ADSR_ERR_CUDA;
-        attr_set = true;
-    }
+    if (p.out_mode == ADSR_OUT_PIXEL_SHUFFLE2 &&
+        ((p.BN % 32) != 0 || (p.ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15)))
+        return ADSR_ERR_BAD_SHAPE;
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    tc_gemm_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(p);
-    return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
+    auto launch = [&](auto kernel) -> int {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return ADSR_ERR_CUDA;
+        kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(p);
+        return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
+    };
+    switch (p.act) {
+        case ADSR_ACT_NONE: return launch(tc_gemm_kernel<ADSR_ACT_NONE>);
+        case ADSR_ACT_LRELU: return launch(tc_gemm_kernel<ADSR_ACT_LRELU>);
+        case ADSR_ACT_GELU: return launch(tc_gemm_kernel<ADSR_ACT_GELU>);
+        case ADSR_ACT_RELU: return launch(tc_gemm_kernel<ADSR_ACT_RELU>);
+    }
+    return ADSR_ERR_BAD_SHAPE;
 }
 
 }  // namespace adsr
