@@ -29,7 +29,8 @@ extern "C" int adsr_device_check(int* host_num_sms) {
 extern "C" int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* w_packed, const float* bias_padded,
                                  int N, int BN, int n_tiles, int act, float slope, float alpha, const void* res,
                                  int64_t ldres, void* out, int64_t ldo, int ocol0, int n_store, int num_sms, void* stream) {
-    if (K <= 0 || N <= 0 || n_store > n_tiles * BN || lda < ((K + 7) & ~7)) return ADSR_ERR_BAD_SHAPE;
+    if (M <= 0) return ADSR_OK;
+    if (K <= 0 || N <= 0 || n_store > n_tiles * BN || lda < K) return ADSR_ERR_BAD_SHAPE;
     TcGemmParams p{};
     p.A = static_cast<const __nv_bfloat16*>(A);
     p.lda = lda;
@@ -58,6 +59,11 @@ extern "C" int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K, const
     p.ldo = ldo;
     p.ocol0 = ocol0;
     p.out_mode = ADSR_OUT_ROWS;
+    // A tiles come by TMA: tensor = [M rows x K cols]; columns >= K and rows >= M are zero-filled by the hardware
+    p.use_tma = 1;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda % 8)) return ADSR_ERR_BAD_ALIGN;
+    const int st = encode_tmap_rows_bf16(&p.tmap_a, A, M, K, lda);
+    if (st != ADSR_OK) return st;
     return launch_tc_gemm(p, num_sms, static_cast<cudaStream_t>(stream));
 }
 

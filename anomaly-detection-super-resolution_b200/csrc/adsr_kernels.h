@@ -1,5 +1,6 @@
 // Internal declarations shared by the .cu translation units (not part of the public C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -9,6 +10,8 @@
 namespace adsr {
 
 struct TcGemmParams {
+    CUtensorMap tmap_a;  // GEMM mode: [M rows x K cols] bf16, box 128 x 64, 128-byte swizzle (first: 64 B aligned)
+    int use_tma;         // 1 = A tiles arrive by TMA (GEMM), 0 = producer warps gather them (conv)
     // A operand: token rows (GEMM) or NHWC image (implicit-GEMM conv)
     const __nv_bfloat16* A;
     long long lda;       // row / pixel pitch in elements (multiple of 8)
@@ -34,5 +37,7 @@ struct TcGemmParams {
 };
 
 int launch_tc_gemm(const TcGemmParams& p, int num_sms, cudaStream_t stream);
+// Encodes the TMA descriptor of a row-major bf16 matrix (driver entry point resolved at run time).
+int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems);
 
 }  // namespace adsr

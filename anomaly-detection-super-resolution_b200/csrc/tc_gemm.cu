@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t add_bf16x2_f32(uint32_t a, uint32_t b, bool 
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const TcGemmParams p) {
+__global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kAStageBytes;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const TcGemmPar
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&bars->full[s], 128 + 1);    // 128 producer threads + the bulk-copy issuer
+            mbar_init(&bars->full[s], p.use_tma ? 1 : 128 + 1);   // (128 producer threads +) the copy issuer
             mbar_init(&bars->empty[s], 1);         // one tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
@@ -120,14 +120,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const TcGemmPar
         // ================================ B loader: one bulk copy per ring stage =================
         if (lane == 0) {
             const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
+            const uint32_t tx_bytes = b_bytes + (p.use_tma ? static_cast<uint32_t>(kAStageBytes) : 0u);
+            if (p.use_tma) tma_prefetch_desc(&p.tmap_a);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.n_tiles;
+                const int m0 = (tile / p.n_tiles) * 128;
                 const uint8_t* src = p.Bp + static_cast<size_t>(n_tile) * p.num_k_stages * b_bytes;
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&bars->full[stage], b_bytes);
+                    mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
+                    if (p.use_tma) tma_load_2d(smem_a + stage * kAStageBytes, &p.tmap_a, ks * 64, m0, &bars->full[stage]);
                     bulk_g2s(smem_b + stage * kBStageBytes, src + static_cast<size_t>(ks) * b_bytes, b_bytes,
                              &bars->full[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const TcGemmPar
             tc_fence_before_sync();
             mbar_arrive(&bars->tmem_empty[buf]);
         }
-    } else if (warp >= 4 + kEpiWarps) {
+    } else if (warp >= 4 + kEpiWarps && !p.use_tma) {
         // ================================ A producers (4 warps, 128 threads) =========================
         const int pw = warp - (4 + kEpiWarps);
         const int chunk = lane & 7;                            // 16-byte chunk inside the 128 B row
@@ -387,6 +391,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const TcGemmPar
 }
 
 }  // namespace
+
+int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems) {
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess || fn == nullptr)
+            return ADSR_ERR_CUDA;
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ADSR_OK : ADSR_ERR_CUDA;
+}
 
 int launch_tc_gemm(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     if (p.M <= 0) return ADSR_OK;
