@@ -233,6 +233,204 @@ __global__ void __launch_bounds__(128) window_attn_kernel(const AttnParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path for N == 64 (window 8x8, the headline configuration): one CTA = one window x HPC heads.
+// All q|k|v rows of the window are pulled into shared memory with cp.async (16 B, L1 bypass) in one
+// sweep (deep memory-level parallelism, 3 row segments of HPC*hdp*2 bytes per token), each of the
+// 4 warps owns 16 query rows and loops over the CTA's heads, and the output rows are staged over the
+// (consumed) q columns so that global stores are contiguous HPC*hdp*2-byte segments.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int KD, int HPC>
+__global__ void __launch_bounds__(128) window_attn64_kernel(const AttnParams p) {
+    constexpr int HDP = KD * 16;
+    constexpr int SEG = HPC * HDP;            // elements per q / k / v segment of a row
+    constexpr int PITCH = 3 * SEG + 8;        // odd number of 16 B chunks: conflict-free ldmatrix
+    constexpr int CH = 3 * SEG / 8;           // 16 B chunks per row
+    extern __shared__ __align__(16) uint8_t smem[];
+    __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(smem);
+    int* sTok = reinterpret_cast<int*>(sX + 64 * PITCH);
+    int* sInfo = sTok + 64;
+    float* sBias = reinterpret_cast<float*>(sInfo + 64);      // [HPC][nbias]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int hg = blockIdx.y;                                 // head group
+    const int g0 = blockIdx.x * 64;
+    const int nbias = (2 * p.ws - 1) * (2 * p.ws - 1);
+
+    if (tid < 64) {
+        int info, win;
+        sTok[tid] = slot_to_token(p, g0 + tid, info, win);
+        sInfo[tid] = info;
+    }
+    for (int i = tid; i < HPC * nbias; i += 128) {
+        const int hl = i / nbias, e = i - hl * nbias;
+        sBias[i] = __ldg(p.table + static_cast<long long>(e) * p.nH + hg * HPC + hl);
+    }
+    __syncthreads();
+    {
+        const long long seg_stride = static_cast<long long>(p.nH) * HDP;          // q -> k -> v column distance
+        const long long col0 = static_cast<long long>(hg) * SEG;
+        const uint32_t sbase = smem_u32(sX);
+        for (int idx = tid; idx < 64 * CH; idx += 128) {
+            const int r = idx / CH, c = idx - r * CH;
+            const int part = c / (SEG / 8), cc = c - part * (SEG / 8);
+            const int tok = sTok[r];
+            const uint32_t dst = sbase + static_cast<uint32_t>((r * PITCH + c * 8) * 2);
+            if (tok >= 0) {
+                cp_async16(dst, p.qkv + tok * p.ldq + part * seg_stride + col0 + cc * 8);
+            } else {
+                asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0) : "memory");
+            }
+        }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+
+    const int gq = lane >> 2, tq = lane & 3;
+    const int r0 = warp * 16 + gq, r1 = r0 + 8;
+    const int infoq0 = sInfo[r0], infoq1 = sInfo[r1];
+    const int bw = 2 * p.ws - 1;
+    const int qb0 = (((infoq0 >> 8) & 255) + p.ws - 1) * bw + (infoq0 & 255) + p.ws - 1;
+    const int qb1 = (((infoq1 >> 8) & 255) + p.ws - 1) * bw + (infoq1 & 255) + p.ws - 1;
+    const int idq0 = infoq0 >> 16, idq1 = infoq1 >> 16;
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    // per-key mask / bias offsets do not depend on the head: hoist them (16 keys per thread)
+    int kboff[16];
+    float mk0[16], mk1[16];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int kc = nt * 8 + tq * 2 + e;
+            const int ik = sInfo[kc];
+            kboff[nt * 2 + e] = ((ik >> 8) & 255) * bw + (ik & 255);
+            const int idk = ik >> 16;
+            const bool kvalid = sTok[kc] >= 0;
+            mk0[nt * 2 + e] = !kvalid ? -INFINITY : (idq0 != idk ? -100.f * LOG2E : 0.f);
+            mk1[nt * 2 + e] = !kvalid ? -INFINITY : (idq1 != idk ? -100.f * LOG2E : 0.f);
+        }
+
+#pragma unroll 1
+    for (int hl = 0; hl < HPC; ++hl) {
+        const __nv_bfloat16* sQ = sX + hl * HDP;
+        const __nv_bfloat16* sK = sX + SEG + hl * HDP;
+        const __nv_bfloat16* sV = sX + 2 * SEG + hl * HDP;
+        const float* bias = sBias + hl * nbias;
+        uint32_t qf[KD][4];
+#pragma unroll
+        for (int kd = 0; kd < KD; ++kd)
+            ldmatrix_x4(qf[kd], smem_u32(sQ + (warp * 16 + (lane & 15)) * PITCH + kd * 16 + (lane >> 4) * 8));
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kd = 0; kd < KD; ++kd) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bfr[4];
+                ldmatrix_x4(bfr, smem_u32(sK + (8 * (2 * np + (lane >> 4)) + (lane & 7)) * PITCH + kd * 16 + ((lane >> 3) & 1) * 8));
+                mma_bf16_16816(s[2 * np], qf[kd], bfr[0], bfr[1]);
+                mma_bf16_16816(s[2 * np + 1], qf[kd], bfr[2], bfr[3]);
+            }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int ki = nt * 2 + e;
+                const float v0 = fmaf(s[nt][e], p.scale_log2e, fmaf(bias[qb0 - kboff[ki]], LOG2E, mk0[ki]));
+                const float v1 = fmaf(s[nt][2 + e], p.scale_log2e, fmaf(bias[qb1 - kboff[ki]], LOG2E, mk1[ki]));
+                s[nt][e] = v0;
+                s[nt][2 + e] = v1;
+                mx0 = fmaxf(mx0, v0);
+                mx1 = fmaxf(mx1, v1);
+            }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float sub0 = mx0 == -INFINITY ? 0.f : mx0, sub1 = mx1 == -INFINITY ? 0.f : mx1;
+        float l0 = 0.f, l1 = 0.f;
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float p00 = exp2f(s[nt][0] - sub0), p01 = exp2f(s[nt][1] - sub0);
+            const float p10 = exp2f(s[nt][2] - sub1), p11 = exp2f(s[nt][3] - sub1);
+            l0 += p00 + p01;
+            l1 += p10 + p11;
+            const int j = nt >> 1;
+            if ((nt & 1) == 0) { pf[j][0] = pack_bf16x2(p00, p01); pf[j][1] = pack_bf16x2(p10, p11); }
+            else               { pf[j][2] = pack_bf16x2(p00, p01); pf[j][3] = pack_bf16x2(p10, p11); }
+        }
+        float o[2 * KD][4];
+#pragma unroll
+        for (int i = 0; i < 2 * KD; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int nd = 0; nd < 2 * KD; nd += 2) {
+                uint32_t bfr[4];
+                ldmatrix_x4_trans(bfr, smem_u32(sV + (16 * j + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + 8 * (nd + (lane >> 4))));
+                mma_bf16_16816(o[nd], pf[j], bfr[0], bfr[1]);
+                mma_bf16_16816(o[nd + 1], pf[j], bfr[2], bfr[3]);
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+        __syncwarp();                                   // every lane's q fragments of this head are in registers
+        __nv_bfloat16* sO = sX + hl * HDP;              // overwrite this warp's own q rows with the output
+#pragma unroll
+        for (int nd = 0; nd < 2 * KD; ++nd) {
+            *reinterpret_cast<uint32_t*>(sO + r0 * PITCH + nd * 8 + tq * 2) = pack_bf16x2(o[nd][0] * inv0, o[nd][1] * inv0);
+            *reinterpret_cast<uint32_t*>(sO + r1 * PITCH + nd * 8 + tq * 2) = pack_bf16x2(o[nd][2] * inv1, o[nd][3] * inv1);
+        }
+    }
+    __syncwarp();
+    constexpr int OCH = SEG / 8;
+    for (int idx = lane; idx < 16 * OCH; idx += 32) {
+        const int r = warp * 16 + idx / OCH, c = idx % OCH;
+        const int tok = sTok[r];
+        if (tok >= 0)
+            *reinterpret_cast<uint4*>(p.out + tok * p.ldo + static_cast<long long>(hg) * SEG + c * 8) =
+                *reinterpret_cast<const uint4*>(sX + r * PITCH + c * 8);
+    }
+}
+
+template <int KD, int HPC>
+int launch_attn64(const AttnParams& p, cudaStream_t stream) {
+    constexpr int HDP = KD * 16;
+    const int nbias = (2 * p.ws - 1) * (2 * p.ws - 1);
+    const size_t smem = static_cast<size_t>(64) * (3 * HPC * HDP + 8) * 2 + 2 * 64 * 4 + static_cast<size_t>(HPC) * nbias * 4;
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(window_attn64_kernel<KD, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+            return ADSR_ERR_CUDA;
+    }
+    dim3 grid((p.total_slots + 63) / 64, p.nH / HPC);
+    window_attn64_kernel<KD, HPC><<<grid, 128, smem, stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
+}
+
+template <int KD>
+int dispatch_attn64(const AttnParams& p, cudaStream_t stream) {
+    // heads per CTA: the largest of {3,2,1} that divides nH and keeps the q|k|v tile around 60 KB
+    if constexpr (KD <= 3) { if (p.nH % 3 == 0) return launch_attn64<KD, 3>(p, stream); }
+    if constexpr (KD <= 5) { if (p.nH % 2 == 0) return launch_attn64<KD, 2>(p, stream); }
+    return launch_attn64<KD, 1>(p, stream);
+}
+
 template <int KD>
 int launch_attn(const AttnParams& p, cudaStream_t stream) {
     constexpr int HDP = KD * 16;
@@ -273,6 +471,18 @@ extern "C" int adsr_window_attention(const void* qkv, int64_t ldq, void* out, in
     p.total_slots = B * p.nW * N;
     p.scale_log2e = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N == 64) {
+        switch (hdp / 16) {
+            case 1: return dispatch_attn64<1>(p, st);
+            case 2: return dispatch_attn64<2>(p, st);
+            case 3: return dispatch_attn64<3>(p, st);
+            case 4: return dispatch_attn64<4>(p, st);
+            case 5: return dispatch_attn64<5>(p, st);
+            case 6: return dispatch_attn64<6>(p, st);
+            case 7: return dispatch_attn64<7>(p, st);
+            case 8: return dispatch_attn64<8>(p, st);
+        }
+    }
     switch (hdp / 16) {
         case 1: return launch_attn<1>(p, st);
         case 2: return launch_attn<2>(p, st);
