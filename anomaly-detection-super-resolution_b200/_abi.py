@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadsr_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ACT_NONE, ACT_LRELU, ACT_GELU, ACT_RELU = 0, 1, 2, 3
 OUT_ROWS, OUT_PIXEL_SHUFFLE2 = 0, 1
@@ -25,7 +25,7 @@ _SIGNATURES = {
                                   c_float, c_float, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "adsr_conv3x3_igemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                         c_int, c_int, c_int, c_float, c_float, c_void_p, c_int64, c_void_p, c_int64,
-                                        c_int, c_int, c_int, c_void_p]),
+                                        c_int, c_int, c_int, c_int, c_void_p]),
     "adsr_layernorm_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_float,
                                     c_void_p]),
     "adsr_window_attention": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -45,6 +45,12 @@ _SIGNATURES = {
     "adsr_score_images_strided": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_int64),
                                           POINTER(c_int64), c_float, c_int, c_int, c_double, c_double, c_double,
                                           POINTER(c_int32), c_int, c_void_p, c_void_p]),
+    "adsr_bicubic_affine": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "adsr_conv3x3_small": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64,
+                                   c_void_p, c_int64, c_int, c_void_p]),
+    "adsr_channel_mean": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "adsr_rcab_ca_scale": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

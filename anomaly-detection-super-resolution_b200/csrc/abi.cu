@@ -70,11 +70,11 @@ extern "C" int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K, const
 extern "C" int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int Hin, int Win, int Cin, int stride,
                                        const void* w_packed, const float* bias_padded, int N, int BN, int n_tiles, int act,
                                        float slope, float alpha, const void* res, int64_t ldres, void* out, int64_t ldo,
-                                       int out_mode, int n_store, int num_sms, void* stream) {
+                                       int ocol0, int out_mode, int n_store, int num_sms, void* stream) {
     if (B <= 0) return ADSR_OK;
     if (Cin <= 0 || N <= 0 || (stride != 1 && stride != 2) || n_store > n_tiles * BN || ld_in < ((Cin + 7) & ~7))
         return ADSR_ERR_BAD_SHAPE;
-    if (out_mode == ADSR_OUT_PIXEL_SHUFFLE2 && ((N % 4) || stride != 1 || res != nullptr)) return ADSR_ERR_BAD_SHAPE;
+    if (out_mode == ADSR_OUT_PIXEL_SHUFFLE2 && ((N % 4) || stride != 1 || res != nullptr || ocol0 != 0)) return ADSR_ERR_BAD_SHAPE;
     TcGemmParams p{};
     p.A = static_cast<const __nv_bfloat16*>(in);
     p.lda = ld_in;
@@ -104,7 +104,7 @@ extern "C" int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int
     p.ldres = ldres;
     p.out = static_cast<__nv_bfloat16*>(out);
     p.ldo = ldo;
-    p.ocol0 = 0;
+    p.ocol0 = ocol0;
     p.out_mode = out_mode;
     return launch_tc_gemm(p, num_sms, static_cast<cudaStream_t>(stream));
 }

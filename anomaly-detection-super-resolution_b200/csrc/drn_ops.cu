@@ -1,0 +1,235 @@
+// Bandwidth-bound kernels specific to the DRN path: bicubic up-sampling fused with the sub_mean MeanShift,
+// the 1/3-channel head convolution, per-image channel means (global average pool) and the RCAB channel-
+// attention epilogue  out = res * sigmoid(W2 relu(W1 mean + b1) + b2) + x.
+#include "adsr_kernels.h"
+#include "ptx.cuh"
+
+namespace adsr {
+namespace {
+
+// ATen upsample_bicubic2d coefficients (A = -0.75), align_corners = False.
+__device__ __forceinline__ float cubic1(float x) { return ((1.25f * x - 2.25f) * x) * x + 1.f; }             // |x| <= 1
+__device__ __forceinline__ float cubic2(float x) { return ((-0.75f * x + 3.75f) * x - 6.f) * x + 3.f; }      // 1 < |x| < 2
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+    c[0] = cubic2(t + 1.f);
+    c[1] = cubic1(t);
+    c[2] = cubic1(1.f - t);
+    c[3] = cubic2(2.f - t);
+}
+
+// out[b, :, oy, ox] = Wm * bicubic(in)[b, :, oy, ox] + bm      (nn.Upsample(bicubic) + MeanShift, src/drn.py:243-246)
+__global__ void __launch_bounds__(256) bicubic_affine_kernel(const float* __restrict__ in, int B, int nc, int h, int w,
+                                                              int scale, const float* __restrict__ Wm,
+                                                              const float* __restrict__ bm, float* __restrict__ out) {
+    const int H = h * scale, W = w * scale;
+    const long long total = static_cast<long long>(B) * H * W;
+    const float inv = 1.0f / static_cast<float>(scale);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % W);
+        const int oy = static_cast<int>((i / W) % H);
+        const int b = static_cast<int>(i / (static_cast<long long>(W) * H));
+        const float sy = (oy + 0.5f) * inv - 0.5f, sx = (ox + 0.5f) * inv - 0.5f;
+        const float fy = floorf(sy), fx = floorf(sx);
+        const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
+        float cy[4], cx[4];
+        cubic_coeffs(sy - fy, cy);
+        cubic_coeffs(sx - fx, cx);
+        float v[3] = {0.f, 0.f, 0.f};
+        for (int c = 0; c < nc; ++c) {
+            const float* plane = in + (static_cast<long long>(b) * nc + c) * h * w;
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int yy = min(max(iy - 1 + r, 0), h - 1);
+                float row = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int xx = min(max(ix - 1 + q, 0), w - 1);
+                    row += __ldg(plane + yy * w + xx) * cx[q];
+                }
+                acc += row * cy[r];
+            }
+            v[c] = acc;
+        }
+        for (int c = 0; c < nc; ++c) {
+            float o = __ldg(bm + c);
+            for (int k = 0; k < nc; ++k) o += __ldg(Wm + c * nc + k) * v[k];
+            out[((static_cast<long long>(b) * nc + c) * H + oy) * W + ox] = o;
+        }
+    }
+}
+
+// 3x3 conv, pad 1, stride 1, Cin <= 3 (fp32 NCHW in) -> Cout <= 64 channels, NHWC bf16, to one or two destinations
+// (DRN head, src/drn.py:247; the second destination is the skip-connection slice of the concat buffer).
+__global__ void __launch_bounds__(128) conv3x3_small_kernel(const float* __restrict__ x, int B, int nc, int H, int W,
+                                                             const float* __restrict__ weight, const float* __restrict__ bias,
+                                                             int C, __nv_bfloat16* __restrict__ out1, long long ld1,
+                                                             int npad1, __nv_bfloat16* __restrict__ out2, long long ld2,
+                                                             int col2) {
+    extern __shared__ float sw[];                     // [nc*9][C] + bias[C]
+    const int kk = nc * 9;
+    for (int i = threadIdx.x; i < kk * C; i += blockDim.x) {
+        const int k = i / C, c = i - k * C;
+        sw[i] = weight[c * kk + k];
+    }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sw[kk * C + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const long long total = static_cast<long long>(B) * H * W;
+    const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= total) return;
+    const int b = static_cast<int>(pix / (H * W));
+    const int rem = static_cast<int>(pix - static_cast<long long>(b) * H * W);
+    const int y = rem / W, xx = rem - y * W;
+    float taps[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) taps[k] = 0.f;
+    for (int c = 0; c < nc; ++c)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int iy = y + t / 3 - 1, ix = xx + t % 3 - 1;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                taps[c * 9 + t] = __ldg(x + ((static_cast<long long>(b) * nc + c) * H + iy) * W + ix);
+        }
+    for (int c0 = 0; c0 < C; c0 += 4) {                // C % 4 == 0
+        float a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = sw[kk * C + c0 + j];
+        for (int k = 0; k < kk; ++k) {
+            const float4 wv = *reinterpret_cast<const float4*>(sw + k * C + c0);
+            a[0] = fmaf(taps[k], wv.x, a[0]); a[1] = fmaf(taps[k], wv.y, a[1]);
+            a[2] = fmaf(taps[k], wv.z, a[2]); a[3] = fmaf(taps[k], wv.w, a[3]);
+        }
+        const uint2 o = make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
+        *reinterpret_cast<uint2*>(out1 + pix * ld1 + c0) = o;
+        if (out2) *reinterpret_cast<uint2*>(out2 + pix * ld2 + col2 + c0) = o;
+    }
+    for (int c0 = C; c0 < npad1; c0 += 4) *reinterpret_cast<uint2*>(out1 + pix * ld1 + c0) = make_uint2(0, 0);
+}
+
+// mean over the HW pixels of each image, per channel: x [B, HW, ld] bf16 -> mean [B, C] fp32 (AdaptiveAvgPool2d(1)).
+// grid = (slices, B): each CTA reduces a slice of pixels and atomically adds its partial mean.
+__global__ void __launch_bounds__(256) channel_mean_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int HW, int C,
+                                                            float* __restrict__ mean) {
+    __shared__ float red[8][128];
+    const int b = blockIdx.y;
+    const int cpairs = C / 2;
+    const int lanes_per_pix = cpairs;                      // one thread per channel pair
+    const int pix_per_iter = blockDim.x / lanes_per_pix;
+    const int cp = threadIdx.x % lanes_per_pix, pslot = threadIdx.x / lanes_per_pix;
+    const int per_slice = (HW + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * per_slice, p1 = min(HW, p0 + per_slice);
+    float s0 = 0.f, s1 = 0.f;
+    if (pslot < pix_per_iter)
+        for (int p = p0 + pslot; p < p1; p += pix_per_iter) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(x + (static_cast<long long>(b) * HW + p) * ld + 2 * cp));
+            s0 += bf16_lo(v);
+            s1 += bf16_hi(v);
+        }
+    // reduce over pixel slots through shared memory (C <= 128 channels, <= 8 slots kept)
+    const int nslots = min(pix_per_iter, 8);
+    if (pslot < 8) { red[pslot][2 * cp] = 0.f; red[pslot][2 * cp + 1] = 0.f; }
+    __syncthreads();
+    if (pslot < pix_per_iter) {
+        atomicAdd(&red[pslot % nslots][2 * cp], s0);
+        atomicAdd(&red[pslot % nslots][2 * cp + 1], s1);
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        float t = 0.f;
+        for (int s = 0; s < nslots; ++s) t += red[s][threadIdx.x];
+        atomicAdd(mean + static_cast<long long>(b) * C + threadIdx.x, t / static_cast<float>(HW));
+    }
+}
+
+// out = res * sigmoid(W2 relu(W1 mean_b + b1) + b2) + x       (CALayer + RCAB residual, src/drn.py:123-158)
+__global__ void __launch_bounds__(256) rcab_ca_scale_kernel(const __nv_bfloat16* __restrict__ res, long long ldr,
+                                                             const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                             __nv_bfloat16* __restrict__ out, long long ldo,
+                                                             const float* __restrict__ mean, const float* __restrict__ w1,
+                                                             const float* __restrict__ b1, const float* __restrict__ w2,
+                                                             const float* __restrict__ b2, int HW, int C, int Cr) {
+    __shared__ float hid[16];
+    __shared__ float sc[128];
+    const int b = blockIdx.y;
+    if (threadIdx.x < Cr) {
+        float a = b1[threadIdx.x];
+        for (int c = 0; c < C; ++c) a = fmaf(w1[threadIdx.x * C + c], mean[static_cast<long long>(b) * C + c], a);
+        hid[threadIdx.x] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        float a = b2[threadIdx.x];
+        for (int j = 0; j < Cr; ++j) a = fmaf(w2[threadIdx.x * Cr + j], hid[j], a);
+        sc[threadIdx.x] = 1.f / (1.f + __expf(-a));
+    }
+    __syncthreads();
+    const int vec = C / 8;                                  // 16-byte vectors per pixel
+    const long long n = static_cast<long long>(HW) * vec;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long p = static_cast<long long>(b) * HW + i / vec;
+        const int c0 = static_cast<int>(i % vec) * 8;
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + p * ldr + c0));
+        const uint4 xv = *reinterpret_cast<const uint4*>(x + p * ldx + c0);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            o[j] = pack_bf16x2(fmaf(bf16_lo(rr[j]), sc[c0 + 2 * j], bf16_lo(xx[j])),
+                               fmaf(bf16_hi(rr[j]), sc[c0 + 2 * j + 1], bf16_hi(xx[j])));
+        *reinterpret_cast<uint4*>(out + p * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+inline int check_launch() { return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH; }
+
+}  // namespace
+}  // namespace adsr
+
+using namespace adsr;
+
+extern "C" int adsr_bicubic_affine(const float* x_nchw, int B, int nc, int h, int w, int scale, const float* mat,
+                                   const float* bias, float* out_nchw, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (nc < 1 || nc > 3 || scale < 1 || h < 1 || w < 1) return ADSR_ERR_BAD_SHAPE;
+    const long long total = static_cast<long long>(B) * h * scale * w * scale;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    bicubic_affine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x_nchw, B, nc, h, w, scale, mat, bias, out_nchw);
+    return check_launch();
+}
+
+extern "C" int adsr_conv3x3_small(const float* x_nchw, int B, int nc, int H, int W, const float* weight, const float* bias,
+                                  int C, void* out1, int64_t ld1, void* out2, int64_t ld2, int col2, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (nc < 1 || nc > 3 || C < 4 || C > 64 || (C % 4) || (ld1 % 4) || (out2 && ((ld2 % 4) || (col2 % 4)))) return ADSR_ERR_BAD_SHAPE;
+    const int npad1 = std::min<int64_t>(ld1, (C + 15) & ~15);
+    const size_t smem = (static_cast<size_t>(nc) * 9 * C + C) * sizeof(float);
+    const long long total = static_cast<long long>(B) * H * W;
+    conv3x3_small_kernel<<<static_cast<int>((total + 127) / 128), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        x_nchw, B, nc, H, W, weight, bias, C, static_cast<__nv_bfloat16*>(out1), ld1, npad1,
+        static_cast<__nv_bfloat16*>(out2), ld2, col2);
+    return check_launch();
+}
+
+extern "C" int adsr_channel_mean(const void* x, int64_t ld, int B, int HW, int C, float* mean, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (C < 2 || C > 128 || (C % 2) || (ld % 2)) return ADSR_ERR_BAD_SHAPE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(mean, 0, static_cast<size_t>(B) * C * sizeof(float), st) != cudaSuccess) return ADSR_ERR_CUDA;
+    const int slices = std::max(1, std::min(32, HW / 256));
+    channel_mean_kernel<<<dim3(slices, B), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ld, HW, C, mean);
+    return check_launch();
+}
+
+extern "C" int adsr_rcab_ca_scale(const void* res, int64_t ldr, const void* x, int64_t ldx, void* out, int64_t ldo,
+                                  const float* mean, const float* w1, const float* b1, const float* w2, const float* b2,
+                                  int B, int HW, int C, int Cr, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (C < 8 || C > 128 || (C % 8) || Cr < 1 || Cr > 16 || (ldr % 8) || (ldx % 8) || (ldo % 8)) return ADSR_ERR_BAD_SHAPE;
+    const int slices = std::max(1, std::min(64, HW * (C / 8) / 1024));
+    rcab_ca_scale_kernel<<<dim3(slices, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(res), ldr, static_cast<const __nv_bfloat16*>(x), ldx,
+        static_cast<__nv_bfloat16*>(out), ldo, mean, w1, b1, w2, b2, HW, C, Cr);
+    return check_launch();
+}

@@ -286,7 +286,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
                             o.w = add_bf16x2_f32(val.w, rres[i].w, col + 6 < p.N, col + 7 < p.N);
                         }
                         __nv_bfloat16* dst = p.out + static_cast<long long>(r) * p.ldo + p.ocol0 + col;
-                        if (st16) {
+                        if (col + 8 > n_lim) {                  // n_store % 8 == 4: only the first 4 columns belong to us
+                            reinterpret_cast<uint2*>(dst)[0] = make_uint2(o.x, o.y);
+                        } else if (st16) {
                             *reinterpret_cast<uint4*>(dst) = o;
                         } else {                                // slab slices start at 8-byte aligned columns
                             reinterpret_cast<uint2*>(dst)[0] = make_uint2(o.x, o.y);
@@ -424,7 +426,7 @@ int launch_tc_gemm(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     if (p.out_mode == ADSR_OUT_ROWS && (p.ocol0 % 8) == 0 &&
         ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldo % 8) != 0))
         return ADSR_ERR_BAD_ALIGN;
-    if (p.num_k_stages <= 0 || p.n_tiles <= 0) return ADSR_ERR_BAD_SHAPE;
+    if (p.num_k_stages <= 0 || p.n_tiles <= 0 || (p.n_store % 4) != 0) return ADSR_ERR_BAD_SHAPE;
     if (p.out_mode == ADSR_OUT_PIXEL_SHUFFLE2 &&
         ((p.BN % 32) != 0 || (p.ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15)))
         return ADSR_ERR_BAD_SHAPE;

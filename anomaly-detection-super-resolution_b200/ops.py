@@ -57,14 +57,14 @@ def tc_gemm(a: torch.Tensor, k: int, w: PackedWeight, out: torch.Tensor, *, act:
 
 def conv3x3(x: torch.Tensor, b: int, h: int, wd: int, cin: int, w: PackedWeight, out: torch.Tensor, *, stride: int = 1,
             act: int = ACT_NONE, slope: float = 0.0, alpha: float = 1.0, res: Optional[torch.Tensor] = None,
-            out_mode: int = OUT_ROWS, n_store: Optional[int] = None) -> None:
-    """x: [b*h*wd, ld] NHWC bf16 -> out rows (b*ho*wo) or pixel-shuffled [b, 2h, 2w, N/4]."""
+            out_mode: int = OUT_ROWS, n_store: Optional[int] = None, ocol0: int = 0) -> None:
+    """x: [b*h*wd, ld] NHWC bf16 -> out rows (b*ho*wo) [at column ocol0] or pixel-shuffled [b, 2h, 2w, N/4]."""
     _cuda(x, "x")
     n_store = (w.N + 15) // 16 * 16 if n_store is None else n_store
     _t = _begin()
     check(lib().adsr_conv3x3_igemm_bf16(ptr(x), x.stride(0), b, h, wd, cin, stride, ptr(w.data), ptr(w.bias), w.N, w.BN,
                                         w.n_tiles, act, slope, alpha, ptr(res), res.stride(0) if res is not None else 0,
-                                        ptr(out), out.stride(0), out_mode, n_store, _abi.num_sms(), stream_ptr()),
+                                        ptr(out), out.stride(0), ocol0, out_mode, n_store, _abi.num_sms(), stream_ptr()),
           "adsr_conv3x3_igemm_bf16")
     _count("conv3x3", 2.0 * b * (-(-h // stride)) * (-(-wd // stride)) * 9 * cin * w.N, _t)
 
@@ -187,3 +187,38 @@ def score_images_strided(sr: torch.Tensor, hr: torch.Tensor, layout: str, window
           "adsr_score_images_strided")
     _count("score_images", 0.0, _t)
     return out
+
+
+def bicubic_affine(x: torch.Tensor, scale: int, mat: torch.Tensor, bias: torch.Tensor, out: torch.Tensor) -> None:
+    _cuda(x, "x")
+    b, nc, h, w = x.shape
+    _t = _begin()
+    check(lib().adsr_bicubic_affine(ptr(x), b, nc, h, w, scale, ptr(mat), ptr(bias), ptr(out), stream_ptr()),
+          "adsr_bicubic_affine")
+    _count("bicubic", 0.0, _t)
+
+
+def conv3x3_small(x: torch.Tensor, weight, bias, c: int, out1: torch.Tensor, out2: Optional[torch.Tensor] = None,
+                  col2: int = 0) -> None:
+    _cuda(x, "x")
+    b, nc, h, w = x.shape
+    _t = _begin()
+    check(lib().adsr_conv3x3_small(ptr(x), b, nc, h, w, ptr(weight), ptr(bias), c, ptr(out1), out1.stride(0), ptr(out2),
+                                   out2.stride(0) if out2 is not None else 0, col2, stream_ptr()), "adsr_conv3x3_small")
+    _count("conv3x3_small", 2.0 * b * h * w * 9 * nc * c, _t)
+
+
+def channel_mean(x: torch.Tensor, b: int, hw: int, c: int, mean: torch.Tensor) -> None:
+    _cuda(x, "x")
+    _t = _begin()
+    check(lib().adsr_channel_mean(ptr(x), x.stride(0), b, hw, c, ptr(mean), stream_ptr()), "adsr_channel_mean")
+    _count("channel_mean", 0.0, _t)
+
+
+def rcab_ca_scale(res: torch.Tensor, x: torch.Tensor, out: torch.Tensor, mean, w1, b1, w2, b2, b: int, hw: int, c: int,
+                  cr: int) -> None:
+    _cuda(res, "res")
+    _t = _begin()
+    check(lib().adsr_rcab_ca_scale(ptr(res), res.stride(0), ptr(x), x.stride(0), ptr(out), out.stride(0), ptr(mean), ptr(w1),
+                                   ptr(b1), ptr(w2), ptr(b2), b, hw, c, cr, stream_ptr()), "adsr_rcab_ca_scale")
+    _count("rcab_ca_scale", 0.0, _t)

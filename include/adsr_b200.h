@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 1
+#define ADSR_ABI_VERSION 2
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -64,7 +64,7 @@ int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int Hin, int W
                             const void* w_packed, const float* bias_padded, int N, int BN, int n_tiles,
                             int act, float slope, float alpha,
                             const void* res, int64_t ldres,
-                            void* out, int64_t ldo, int out_mode, int n_store,
+                            void* out, int64_t ldo, int ocol0, int out_mode, int n_store,
                             int num_sms, void* stream);
 
 /* ---- LayerNorm over the first C columns of each row (eps, affine); writes round16(C) columns ---------
@@ -111,6 +111,22 @@ int adsr_conv_last_quant(const void* in, int64_t ld_in, int B, int H, int W, int
 /* ---- uint8 truncation of an fp32 NCHW image batch (HR side of src/evaluate.py:215) ----------------------- */
 int adsr_quantize_u8(const float* x_nchw, int B, int nc, int H, int W, float rgb_range, uint8_t* out_u8_hwc,
                      void* stream);
+
+/* ---- DRN-only bandwidth-bound pieces --------------------------------------------------------------------------
+ * adsr_bicubic_affine: nn.Upsample(scale, 'bicubic', align_corners=False) + the sub_mean MeanShift 1x1 conv
+ *   (src/drn.py:174-175, 243-246); mat = [nc, nc] fp32, bias = [nc].   fp32 NCHW in and out.
+ * adsr_conv3x3_small: `head` conv, Cin <= 3 (fp32 NCHW) -> C <= 64 channels NHWC bf16 (src/drn.py:187, 247), written to
+ *   out1 and, optionally, to the column slice col2.. of out2 (the skip-connection half of the later torch.cat).
+ * adsr_channel_mean: AdaptiveAvgPool2d(1) of CALayer (src/drn.py:126, 137): x [B, HW, ld] bf16 -> mean [B, C] fp32.
+ * adsr_rcab_ca_scale: out = res * sigmoid(W2 relu(W1 mean + b1) + b2) + x   (src/drn.py:128-139, 155-158). */
+int adsr_bicubic_affine(const float* x_nchw, int B, int nc, int h, int w, int scale, const float* mat,
+                        const float* bias, float* out_nchw, void* stream);
+int adsr_conv3x3_small(const float* x_nchw, int B, int nc, int H, int W, const float* weight, const float* bias,
+                       int C, void* out1, int64_t ld1, void* out2, int64_t ld2, int col2, void* stream);
+int adsr_channel_mean(const void* x, int64_t ld, int B, int HW, int C, float* mean, void* stream);
+int adsr_rcab_ca_scale(const void* res, int64_t ldr, const void* x, int64_t ldx, void* out, int64_t ldo,
+                       const float* mean, const float* w1, const float* b1, const float* w2, const float* b2,
+                       int B, int HW, int C, int Cr, void* stream);
 
 /* ---- per-image anomaly scores ---------------------------------------------------------------------------------
  * replaces ssim_numpy (src/metrics.py:26-67) for every window size of the sweep (src/evaluate.py:233-248),

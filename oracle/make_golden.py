@@ -127,6 +127,47 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "scoring.npz"), **cases)
     print("scoring cases", k)
 
+    # ---- DRN: reference src/drn.py on oracle-generated weights (key/shape layout checked strictly) ---------------------
+    from oracle import drn_oracle as DO
+    rdrn = sys.modules["src.drn"]
+    for name, cfg, B in (("drn_l_rgb", DO.DrnCfg(), 1), ("drn_small_gray", DO.DrnCfg(n_blocks=3, n_colors=1), 2)):
+        opt = rmain.DRN()
+        opt.scale = [2 ** (i + 1) for i in range(cfg.phase)]
+        opt.n_blocks, opt.n_feats, opt.n_colors, opt.rgb_range, opt.negval = cfg.n_blocks, cfg.n_feats, cfg.n_colors, 255, cfg.negval
+        model = rdrn.DRN(opt).eval()
+        sd = DO.make_state_dict(cfg, seed=5)
+        assert set(model.state_dict().keys()) == set(sd.keys()), set(model.state_dict().keys()) ^ set(sd.keys())
+        for kk, v in model.state_dict().items():
+            assert v.shape == sd[kk].shape, kk
+        model.load_state_dict(sd, strict=True)
+        gx = torch.Generator().manual_seed(13)
+        x = torch.rand(B, cfg.n_colors, 32, 32, generator=gx) * 255.0
+        with torch.no_grad():
+            ys = model(x)
+        np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), x=x.numpy(), checksum=DO.state_dict_checksum(sd),
+                            **{f"sr{i}": y.numpy() for i, y in enumerate(ys)})
+        print(name, [tuple(y.shape) for y in ys], float(ys[-1].min()), float(ys[-1].max()))
+
+    # ---- psnr_torch / ssim_torch (validation metrics, src/metrics.py:70-108) and float-input ssim/psnr_numpy --------
+    gt = torch.Generator().manual_seed(21)
+    mt = {}
+    k = 0
+    for (C, H, W, rr) in [(3, 40, 40, 255.0), (1, 24, 24, 255.0), (3, 32, 48, 1.0), (1, 8, 8, 255.0)]:
+        hr = torch.rand(1, C, H, W, generator=gt) * rr
+        sr = (hr + (torch.rand(1, C, H, W, generator=gt) - 0.5) * 0.2 * rr)
+        mt[f"t{k}.hr"], mt[f"t{k}.sr"], mt[f"t{k}.rgb_range"] = hr.numpy(), sr.numpy(), np.float64(rr)
+        mt[f"t{k}.psnr"] = np.float64(rmetrics.psnr_torch(sr, hr, rr))
+        mt[f"t{k}.ssim"] = np.float64(rmetrics.ssim_torch(sr, hr, rr))
+        mt[f"t{k}.ssim7"] = np.float64(rmetrics.ssim_torch(sr, hr, rr, win_size=7))
+        a = (hr[0].permute(1, 2, 0).numpy() / rr).astype(np.float32)
+        b = (sr[0].permute(1, 2, 0).numpy() / rr).astype(np.float32)
+        mt[f"t{k}.np_ssim5"] = np.float64(rmetrics.ssim_numpy(a, b, 5))
+        mt[f"t{k}.np_psnr"] = np.float64(rmetrics.psnr_numpy(a, b))
+        mt[f"t{k}.np_ssim5_dr255"] = np.float64(rmetrics.ssim_numpy(a * 255, b * 255, 5, data_range=255.0))
+        k += 1
+    mt["n"] = np.int64(k)
+    np.savez_compressed(os.path.join(GOLD, "metrics_api.npz"), **mt)
+
     # ---- AUC -------------------------------------------------------------------------------------------
     from sklearn.metrics import roc_auc_score
 
