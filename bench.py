@@ -38,7 +38,9 @@ def parse():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    p.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 256 DRCT-L, 64 DRN-L)")
+    p.add_argument("--workload", default="drct-l", choices=["drct-l", "drn-l"],
+                   help="drct-l = BASELINE configs[2] (headline); drn-l = configs[1]")
     p.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
@@ -186,6 +188,8 @@ def run_reference_arm(args, rank: int):
 # ---------------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if args.batch is None:
+        args.batch = 256 if args.workload == "drct-l" else 64
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -209,7 +213,20 @@ def main():
     opt = main_mod.setup_opt_drct(main_mod.DRCT(), 0.0, 11, "mvtec", "carpet", False, SCALE, True, NC, 1, args.batch, HR,
                                   HR // SCALE, "", "", "", 1, 1, 1, 0.0, 0, ".", "1*L1")
     torch.manual_seed(1)
-    model = drct.DRCT(opt).to(dev).eval()
+    if args.workload == "drct-l":
+        model = drct.DRCT(opt).to(dev).eval()
+        flops_img, metric, wl = 60.436e9, METRIC, "configs[2]: DRCT-L x4 RGB 32->128 px, batch 256 per GPU"
+    else:
+        drn = importlib.import_module(PKG + ".drn")
+        dopt = main_mod.setup_opt_drn(main_mod.DRN(), 0.0, 11, "mvtec", "carpet", False, SCALE, True, NC, 1, args.batch, HR, "",
+                                      "", "", 1, 1, 1, 0.0, 0, ".", ".", "1*L1")
+        model = drn.DRN(dopt).to(dev).eval()
+        with torch.no_grad():                      # keep 80 residual blocks numerically tame with random weights
+            for n_, p_ in model.named_parameters():
+                if ".body.0." in n_ or ".body.2." in n_:
+                    p_.mul_(0.5)
+        flops_img, metric, wl = 49.877e9, "DRN-L x4 128px HR images/sec (inference+scoring)", \
+            "configs[1]: DRN-L x4 RGB 32->128 px, batch 64 per GPU"
 
     # ---- synthetic MVTec-shaped data; every rank gets its own shard of a (world * batch)-image set
     B = args.batch
@@ -309,12 +326,12 @@ def main():
                     "traffic": None, "launches": len(gemm), "flops_per_step": flops, "kernel_ms_per_step": tms,
                     "share_of_step": tms / step_ms if step_ms else None,
                     "ms_by_kernel": {k: round(v, 3) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1])},
-                    "model_flops_per_image": 60.436e9,
-                    "model_tensor_frac": (value / world) * 60.436e9 / (peaks["sustained"] * 1e12)}
+                    "model_flops_per_image": flops_img,
+                    "model_tensor_frac": (value / world) * flops_img / (peaks["sustained"] * 1e12)}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on a bounded sample
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "drct-l":
         n = args.cpu_sample
         O, S, sd, cfg, lr_f, hr_np, wss_c = cpu_setup(n)
         cpu_step(O, S, sd, cfg, lr_f, hr_np, wss_c)
@@ -330,11 +347,10 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[2]: DRCT-L x4 RGB 32->128 px, batch 256 per GPU, inference + scoring "
-                                   "(13-window SSIM sweep + MSE + PSNR per image)",
+            "config": {"workload": wl + ", inference + scoring (13-window SSIM sweep + MSE + PSNR per image)",
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world} (images sharded by rank; "
                        "all_gather of score rows)", "l2": "flushed between steps (256 MiB write)",
                        "weights": "random init, seed 1", "auc": auc},
