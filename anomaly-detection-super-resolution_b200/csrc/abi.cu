@@ -28,7 +28,10 @@ extern "C" int adsr_device_check(int* host_num_sms) {
 
 extern "C" int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K, const void* w_packed, const float* bias_padded,
                                  int N, int BN, int n_tiles, int act, float slope, float alpha, const void* res,
-                                 int64_t ldres, void* out, int64_t ldo, int ocol0, int n_store, int num_sms, void* stream) {
+                                 int64_t ldres, void* out, int64_t ldo, int ocol0, int n_store,
+                                 const float* ln_colsum, float ln_eps, const float* ln_stats_in, int stats_in_slots,
+                                 int stats_in_stride, float* stats_out, int stats_out_slot0, int stats_out_stride,
+                                 int num_sms, void* stream) {
     if (M <= 0) return ADSR_OK;
     if (K <= 0 || N <= 0 || n_store > n_tiles * BN || lda < K) return ADSR_ERR_BAD_SHAPE;
     TcGemmParams p{};
@@ -59,6 +62,18 @@ extern "C" int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K, const
     p.ldo = ldo;
     p.ocol0 = ocol0;
     p.out_mode = ADSR_OUT_ROWS;
+    p.ln_fold = ln_colsum != nullptr;
+    p.ln_C = K;
+    p.ln_eps = ln_eps;
+    p.colsum = ln_colsum;
+    p.stats_in = reinterpret_cast<const float2*>(ln_stats_in);
+    p.stats_in_slots = stats_in_slots;
+    p.stats_in_stride = stats_in_stride;
+    p.stats_out = reinterpret_cast<float2*>(stats_out);
+    p.stats_out_slot0 = stats_out_slot0;
+    p.stats_out_stride = stats_out_stride;
+    if (p.ln_fold && ln_stats_in == nullptr) return ADSR_ERR_BAD_SHAPE;
+    if (stats_out != nullptr && stats_out_slot0 + 2 * n_tiles > stats_out_stride) return ADSR_ERR_BAD_SHAPE;
     // A tiles come by TMA: tensor = [M rows x K cols]; columns >= K and rows >= M are zero-filled by the hardware
     p.use_tma = 1;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda % 8)) return ADSR_ERR_BAD_ALIGN;

@@ -10,8 +10,11 @@
 namespace adsr {
 
 struct TcGemmParams {
-    CUtensorMap tmap_a;  // GEMM mode: [M rows x K cols] bf16, box 128 x 64, 128-byte swizzle (first: 64 B aligned)
-    int use_tma;         // 1 = A tiles arrive by TMA (GEMM), 0 = producer warps gather them (conv)
+    CUtensorMap tmap_a;    // GEMM mode: [M rows x K cols] bf16, box 128 x 64, 128-byte swizzle (first: 64 B aligned)
+    CUtensorMap tmap_out;  // TMA epilogue: output  [M x (ocol0 + n_store)], box 32 x 32, 64-byte swizzle
+    CUtensorMap tmap_res;  // TMA epilogue: residual [M x N], same box (columns >= N read as zero)
+    int use_tma;           // 1 = A tiles arrive by TMA (GEMM), 0 = producer warps gather them (conv)
+    int epi_tma;           // set by launch_tc_gemm: 1 = TMA epilogue, 0 = manual epilogue
     // A operand: token rows (GEMM) or NHWC image (implicit-GEMM conv)
     const __nv_bfloat16* A;
     long long lda;       // row / pixel pitch in elements (multiple of 8)
@@ -25,6 +28,19 @@ struct TcGemmParams {
     // B operand: packed weight image
     const uint8_t* Bp;
     int n_tiles, BN, m_tiles;
+    // LayerNorm folded into the GEMM: A holds RAW rows, the weights carry gamma, the epilogue applies
+    //   out = rstd_m * (acc - mean_m * colsum_n) + bias_n
+    // with (sum, sumsq) of row m read from `stats_in` (stats_in_slots partial slots per row, written by the
+    // epilogue(s) of the kernel(s) that produced A).
+    int ln_fold;          // 0 / 1
+    int ln_C;             // number of columns the statistics run over (= K)
+    float ln_eps;
+    const float* colsum;  // [n_tiles * BN]  s_n = sum_k gamma_k W_nk (of the bf16-rounded packed weights)
+    const float2* stats_in;
+    int stats_in_slots, stats_in_stride;
+    // producer side: per-row partial (sum, sumsq) of THIS kernel's output -> stats_out[row*stride + slot0 + n_tile*2 + half]
+    float2* stats_out;
+    int stats_out_slot0, stats_out_stride;
     // epilogue
     const float* bias;
     int N, n_store, act;
@@ -36,7 +52,8 @@ struct TcGemmParams {
     int ocol0, out_mode;
 };
 
-int launch_tc_gemm(const TcGemmParams& p, int num_sms, cudaStream_t stream);
+int launch_tc_gemm(TcGemmParams& p, int num_sms, cudaStream_t stream);
+int launch_tc_gemm_manual(const TcGemmParams& p, int grid, cudaStream_t stream);   // tc_gemm_manual.cu
 // Encodes the TMA descriptor of a row-major bf16 matrix (driver entry point resolved at run time).
 int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems);
 

@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(256) drct_head_kernel(const float* __restrict_
                                                          const float* __restrict__ mean, float img_range,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          float eps, int C, __nv_bfloat16* __restrict__ x0, long long ld0,
-                                                         __nv_bfloat16* __restrict__ slab, long long lds) {
+                                                         __nv_bfloat16* __restrict__ slab, long long lds,
+                                                         float2* __restrict__ stats_out, int stats_stride) {
     extern __shared__ float sw[];                 // [C][nc*9] then bias[C], gamma[C], beta[C]
     const int kk = nc * 9;
     float* sb = sw + C * kk;
@@ -295,13 +296,25 @@ __global__ void __launch_bounds__(256) drct_head_kernel(const float* __restrict_
             var += d * d;
         }
         const float rstd = rsqrtf(warp_sum(var) / static_cast<float>(C) + eps);
+        float osum = 0.f, osq = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int ch = lane + 32 * j;
             if (ch < cpad) {
                 const bool ok = ch < C;
+                const float o = ok ? (acc[j] - mu) * rstd * sg[ch] + sbt[ch] : 0.f;
                 x0[pix * ld0 + ch] = __float2bfloat16(ok ? acc[j] : 0.f);
-                slab[pix * lds + ch] = __float2bfloat16(ok ? (acc[j] - mu) * rstd * sg[ch] + sbt[ch] : 0.f);
+                slab[pix * lds + ch] = __float2bfloat16(o);
+                osum += o;
+                osq = fmaf(o, o, osq);
+            }
+        }
+        if (stats_out != nullptr) {                           // row statistics of the slab for the first folded LayerNorm
+            osum = warp_sum(osum);
+            osq = warp_sum(osq);
+            if (lane == 0) {
+                stats_out[pix * stats_stride] = make_float2(osum, osq);
+                stats_out[pix * stats_stride + 1] = make_float2(0.f, 0.f);
             }
         }
     }
@@ -437,16 +450,17 @@ extern "C" int adsr_window_reverse_unshift(const void* windows, int64_t ldw, voi
 
 extern "C" int adsr_drct_head(const float* x_nchw, int B, int nc, int H, int W, const float* weight, const float* bias,
                               const float* mean, float img_range, const float* ln_gamma, const float* ln_beta, float eps,
-                              int C, void* x0, int64_t ld0, void* slab, int64_t lds, void* stream) {
+                              int C, void* x0, int64_t ld0, void* slab, int64_t lds, float* stats_out, int stats_out_stride,
+                              void* stream) {
     if (B <= 0) return ADSR_OK;
     if (nc < 1 || nc > 3 || C <= 0 || C > 256) return ADSR_ERR_BAD_SHAPE;
     const int cpad = (C + 15) & ~15;
-    if (ld0 < cpad || lds < cpad) return ADSR_ERR_BAD_SHAPE;
+    if (ld0 < cpad || lds < cpad || (stats_out != nullptr && stats_out_stride < 2)) return ADSR_ERR_BAD_SHAPE;
     const size_t smem = (static_cast<size_t>(C) * nc * 9 + 3 * C) * sizeof(float);
     if (smem > 48 * 1024) return ADSR_ERR_BAD_SHAPE;
     drct_head_kernel<<<grid_for(static_cast<long long>(B) * H * W, 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         x_nchw, B, nc, H, W, weight, bias, mean, img_range, ln_gamma, ln_beta, eps, C, static_cast<__nv_bfloat16*>(x0), ld0,
-        static_cast<__nv_bfloat16*>(slab), lds);
+        static_cast<__nv_bfloat16*>(slab), lds, reinterpret_cast<float2*>(stats_out), stats_out_stride);
     return check_launch();
 }
 

@@ -1,20 +1,28 @@
 // tcgen05 / TMEM GEMM and implicit-GEMM 3x3 convolution for sm_100a.
 //
-// One persistent, warp-specialised kernel.  Per 128-row output tile the K dimension is streamed
-// through a 4-deep shared-memory ring; each ring stage holds
-//   * an A tile  [128 rows x 64 bf16]  (K-major, 128-byte swizzle) written by 4 producer warps that
-//     either copy token rows (GEMM) or gather the 3x3 taps of an NHWC image with zero padding
-//     (implicit GEMM: the im2col matrix is never materialised), and
-//   * a  B tile  [BN rows  x 64 bf16]  = pre-swizzled weight image fetched with ONE bulk async copy
-//     (cp.async.bulk, the TMA engine) -- weights are packed once at load time into exactly the
-//     shared-memory image the tensor core wants, so no tensor map is needed.
-// A single elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16) into one of two TMEM
-// accumulator buffers; 4 epilogue warps drain the other buffer with tcgen05.ld and apply
-// bias / activation / residual / pixel-shuffle before storing bf16.
+// One persistent, warp-specialised kernel (grid = #SMs, 16 warps).  Per 128-row output tile the K dimension is
+// streamed through a 4-deep shared-memory ring; each ring stage holds
+//   * an A tile  [128 rows x 64 bf16]  (K-major, 128-byte swizzle): in GEMM mode it arrives by TMA
+//     (cp.async.bulk.tensor, out-of-bounds K columns / M rows zero-filled by the hardware); in conv mode 4 producer
+//     warps gather the 3x3 taps of an NHWC image with zero padding (implicit GEMM, im2col never materialised), and
+//   * a  B tile  [BN rows  x 64 bf16]  = pre-swizzled weight image fetched with ONE bulk async copy per stage
+//     (weights are packed once at load time into exactly the shared-memory image the tensor core wants).
+// A single elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16, bf16 -> fp32) into one of two TMEM accumulator
+// buffers; 8 epilogue warps drain the other buffer with tcgen05.ld.  The row-owner thread does all the math in fp32
+// (folded LayerNorm, bias, GELU / LeakyReLU / ReLU, alpha, residual), rounds once to bf16 and can emit the row's
+// (sum, sum of squares) for the NEXT LayerNorm.
 //
-// Replaces (reference call sites): nn.Linear qkv/proj/fc1/fc2 (src/drct.py:278,300,185-188), the 1x1
-// adjust convs (src/drct.py:334-374, 389-393), conv_after_body / conv_before_upsample / Upsample
-// convs + PixelShuffle (src/drct.py:837,844-845,702-705) and every 3x3 conv of DRN (src/drn.py:29-32).
+// Two epilogue variants (template EPI_TMA):
+//   * TMA epilogue (row-major outputs at 16-byte aligned columns): every warp owns a double-buffered 32x32 bf16
+//     staging tile in the 64-byte-swizzle layout.  The residual tile is TMA-LOADED into it (one chunk ahead), the row
+//     owner adds it from shared memory and writes the result back in place, one lane TMA-STORES the box.  No address
+//     arithmetic, predicates or global load/store instructions in the hot loop; M / N edges are clipped by the TMA unit.
+//   * manual epilogue (PixelShuffle(2) stores, slab slices at 8-byte aligned columns): staged tile, coalesced 64-byte
+//     row segments written with ordinary stores, residual added in the write-out mapping.
+//
+// Replaces (reference call sites): nn.Linear qkv/proj/fc1/fc2 (src/drct.py:278,300,185-188) with the LayerNorms in front
+// of qkv / fc1 (src/drct.py:481,510), the 1x1 adjust convs (src/drct.py:334-374, 389-393), conv_after_body /
+// conv_before_upsample / Upsample convs + PixelShuffle (src/drct.py:837,844-845,702-705) and every 3x3 conv of DRN.
 #include "adsr_kernels.h"
 #include "ptx.cuh"
 
@@ -25,19 +33,21 @@ namespace {
 constexpr int kStages = 4;
 constexpr int kAStageBytes = 128 * 128;       // 128 rows x 64 bf16
 constexpr int kBStageBytes = 256 * 128;       // up to 256 rows x 64 bf16
-constexpr int kNumThreads = 512;              // 16 warps: B loader, MMA, TMEM alloc, spare, 8 epilogue, 4 producers
+constexpr int kNumThreads = 512;              // 16 warps: loader, MMA, TMEM alloc, spare, 8 epilogue, 4 producers
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTmemCols = 512;                // 2 accumulator buffers x 256 fp32 columns
-constexpr int kStageOutBytes = 32 * 64;       // per epilogue warp: 32 rows x 32 bf16 staging tile
+constexpr int kStageTileBytes = 32 * 64;      // 32 rows x 32 bf16 staging tile
 constexpr int kRingBytes = kStages * (kAStageBytes + kBStageBytes);
-constexpr int kSmemBytes = kRingBytes + kEpiWarps * kStageOutBytes + 2 * 256 * 4 + 256;
+constexpr int kStagingBytes = kEpiWarps * 2 * kStageTileBytes;     // double-buffered per warp
+constexpr int kSmemBytes = kRingBytes + kStagingBytes + 512 /*barriers*/;
 
 struct __align__(8) RingBarriers {
     uint64_t full[kStages];
     uint64_t empty[kStages];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
+    uint64_t res_full[kEpiWarps][2];   // residual tile of a warp's staging buffer has landed
     uint32_t tmem_base;
 };
 
@@ -62,10 +72,6 @@ __device__ __forceinline__ float apply_act(float v, float slope) {
     return v;
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -78,35 +84,60 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+// TMA store of a 2-D box from shared memory (bulk async group) and the group bookkeeping
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {      // <= N most recent groups may still be READING shared memory
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t add_bf16x2_f32(uint32_t a, uint32_t b, bool lo_ok, bool hi_ok) {
     const float l = bf16_lo(a) + (lo_ok ? bf16_lo(b) : 0.f);
     const float h = bf16_hi(a) + (hi_ok ? bf16_hi(b) : 0.f);
     return pack_bf16x2(l, h);
 }
 
-template <int ACT>
+template <int ACT, bool EPI_TMA, bool STATS>
 __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kAStageBytes;
-    uint8_t* smem_out = smem + kRingBytes;                                   // [8 warps][32 rows][64 B]
-    float* smem_bias = reinterpret_cast<float*>(smem_out + kEpiWarps * kStageOutBytes);   // [2][256]
-    RingBarriers* bars = reinterpret_cast<RingBarriers*>(smem_bias + 2 * 256);
+    uint8_t* smem_stg = smem + kRingBytes;                                   // [8 warps][2][32 rows][64 B]
+    RingBarriers* bars = reinterpret_cast<RingBarriers*>(smem_stg + kStagingBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.m_tiles * p.n_tiles;
+
+    // Tile schedule (identical in every warp role): tiles are dealt round-robin (tile = it * grid + cta) with N fastest,
+    // so the N tiles of one row block run on neighbouring CTAs at the same time and share the A tile through L2.
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+#define ADSR_TILE_COORDS(it_)                                                            \
+    const int lin_ = (it_) * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x); \
+    const int m_tile = lin_ / p.n_tiles;                                                  \
+    const int n_tile = lin_ % p.n_tiles;
 
     if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B operands need 1024 B alignment
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&bars->full[s], p.use_tma ? 1 : 128 + 1);   // (128 producer threads +) the copy issuer
-            mbar_init(&bars->empty[s], 1);         // one tcgen05.commit
+            mbar_init(&bars->empty[s], 1);                         // one tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->tmem_full[b], 1);
             mbar_init(&bars->tmem_empty[b], kEpiThreads);
+        }
+        for (int w = 0; w < kEpiWarps; ++w) {
+            mbar_init(&bars->res_full[w][0], 1);
+            mbar_init(&bars->res_full[w][1], 1);
         }
         fence_barrier_init();
     }
@@ -117,16 +148,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
-        // ================================ B loader: one bulk copy per ring stage =================
+        // ================================ loader: TMA A tile + bulk-copied B tile per ring stage =====
         if (lane == 0) {
             const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
             const uint32_t tx_bytes = b_bytes + (p.use_tma ? static_cast<uint32_t>(kAStageBytes) : 0u);
             if (p.use_tma) tma_prefetch_desc(&p.tmap_a);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.n_tiles;
-                const int m0 = (tile / p.n_tiles) * 128;
+            for (int it = 0; it < my_tiles; ++it) {
+                ADSR_TILE_COORDS(it)
+                const int m0 = m_tile * 128;
                 const uint8_t* src = p.Bp + static_cast<size_t>(n_tile) * p.num_k_stages * b_bytes;
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -144,8 +175,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
             const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.BN));
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int it = 0; it < my_tiles; ++it) {
                 const int buf = it & 1;
                 const uint32_t use = static_cast<uint32_t>(it >> 1);
                 mbar_wait(&bars->tmem_empty[buf], (use & 1) ^ 1);
@@ -175,43 +205,81 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
             }
         }
     } else if (warp >= 4 && warp < 4 + kEpiWarps) {
-        // ================================ epilogue: TMEM -> regs -> smem staging -> coalesced global ==
-        // 8 warps: quadrant q = warp & 3 owns TMEM lanes / tile rows 32q..32q+31, the two warps of a
-        // quadrant take alternate 32-column chunks.  Values are staged as bf16 in a per-warp 32x32
-        // swizzled tile so that global stores (and residual loads) are row-contiguous 64 B segments.
+        // ================================ epilogue ====================================================
+        // quadrant q = warp & 3 owns TMEM lanes / tile rows 32q..32q+31 (thread = row); the two warps of a quadrant take
+        // alternate 32-column chunks.
         const int ew = warp - 4;
         const int quad = warp & 3;
         const int half = ew >> 2;
-        const int et = threadIdx.x - 4 * 32;                   // 0..255 inside the epilogue group
-        uint8_t* stg = smem_out + ew * kStageOutBytes;
-        const uint32_t stg_w = smem_u32(stg) + static_cast<uint32_t>(lane * 64);     // my row when writing
-        const int wsw = (lane >> 1) & 3;
+        uint8_t* stg = smem_stg + ew * 2 * kStageTileBytes;    // this warp's two staging tiles
+        const int wsw = (lane >> 1) & 3;                       // 64-byte swizzle phase of my row
         const int n_chunks = (p.BN + 31) >> 5;
-        const bool st16 = (p.ocol0 & 7) == 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_tile = tile / p.n_tiles;
-            const int n_tile = tile % p.n_tiles;
+        const bool has_res = p.res != nullptr;
+        int g = 0;                                             // chunks processed by this warp (staging buffer = g & 1)
+
+        // (tile index, chunk) of the first chunk at or after (it, ch) that this warp really stores
+        auto next_chunk = [&](int it, int ch, int& it_out, int& ch_out) -> bool {
+            while (it < my_tiles) {
+                const int lin = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+                const int nb = (lin % p.n_tiles) * p.BN;
+                const int lim = min(p.n_store, nb + p.BN);
+                if (ch < n_chunks && nb + ch * 32 < lim) { it_out = it; ch_out = ch; return true; }
+                ++it;
+                ch = half;
+            }
+            return false;
+        };
+        auto issue_res_load = [&](int it, int ch, int bufi) {     // lane 0 only
+            const int lin = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+            const int mt = lin / p.n_tiles, nt = lin % p.n_tiles;
+            uint64_t* bar = &bars->res_full[ew][bufi];
+            mbar_arrive_expect_tx(bar, kStageTileBytes);
+            tma_load_2d(stg + bufi * kStageTileBytes, &p.tmap_res, nt * p.BN + ch * 32, mt * 128 + quad * 32, bar);
+        };
+        if (EPI_TMA && has_res && lane == 0) {
+            int it0, ch0;
+            if (next_chunk(0, half, it0, ch0)) issue_res_load(it0, ch0, 0);
+        }
+
+        for (int it = 0; it < my_tiles; ++it) {
+            ADSR_TILE_COORDS(it)
             const int buf = it & 1;
             const uint32_t use = static_cast<uint32_t>(it >> 1);
             const int n_base = n_tile * p.BN;
             const int n_lim = min(p.n_store, n_base + p.BN);   // never write into the next N tile's columns
-            float* bias_s = smem_bias + buf * 256;
-            if (et < p.BN) bias_s[et] = __ldg(p.bias + n_base + et);
-            named_bar_sync(1, kEpiThreads);
+            const int row0 = m_tile * 128 + quad * 32;
+            const int row = row0 + lane;                       // the row this thread owns
+            const bool row_ok = row < p.M;
+            // LayerNorm statistics of my row: partial (sum, sumsq) slots written by the producing kernel(s)
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if (p.ln_fold && row_ok) {
+                const float2* sp = p.stats_in + static_cast<long long>(row) * p.stats_in_stride;
+                float s1 = 0.f, s2 = 0.f;
+                for (int k = 0; k < p.stats_in_slots; ++k) {
+                    const float2 v = __ldg(sp + k);
+                    s1 += v.x;
+                    s2 += v.y;
+                }
+                const float inv_c = 1.0f / static_cast<float>(p.ln_C);
+                ln_mean = s1 * inv_c;
+                ln_rstd = rsqrtf(fmaxf(s2 * inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+            }
             mbar_wait(&bars->tmem_full[buf], use & 1);
             tc_fence_after_sync();
-            const int row0 = m_tile * 128 + quad * 32;
             const uint32_t taddr = tmem_base + static_cast<uint32_t>(buf * 256) + (static_cast<uint32_t>(quad * 32) << 16);
+            float st_sum = 0.f, st_sq = 0.f;
 
             for (int ch = half; ch < n_chunks; ch += 2) {
                 const int c0 = ch * 32;
                 const int n0 = n_base + c0;
-                const bool wide = c0 + 32 <= p.BN;             // BN % 32 == 16: last chunk is 16 columns
-                const bool do_store = n0 < n_lim;              // warp-uniform
-                // ---- residual prefetch in the coalesced (write-out) mapping: 4 rows-of-8 x 4 chunks
+                if (n0 >= n_lim) continue;                      // warp-uniform: nothing of this chunk is stored
+                const bool wide = c0 + 32 <= p.BN;             // BN % 32 == 16 (manual epilogue only): 16-column tail
+                uint8_t* sbuf = stg + (g & 1) * kStageTileBytes;
+                const uint32_t sbuf_row = smem_u32(sbuf) + static_cast<uint32_t>(lane * 64);
+
+                // manual epilogue: residual prefetch in the coalesced (write-out) mapping
                 uint4 rres[4];
-                if (p.res != nullptr && do_store) {
+                if (!EPI_TMA && has_res) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = row0 + i * 8 + (lane >> 2);
@@ -232,24 +300,69 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
                     for (int j = 0; j < 16; ++j) { raw[j] = lo[j]; raw[16 + j] = 0; }
                 }
                 tmem_ld_wait();
-                if (!do_store) continue;                        // warp-uniform
-                // ---- bias + activation + alpha, pack to bf16, stage
+
+                if (EPI_TMA) {
+                    if (has_res) {
+                        // prefetch the residual tile of my NEXT chunk into the other staging buffer; the store that last
+                        // used that buffer (chunk g-1) must have finished reading it
+                        if (lane == 0) {
+                            int it2, ch2;
+                            if (next_chunk(it, ch + 2, it2, ch2)) {
+                                bulk_wait_read<0>();
+                                issue_res_load(it2, ch2, (g + 1) & 1);
+                            }
+                        }
+                        mbar_wait(&bars->res_full[ew][g & 1], static_cast<uint32_t>(g >> 1) & 1);   // my residual tile landed
+                    } else {
+                        if (lane == 0) bulk_wait_read<1>();     // the store of chunk g-2 has finished reading this buffer
+                        __syncwarp();
+                    }
+                }
+
+                // ---- fp32 math per element, one rounding to bf16; logical 16-byte chunk j of my row holds columns 8j..8j+7
                 uint32_t pk[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
-                    const float v0 = apply_act<ACT>(__uint_as_float(raw[4 * j + 0]) + bb.x, p.slope) * p.alpha;
-                    const float v1 = apply_act<ACT>(__uint_as_float(raw[4 * j + 1]) + bb.y, p.slope) * p.alpha;
-                    const float v2 = apply_act<ACT>(__uint_as_float(raw[4 * j + 2]) + bb.z, p.slope) * p.alpha;
-                    const float v3 = apply_act<ACT>(__uint_as_float(raw[4 * j + 3]) + bb.w, p.slope) * p.alpha;
-                    if (p.out_mode == ADSR_OUT_ROWS) {
-                        pk[2 * j] = pack_bf16x2(v0, v1);
-                        pk[2 * j + 1] = pack_bf16x2(v2, v3);
-                    } else {
-                        // PixelShuffle(2): column 4c+sub -> staging position sub*8 + c  (8 channels per chunk)
-                        // handled below from the float values: keep them in raw[]
-                        raw[4 * j + 0] = __float_as_uint(v0); raw[4 * j + 1] = __float_as_uint(v1);
-                        raw[4 * j + 2] = __float_as_uint(v2); raw[4 * j + 3] = __float_as_uint(v3);
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t rw[4] = {0u, 0u, 0u, 0u};
+                    if (EPI_TMA && has_res) {
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3])
+                                     : "r"(sbuf_row + static_cast<uint32_t>((j ^ wsw) << 4)));
+                    }
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int q4 = 2 * j + h2;              // group of 4 columns
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * q4));   // L1-resident, warp-uniform
+                        float a[4] = {__uint_as_float(raw[4 * q4 + 0]), __uint_as_float(raw[4 * q4 + 1]),
+                                      __uint_as_float(raw[4 * q4 + 2]), __uint_as_float(raw[4 * q4 + 3])};
+                        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                        if (p.ln_fold) {                        // LN(x) W^T = rstd * (x W'^T - mean * colsum)
+                            const float4 cs = __ldg(reinterpret_cast<const float4*>(p.colsum + n0 + 4 * q4));
+                            const float cv[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) a[e] = ln_rstd * fmaf(-ln_mean, cv[e], a[e]);
+                        }
+                        float v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[e] = apply_act<ACT>(a[e] + bv[e], p.slope) * p.alpha;
+                            if (EPI_TMA && has_res) {
+                                const uint32_t w2 = rw[2 * h2 + (e >> 1)];
+                                v[e] += (e & 1) ? bf16_hi(w2) : bf16_lo(w2);
+                            }
+                            // (columns >= N need no masking: zero weight rows, zero bias / colsum and a zero-filled
+                            //  residual make them exact zeros, and act(0) = 0 for every activation used)
+                            if (STATS) { st_sum += v[e]; st_sq = fmaf(v[e], v[e], st_sq); }
+                        }
+                        if (p.out_mode == ADSR_OUT_ROWS) {
+                            pk[2 * q4] = pack_bf16x2(v[0], v[1]);
+                            pk[2 * q4 + 1] = pack_bf16x2(v[2], v[3]);
+                        } else {
+                            // PixelShuffle(2): column 4c+sub -> staging position sub*8 + c (8 channels per chunk);
+                            // permuted below from the float values kept in raw[]
+                            raw[4 * q4 + 0] = __float_as_uint(v[0]); raw[4 * q4 + 1] = __float_as_uint(v[1]);
+                            raw[4 * q4 + 2] = __float_as_uint(v[2]); raw[4 * q4 + 3] = __float_as_uint(v[3]);
+                        }
                     }
                 }
                 if (p.out_mode != ADSR_OUT_ROWS) {
@@ -262,67 +375,85 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_w + static_cast<uint32_t>((j ^ wsw) << 4)),
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sbuf_row + static_cast<uint32_t>((j ^ wsw) << 4)),
                                  "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                                  : "memory");
                 }
-                __syncwarp();
-                // ---- coalesced write-out: lane -> (row = i*8 + lane/4, 16-byte chunk = lane%4)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rl = i * 8 + (lane >> 2);
-                    const int cc = lane & 3;
-                    const uint4 val = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((cc ^ ((rl >> 1) & 3)) << 4));
-                    const int r = row0 + rl;
-                    if (r >= p.M) continue;
-                    if (p.out_mode == ADSR_OUT_ROWS) {
-                        const int col = n0 + cc * 8;
-                        if (col >= n_lim) continue;
-                        uint4 o = val;
-                        if (p.res != nullptr) {
-                            o.x = add_bf16x2_f32(val.x, rres[i].x, col + 0 < p.N, col + 1 < p.N);
-                            o.y = add_bf16x2_f32(val.y, rres[i].y, col + 2 < p.N, col + 3 < p.N);
-                            o.z = add_bf16x2_f32(val.z, rres[i].z, col + 4 < p.N, col + 5 < p.N);
-                            o.w = add_bf16x2_f32(val.w, rres[i].w, col + 6 < p.N, col + 7 < p.N);
-                        }
-                        __nv_bfloat16* dst = p.out + static_cast<long long>(r) * p.ldo + p.ocol0 + col;
-                        if (col + 8 > n_lim) {                  // n_store % 8 == 4: only the first 4 columns belong to us
-                            reinterpret_cast<uint2*>(dst)[0] = make_uint2(o.x, o.y);
-                        } else if (st16) {
-                            *reinterpret_cast<uint4*>(dst) = o;
-                        } else {                                // slab slices start at 8-byte aligned columns
-                            reinterpret_cast<uint2*>(dst)[0] = make_uint2(o.x, o.y);
-                            reinterpret_cast<uint2*>(dst)[1] = make_uint2(o.z, o.w);
-                        }
-                    } else {
-                        // staging chunk cc = sub-pixel (i2, j2); 8 channels n0/4 .. n0/4+7
-                        const int hw = p.Hout * p.Wout;
-                        const int b = r / hw;
-                        const int rem = r - b * hw;
-                        const int y = rem / p.Wout;
-                        const int x = rem - y * p.Wout;
-                        const int i2 = cc >> 1, j2 = cc & 1;
-                        __nv_bfloat16* dst = p.out +
-                            ((static_cast<long long>(b) * (2 * p.Hout) + 2 * y + i2) * (2 * p.Wout) + 2 * x + j2) * p.ldo + (n0 >> 2);
-                        *reinterpret_cast<uint4*>(dst) = val;
+
+                if (EPI_TMA) {
+                    fence_proxy_async_smem();                   // my st.shared must be visible to the TMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&p.tmap_out, sbuf, p.ocol0 + n0, row0);   // rows >= M / columns >= ocol0+n_store clipped
+                        bulk_commit();
                     }
+                } else {
+                    __syncwarp();
+                    // ---- coalesced write-out: lane -> (row = i*8 + lane/4, 16-byte chunk = lane%4)
+                    const bool st16 = (p.ocol0 & 7) == 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rl = i * 8 + (lane >> 2);
+                        const int cc = lane & 3;
+                        const uint4 val = *reinterpret_cast<const uint4*>(sbuf + rl * 64 + ((cc ^ ((rl >> 1) & 3)) << 4));
+                        const int r = row0 + rl;
+                        if (r >= p.M) continue;
+                        if (p.out_mode == ADSR_OUT_ROWS) {
+                            const int col = n0 + cc * 8;
+                            if (col >= n_lim) continue;
+                            uint4 o = val;
+                            if (has_res) {
+                                o.x = add_bf16x2_f32(val.x, rres[i].x, col + 0 < p.N, col + 1 < p.N);
+                                o.y = add_bf16x2_f32(val.y, rres[i].y, col + 2 < p.N, col + 3 < p.N);
+                                o.z = add_bf16x2_f32(val.z, rres[i].z, col + 4 < p.N, col + 5 < p.N);
+                                o.w = add_bf16x2_f32(val.w, rres[i].w, col + 6 < p.N, col + 7 < p.N);
+                            }
+                            __nv_bfloat16* dst = p.out + static_cast<long long>(r) * p.ldo + p.ocol0 + col;
+                            if (col + 8 > n_lim) {              // n_store % 8 == 4: only the first 4 columns belong to us
+                                reinterpret_cast<uint2*>(dst)[0] = make_uint2(o.x, o.y);
+                            } else if (st16) {
+                                *reinterpret_cast<uint4*>(dst) = o;
+                            } else {                            // slab slices start at 8-byte aligned columns
+                                reinterpret_cast<uint2*>(dst)[0] = make_uint2(o.x, o.y);
+                                reinterpret_cast<uint2*>(dst)[1] = make_uint2(o.z, o.w);
+                            }
+                        } else {
+                            // staging chunk cc = sub-pixel (i2, j2); 8 channels n0/4 .. n0/4+7
+                            const int hw = p.Hout * p.Wout;
+                            const int b = r / hw;
+                            const int rem = r - b * hw;
+                            const int y = rem / p.Wout;
+                            const int x = rem - y * p.Wout;
+                            const int i2 = cc >> 1, j2 = cc & 1;
+                            __nv_bfloat16* dst = p.out +
+                                ((static_cast<long long>(b) * (2 * p.Hout) + 2 * y + i2) * (2 * p.Wout) + 2 * x + j2) * p.ldo + (n0 >> 2);
+                            *reinterpret_cast<uint4*>(dst) = val;
+                        }
+                    }
+                    __syncwarp();                               // the staging tile is reused two chunks later
                 }
-                __syncwarp();                                   // staging tile is reused by the next chunk
+                ++g;
             }
+            // partial LayerNorm statistics of my row for the consumer of this output (deterministic slot, no atomics)
+            if (STATS && row_ok)
+                p.stats_out[static_cast<long long>(row) * p.stats_out_stride + p.stats_out_slot0 + n_tile * 2 + half] =
+                    make_float2(st_sum, st_sq);
             __syncwarp();
             tc_fence_before_sync();
             mbar_arrive(&bars->tmem_empty[buf]);
         }
+        if (EPI_TMA && lane == 0) bulk_wait_all();              // all my stores have left shared memory and are complete
     } else if (warp >= 4 + kEpiWarps && !p.use_tma) {
-        // ================================ A producers (4 warps, 128 threads) =========================
+        // ================================ conv mode: A producers (4 warps, 128 threads) ===============
         const int pw = warp - (4 + kEpiWarps);
         const int chunk = lane & 7;                            // 16-byte chunk inside the 128 B row
         const int rsub = pw * 4 + (lane >> 3);                 // row inside each 16-row step
         const uint32_t sw_off = static_cast<uint32_t>(rsub * 128 + ((chunk ^ (rsub & 7)) << 4));
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.n_tiles;
+        for (int it = 0; it < my_tiles; ++it) {
+            ADSR_TILE_COORDS(it)
+            (void)n_tile;
             const int m0 = m_tile * 128;
             // per-row source bookkeeping (8 rows per thread: r = step*16 + rsub)
             long long row_off[8];
@@ -392,32 +523,49 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     }
 }
 
-}  // namespace
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems) {
-    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode_fn() {
     static EncodeFn encode = nullptr;
     if (encode == nullptr) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
             qres != cudaDriverEntryPointSuccess || fn == nullptr)
-            return ADSR_ERR_CUDA;
+            return nullptr;
         encode = reinterpret_cast<EncodeFn>(fn);
     }
+    return encode;
+}
+
+int encode_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems, int box_cols,
+              int box_rows, CUtensorMapSwizzle swz) {
+    EncodeFn encode = get_encode_fn();
+    if (encode == nullptr) return ADSR_ERR_CUDA;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
-    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? ADSR_OK : ADSR_ERR_CUDA;
 }
 
-int launch_tc_gemm(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+}  // namespace
+
+int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems) {
+    return encode_2d(map, base, rows, cols, ld_elems, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// 32 x 32 bf16 boxes in the 64-byte-swizzle layout of the epilogue staging tiles (residual loads / output stores)
+int encode_tmap_epilogue_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems) {
+    return encode_2d(map, base, rows, cols, ld_elems, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+int launch_tc_gemm(TcGemmParams& p, int num_sms, cudaStream_t stream) {
     if (p.M <= 0) return ADSR_OK;
     if (p.BN < 16 || p.BN > 256 || (p.BN % 16) != 0) return ADSR_ERR_BAD_SHAPE;
     if ((p.lda % 8) != 0 || (p.ldo % 4) != 0 || (p.ocol0 % 4) != 0) return ADSR_ERR_BAD_SHAPE;
@@ -427,21 +575,42 @@ int launch_tc_gemm(const TcGemmParams& p, int num_sms, cudaStream_t stream) {
         ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldo % 8) != 0))
         return ADSR_ERR_BAD_ALIGN;
     if (p.num_k_stages <= 0 || p.n_tiles <= 0 || (p.n_store % 4) != 0) return ADSR_ERR_BAD_SHAPE;
+    if (p.ln_fold && (p.colsum == nullptr || p.stats_in == nullptr || p.ln_C <= 0 || p.stats_in_slots <= 0)) return ADSR_ERR_BAD_SHAPE;
+    if (p.stats_out != nullptr && p.out_mode != ADSR_OUT_ROWS) return ADSR_ERR_BAD_SHAPE;
     if (p.out_mode == ADSR_OUT_PIXEL_SHUFFLE2 &&
         ((p.BN % 32) != 0 || (p.ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15)))
         return ADSR_ERR_BAD_SHAPE;
-    const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = tiles < num_sms ? tiles : num_sms;
+
+    // TMA epilogue when there is a residual to add (row-major output at a 16-byte aligned column, chunks never straddle
+    // N tiles).  Without a residual the manual epilogue is faster today: with two staging tiles per warp the TMA-store
+    // latency caps the store bandwidth of wide outputs (measured 1.9 vs 2.4 TB/s on the qkv shape).
+    p.epi_tma = (p.res != nullptr && p.out_mode == ADSR_OUT_ROWS && (p.ocol0 % 8) == 0 && (p.BN % 32) == 0 &&
+                 (p.n_store % 8) == 0) ? 1 : 0;
+    if (p.epi_tma) {
+        int st = encode_tmap_epilogue_bf16(&p.tmap_out, p.out, p.M, p.ocol0 + p.n_store, p.ldo);
+        if (st != ADSR_OK) return st;
+        if (p.res != nullptr) {
+            st = encode_tmap_epilogue_bf16(&p.tmap_res, p.res, p.M, p.N, p.ldres);
+            if (st != ADSR_OK) return st;
+        }
+    } else if (p.stats_out != nullptr && p.res != nullptr) {
+        return ADSR_ERR_BAD_SHAPE;     // the manual epilogue adds the residual after the statistics are taken
+    }
+
+    const int units = p.m_tiles * p.n_tiles;
+    const int grid = units < num_sms ? units : num_sms;
     auto launch = [&](auto kernel) -> int {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return ADSR_ERR_CUDA;
         kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(p);
         return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };
+    if (!p.epi_tma) return launch_tc_gemm_manual(p, grid, stream);
+    const bool st = p.stats_out != nullptr;
     switch (p.act) {
-        case ADSR_ACT_NONE: return launch(tc_gemm_kernel<ADSR_ACT_NONE>);
-        case ADSR_ACT_LRELU: return launch(tc_gemm_kernel<ADSR_ACT_LRELU>);
-        case ADSR_ACT_GELU: return launch(tc_gemm_kernel<ADSR_ACT_GELU>);
-        case ADSR_ACT_RELU: return launch(tc_gemm_kernel<ADSR_ACT_RELU>);
+        case ADSR_ACT_NONE: return st ? launch(tc_gemm_kernel<ADSR_ACT_NONE, true, true>) : launch(tc_gemm_kernel<ADSR_ACT_NONE, true, false>);
+        case ADSR_ACT_LRELU: return st ? launch(tc_gemm_kernel<ADSR_ACT_LRELU, true, true>) : launch(tc_gemm_kernel<ADSR_ACT_LRELU, true, false>);
+        case ADSR_ACT_GELU: return st ? launch(tc_gemm_kernel<ADSR_ACT_GELU, true, true>) : launch(tc_gemm_kernel<ADSR_ACT_GELU, true, false>);
+        case ADSR_ACT_RELU: return st ? launch(tc_gemm_kernel<ADSR_ACT_RELU, true, true>) : launch(tc_gemm_kernel<ADSR_ACT_RELU, true, false>);
     }
     return ADSR_ERR_BAD_SHAPE;
 }

@@ -186,9 +186,11 @@ class DRCT(nn.Module):
                 b.adjust_out, b.last = adj.out_channels, k == 4
                 b.n1w, b.n1b, b.n2w, b.n2b = f32(sw.norm1.weight), f32(sw.norm1.bias), f32(sw.norm2.weight), f32(sw.norm2.bias)
                 b.table = f32(sw.attn.relative_position_bias_table)
-                b.qkv = pack.pack_qkv_weight(sw.attn.qkv.weight, sw.attn.qkv.bias, b.heads)
+                b.qkv = pack.pack_qkv_weight(sw.attn.qkv.weight, sw.attn.qkv.bias, b.heads, sw.norm1.weight, sw.norm1.bias,
+                                             sw.norm1.eps)
                 b.proj = pack.pack_proj_weight(sw.attn.proj.weight, sw.attn.proj.bias, b.heads)
-                b.fc1 = pack.pack_gemm_weight(sw.mlp.fc1.weight, sw.mlp.fc1.bias)
+                b.fc1 = pack.pack_ln_gemm_weight(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias,
+                                                 sw.norm2.eps)
                 b.fc2 = pack.pack_gemm_weight(sw.mlp.fc2.weight, sw.mlp.fc2.bias)
                 b.adjust = pack.pack_gemm_weight(adj.weight, adj.bias)
                 blocks.append(b)
@@ -230,6 +232,9 @@ class DRCT(nn.Module):
             "z": torch.zeros(M, pitch, **bf), "qkv": torch.zeros(M, qkv_w, **bf), "att": torch.zeros(M, att_w, **bf),
             "h": torch.zeros(M, hid_w, **bf), "x0": torch.zeros(M, e16, **bf), "body": torch.zeros(M, e16, **bf),
             "f": torch.zeros(M, 64, **bf),
+            # per-row (sum, sumsq) partials for the folded LayerNorms: slab = x (2 slots) + x1..x4 (2 slots each); y = proj
+            "st_slab": torch.zeros(M, 10, 2, dtype=torch.float32, device=dev),
+            "st_y": torch.zeros(M, 8, 2, dtype=torch.float32, device=dev),
         }
         ups, m = [], M
         for _ in range(int(math.log2(self.upscale))):
@@ -268,25 +273,27 @@ class DRCT(nn.Module):
         D = self.embed_dim
 
         # (x - mean)*img_range -> conv_first -> x0 ; patch_embed.norm(x0) -> slab[:, :D]
-        ops.drct_head(x, P["cf_w"], P["cf_b"], P["mean"], float(self.img_range), P["pe_w"], P["pe_b"], D, ws["x0"], slab)
+        st_slab, st_y = ws["st_slab"], ws["st_y"]
+        ops.drct_head(x, P["cf_w"], P["cf_b"], P["mean"], float(self.img_range), P["pe_w"], P["pe_b"], D, ws["x0"], slab,
+                      stats_out=st_slab)
 
         for blocks in P["blocks"]:
-            for b in blocks:
+            for k, b in enumerate(blocks):
                 C = b.dim
-                # ---- W-MSA / SW-MSA half (src/drct.py:478-509)
-                ops.layernorm_rows(slab, ln, b.n1w, b.n1b, C)
-                ops.tc_gemm(ln, C, b.qkv, qkv)
+                # ---- W-MSA / SW-MSA half (src/drct.py:478-509); norm1 is folded into the qkv GEMM, its row statistics
+                #      are the partial sums the producing epilogues left in st_slab (x: 2 slots, each x_j: 2 slots)
+                ops.tc_gemm(slab, C, b.qkv, qkv, stats_in=(st_slab, 2 * (k + 1)))
                 ops.window_attention(qkv, att, b.table, B, H, W, b.ws, b.shift, b.heads, b.hd, b.hdp)
-                ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab)
-                # ---- MLP half (src/drct.py:510, 185-189)
-                ops.layernorm_rows(y, ln, b.n2w, b.n2b, C)
-                ops.tc_gemm(ln, C, b.fc1, hb, act=ops.ACT_GELU)
+                ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0))
+                # ---- MLP half (src/drct.py:510, 185-189); norm2 folded into fc1
+                ops.tc_gemm(y, C, b.fc1, hb, act=ops.ACT_GELU, stats_in=(st_y, 2 * b.proj.n_tiles))
                 ops.tc_gemm(hb, b.hidden, b.fc2, z, res=y)
                 # ---- adjust 1x1 conv (+LeakyReLU 0.2) into the slab slice / 0.2*x5 + x  (src/drct.py:389-396)
                 if not b.last:
-                    ops.tc_gemm(z, C, b.adjust, slab, act=ops.ACT_LRELU, slope=0.2, ocol0=C, n_store=b.adjust_out)
+                    ops.tc_gemm(z, C, b.adjust, slab, act=ops.ACT_LRELU, slope=0.2, ocol0=C, n_store=b.adjust_out,
+                                stats_out=(st_slab, 2 + 2 * k))
                 else:
-                    ops.tc_gemm(z, C, b.adjust, slab, alpha=0.2, res=slab)
+                    ops.tc_gemm(z, C, b.adjust, slab, alpha=0.2, res=slab, stats_out=(st_slab, 0))
 
         # final norm -> conv_after_body + x0 -> conv_before_upsample + LeakyReLU(0.01) -> upsample -> conv_last
         ops.layernorm_rows(slab, ln, P["norm_w"], P["norm_b"], D)

@@ -43,15 +43,26 @@ def _cuda(t: torch.Tensor, name: str) -> None:
 
 def tc_gemm(a: torch.Tensor, k: int, w: PackedWeight, out: torch.Tensor, *, act: int = ACT_NONE, slope: float = 0.0,
             alpha: float = 1.0, res: Optional[torch.Tensor] = None, ocol0: int = 0, n_store: Optional[int] = None,
-            m: Optional[int] = None) -> None:
-    """out[:, ocol0:ocol0+n_store] = alpha * act(a[:, :k] @ W^T + b) (+ res[:, :N])."""
+            m: Optional[int] = None, stats_in: Optional[tuple] = None, stats_out: Optional[tuple] = None) -> None:
+    """out[:, ocol0:ocol0+n_store] = alpha * act(a[:, :k] @ W^T + b) (+ res[:, :N]).
+
+    If `w` was packed with pack_ln_gemm_weight the rows of `a` are layer-normalised over their first k columns on the fly;
+    their (sum, sumsq) come from stats_in = (fp32 tensor [M, S, 2], number of leading slots to add up).
+    stats_out = (fp32 tensor [M, S, 2], first slot) makes this call write such partials for ITS output rows
+    (slots first .. first + 2*n_tiles - 1)."""
     _cuda(a, "a")
     m = a.shape[0] if m is None else m
     n_store = (w.N + 15) // 16 * 16 if n_store is None else n_store
+    if (w.colsum is not None) != (stats_in is not None):
+        raise ValueError("LayerNorm-folded weights need stats_in (and only they do)")
+    si_t, si_n = stats_in if stats_in is not None else (None, 0)
+    so_t, so_0 = stats_out if stats_out is not None else (None, 0)
     _t = _begin()
     check(lib().adsr_tc_gemm_bf16(ptr(a), a.stride(0), m, k, ptr(w.data), ptr(w.bias), w.N, w.BN, w.n_tiles, act, slope,
                                   alpha, ptr(res), res.stride(0) if res is not None else 0, ptr(out), out.stride(0), ocol0,
-                                  n_store, _abi.num_sms(), stream_ptr()), "adsr_tc_gemm_bf16")
+                                  n_store, ptr(w.colsum), w.ln_eps, ptr(si_t), si_n, si_t.shape[1] if si_t is not None else 0,
+                                  ptr(so_t), so_0, so_t.shape[1] if so_t is not None else 0, _abi.num_sms(), stream_ptr()),
+          "adsr_tc_gemm_bf16")
     _count("tc_gemm", 2.0 * m * k * w.N, _t)
 
 
@@ -115,12 +126,13 @@ def window_reverse_unshift(windows: torch.Tensor, x: torch.Tensor, b, h, w, c, w
 
 
 def drct_head(x: torch.Tensor, weight, bias, mean, img_range: float, gamma, beta, c: int, x0: torch.Tensor,
-              slab: torch.Tensor, eps: float = 1e-5) -> None:
+              slab: torch.Tensor, eps: float = 1e-5, stats_out: Optional[torch.Tensor] = None) -> None:
     _cuda(x, "x")
     b, nc, h, w = x.shape
     _t = _begin()
     check(lib().adsr_drct_head(ptr(x), b, nc, h, w, ptr(weight), ptr(bias), ptr(mean), img_range, ptr(gamma), ptr(beta), eps,
-                               c, ptr(x0), x0.stride(0), ptr(slab), slab.stride(0), stream_ptr()), "adsr_drct_head")
+                               c, ptr(x0), x0.stride(0), ptr(slab), slab.stride(0), ptr(stats_out),
+                               stats_out.shape[1] if stats_out is not None else 0, stream_ptr()), "adsr_drct_head")
     _count("drct_head", 2.0 * b * h * w * 9 * nc * c, _t)
 
 

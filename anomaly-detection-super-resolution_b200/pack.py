@@ -23,22 +23,32 @@ def round_up(x: int, m: int) -> int:
 
 
 def choose_bn(n: int) -> tuple[int, int]:
-    """(BN, n_tiles): BN multiple of 16, <= 256, minimal padding."""
-    n16 = round_up(n, 16)
-    n_tiles = (n16 + 255) // 256
-    bn = round_up((n16 + n_tiles - 1) // n_tiles, 16)
-    return bn, n_tiles
+    """(BN, n_tiles): BN a multiple of 32 (epilogue chunks of 32 columns never straddle N tiles), <= 256, and the
+    (n_tiles, BN) pair with the least padded columns, each extra tile being charged like 40 padded columns (per-tile
+    epilogue overhead, narrower MMAs)."""
+    best = None
+    t0 = (n + 255) // 256
+    for n_tiles in range(t0, t0 + 3):
+        bn = round_up((n + n_tiles - 1) // n_tiles, 32)
+        if bn > 256:
+            continue
+        cand = (bn * n_tiles + 40 * n_tiles, n_tiles, bn)
+        if best is None or cand < best:
+            best = cand
+    return best[2], best[1]
 
 
 @dataclass
 class PackedWeight:
     data: torch.Tensor        # uint8 [n_tiles * k_stages * BN * 128]
     bias: torch.Tensor        # fp32 [n_tiles * BN]
-    N: int                    # logical output columns
-    K: int                    # logical K (GEMM) or Cin (conv)
-    BN: int
-    n_tiles: int
-    k_stages: int
+    colsum: Optional[torch.Tensor] = None   # fp32 [n_tiles * BN]: LayerNorm-folded weights only (sum_k gamma_k W_nk)
+    ln_eps: float = 1e-5
+    N: int = 0                # logical output columns
+    K: int = 0                # logical K (GEMM) or Cin (conv)
+    BN: int = 0
+    n_tiles: int = 0
+    k_stages: int = 0
 
 
 def _swizzle_tiles(w2d: torch.Tensor, bn: int, n_tiles: int) -> tuple[torch.Tensor, int]:
@@ -72,7 +82,23 @@ def pack_gemm_weight(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> Pack
     w2 = torch.zeros(n, kpad, dtype=torch.float32, device=w.device)
     w2[:, :k] = w
     data, ks = _swizzle_tiles(w2, bn, n_tiles)
-    return PackedWeight(data, _pad_bias(bias, n, bn * n_tiles, w.device), n, k, bn, n_tiles, ks)
+    return PackedWeight(data, _pad_bias(bias, n, bn * n_tiles, w.device), N=n, K=k, BN=bn, n_tiles=n_tiles, k_stages=ks)
+
+
+def pack_ln_gemm_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+                        eps: float = 1e-5) -> PackedWeight:
+    """Linear applied to LayerNorm(x) with the normalisation folded into the GEMM:
+         LN(x) W^T + b = rstd * (x (gamma*W)^T - mean * s) + t,   s_n = sum_k gamma_k W_nk,   t_n = sum_k beta_k W_nk + b_n.
+    The kernel multiplies RAW rows with the packed gamma*W and applies mean / rstd / s / t in its epilogue; s is taken from
+    the bf16-rounded packed weights so that the subtraction cancels exactly what the tensor core accumulated."""
+    w = weight.detach().float().reshape(weight.shape[0], -1)
+    wg = w * gamma.detach().float()[None, :]
+    t = w @ beta.detach().float() + (bias.detach().float() if bias is not None else 0.0)
+    pw = pack_gemm_weight(wg, t)
+    s = wg.to(torch.bfloat16).float().sum(dim=1)
+    pw.colsum = _pad_bias(s, w.shape[0], pw.BN * pw.n_tiles, w.device)
+    pw.ln_eps = float(eps)
+    return pw
 
 
 def pack_conv3x3_weight(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedWeight:
@@ -84,14 +110,15 @@ def pack_conv3x3_weight(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> P
     w2 = torch.zeros(cout, 9, spt * 64, dtype=torch.float32, device=w.device)
     w2[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
     data, ks = _swizzle_tiles(w2.reshape(cout, 9 * spt * 64), bn, n_tiles)
-    return PackedWeight(data, _pad_bias(bias, cout, bn * n_tiles, w.device), cout, cin, bn, n_tiles, ks)
+    return PackedWeight(data, _pad_bias(bias, cout, bn * n_tiles, w.device), N=cout, K=cin, BN=bn, n_tiles=n_tiles, k_stages=ks)
 
 
 def head_pad(hd: int) -> int:
     return round_up(hd, 16)
 
 
-def pack_qkv_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: int) -> PackedWeight:
+def pack_qkv_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: int, gamma: Optional[torch.Tensor] = None,
+                    beta: Optional[torch.Tensor] = None, eps: float = 1e-5) -> PackedWeight:
     """qkv Linear [3C, C] -> rows regrouped as q|k|v blocks of `heads` heads, each padded to head_pad(hd)
     rows (zero weights and bias), the layout adsr_window_attention reads."""
     w = weight.detach().float()
@@ -103,6 +130,8 @@ def pack_qkv_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: i
     b3 = torch.zeros(3, heads, hdp, dtype=torch.float32, device=w.device)
     if bias is not None:
         b3[:, :, :hd] = bias.detach().float().view(3, heads, hd)
+    if gamma is not None:                       # norm1 folded into the qkv GEMM
+        return pack_ln_gemm_weight(w3.view(3 * heads * hdp, c), b3.view(-1), gamma, beta, eps)
     return pack_gemm_weight(w3.view(3 * heads * hdp, c), b3.view(-1))
 
 

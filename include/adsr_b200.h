@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 2
+#define ADSR_ABI_VERSION 4
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -48,12 +48,20 @@ int adsr_device_check(int* host_num_sms);
 /* ---- tcgen05 GEMM: out = alpha * act(A[M,K] * W^T + bias) + res ------------------------------------
  * replaces nn.Linear qkv / proj / fc1 / fc2 (src/drct.py:278, 300, 185-188) and the 1x1 `adjust` convs
  * with their LeakyReLU / 0.2*x5 + x epilogues (src/drct.py:334-374, 389-396).
- * w_packed / bias_padded come from pack.pack_gemm_weight(): n_tiles tiles of BN rows, K padded to 64. */
+ * w_packed / bias_padded come from pack.pack_gemm_weight(): n_tiles tiles of BN rows, K padded to 64.
+ * ln_colsum != NULL fuses the preceding nn.LayerNorm(K, eps=ln_eps) (norm1 / norm2, src/drct.py:432, 438, 481, 510):
+ * A then holds the RAW rows, w_packed carries gamma (pack.pack_ln_gemm_weight), bias_padded carries beta W^T + b,
+ * ln_colsum[n] = sum_k gamma_k W[n,k]; row mean / rstd come from ln_stats_in: per row `stats_in_stride` (sum, sumsq)
+ * float pairs of which the first `stats_in_slots` are added up.
+ * stats_out != NULL makes THIS call emit such partials for its own output rows (over the N valid columns, after
+ * bias / activation / alpha / residual): slot = stats_out_slot0 + 2 * n_tile + {0,1}; needs slot0 + 2*n_tiles <= stride. */
 int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K,
                       const void* w_packed, const float* bias_padded, int N, int BN, int n_tiles,
                       int act, float slope, float alpha,
                       const void* res, int64_t ldres,
                       void* out, int64_t ldo, int ocol0, int n_store,
+                      const float* ln_colsum, float ln_eps, const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
+                      float* stats_out, int stats_out_slot0, int stats_out_stride,
                       int num_sms, void* stream);
 
 /* ---- tcgen05 implicit-GEMM 3x3 convolution (pad 1, stride 1|2) on NHWC bf16 -------------------------
@@ -95,11 +103,13 @@ int adsr_window_reverse_unshift(const void* windows, int64_t ldw, void* x, int64
                                 int B, int H, int W, int C, int ws, int shift, void* stream);
 
 /* ---- DRCT head: (x - mean)*img_range -> conv_first 3x3 -> x0 (long skip) and LayerNorm(x0) -> slab -------
- * src/drct.py:887-892, 650-654 (patch_embed.norm).  x: fp32 NCHW, weights fp32 [C, nc, 3, 3]. */
+ * src/drct.py:887-892, 650-654 (patch_embed.norm).  x: fp32 NCHW, weights fp32 [C, nc, 3, 3].
+ * stats_out (optional): (sum, sumsq) of each slab row in slot 0 and zeros in slot 1, for the first folded LayerNorm. */
 int adsr_drct_head(const float* x_nchw, int B, int nc, int H, int W,
                    const float* weight, const float* bias, const float* mean, float img_range,
                    const float* ln_gamma, const float* ln_beta, float eps, int C,
-                   void* x0, int64_t ld0, void* slab, int64_t lds, void* stream);
+                   void* x0, int64_t ld0, void* slab, int64_t lds,
+                   float* stats_out, int stats_out_stride, void* stream);
 
 /* ---- DRCT tail: conv_last 3x3 (Cin -> nc) + x/img_range + mean, fused uint8 truncation ------------------
  * src/drct.py:895-897 and the quantisation of src/evaluate.py:212-215

@@ -124,3 +124,57 @@ def test_conv_upsample_pixelshuffle():
 def test_conv_stride2_and_odd_sizes():
     _conv_case(2, 32, 32, 80, 80, stride=2, seed=5)
     _conv_case(3, 20, 12, 16, 32, seed=6)        # M not a multiple of 128, tiles straddle images
+
+
+def _row_stats(t: torch.Tensor, slots: int) -> torch.Tensor:
+    """(sum, sumsq) of each row in slot 0, zeros elsewhere: what a producing epilogue leaves behind."""
+    st = torch.zeros(t.shape[0], slots, 2, device=t.device)
+    st[:, 0, 0] = t.float().sum(1)
+    st[:, 0, 1] = (t.float() ** 2).sum(1)
+    return st
+
+
+@pytest.mark.parametrize("K,N,act", [(180, 576, "none"), (212, 424, "gelu"), (308, 960, "none"), (60, 120, "gelu")])
+def test_gemm_with_folded_layernorm(K, N, act):
+    """LayerNorm(K) folded into the GEMM: raw rows in, row statistics from the (sum, sumsq) slots."""
+    ops, pack = mod("ops"), mod("pack")
+    torch.manual_seed(K + N)
+    M = 128 * 150 + 37
+    a = torch.full((M, 320), 50.0, device=DEV, dtype=torch.bfloat16)          # columns >= K must not influence anything
+    a[:, :K] = (torch.randn(M, K, device=DEV) * 2.5 + 1.5 * torch.randn(M, 1, device=DEV)).to(torch.bfloat16)
+    w, b = torch.randn(N, K, device=DEV) * 0.1, torch.randn(N, device=DEV)
+    g, bt = torch.rand(K, device=DEV) + 0.5, torch.randn(K, device=DEV) * 0.3
+    pw = pack.pack_ln_gemm_weight(w, b, g, bt, 1e-5)
+    st = _row_stats(a[:, :K], 4)
+    st[:, 1] = st[:, 0] * 0.25                                                  # statistics split over two slots
+    st[:, 0] = st[:, 0] * 0.75
+    out = torch.zeros(M, 1024, device=DEV, dtype=torch.bfloat16)
+    ops.tc_gemm(a, K, pw, out, act=ops.ACT_GELU if act == "gelu" else ops.ACT_NONE, stats_in=(st, 2))
+    torch.cuda.synchronize()
+    want = F.linear(F.layer_norm(a[:, :K].float(), (K,), g, bt, 1e-5), w, b)
+    if act == "gelu":
+        want = F.gelu(want)
+    err = rel_err(out[:, :N], want)
+    assert err < 0.015, f"LN-folded GEMM K={K} N={N}: rel err {err}"
+
+
+@pytest.mark.parametrize("N,res", [(32, False), (180, True), (308, True)])
+def test_gemm_emits_row_statistics(N, res):
+    """stats_out: per-row (sum, sumsq) partials of the stored output, in deterministic slots."""
+    ops, pack = mod("ops"), mod("pack")
+    torch.manual_seed(N)
+    M, K = 1000, 244
+    a = torch.randn(M, 256, device=DEV).to(torch.bfloat16)
+    w, b = torch.randn(N, K, device=DEV) * 0.1, torch.randn(N, device=DEV)
+    pw = pack.pack_gemm_weight(w, b)
+    r = torch.randn(M, 320, device=DEV).to(torch.bfloat16) if res else None
+    out = torch.zeros(M, 320, device=DEV, dtype=torch.bfloat16)
+    st = torch.full((M, 10, 2), 7.0, device=DEV)
+    ops.tc_gemm(a, K, pw, out, res=r, stats_out=(st, 2))
+    torch.cuda.synchronize()
+    used = 2 * pw.n_tiles
+    got = st[:, 2:2 + used].sum(1)
+    o = out[:, :N].float()
+    assert (got[:, 0] - o.sum(1)).abs().max() < 0.02 * o.abs().sum(1).max() / N ** 0.5 + 0.05
+    assert ((got[:, 1] - (o ** 2).sum(1)).abs() / (o ** 2).sum(1)).max() < 0.01
+    assert float((st[:, :2] - 7).abs().max()) == 0.0 and float((st[:, 2 + used:] - 7).abs().max()) == 0.0

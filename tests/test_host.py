@@ -33,7 +33,7 @@ def test_choose_bn():
     pack = importlib.import_module(PKG + ".pack")
     for n in (3, 32, 64, 180, 212, 256, 276, 308, 360, 424, 488, 576, 768, 864, 960):
         bn, nt = pack.choose_bn(n)
-        assert bn % 16 == 0 and 16 <= bn <= 256 and bn * nt >= n and bn * (nt - 1) < n + 16 * nt
+        assert bn % 32 == 0 and 32 <= bn <= 256 and bn * nt >= n and bn * (nt - 1) < n
 
 
 def test_pack_gemm_layout_roundtrip():
@@ -41,7 +41,7 @@ def test_pack_gemm_layout_roundtrip():
     torch.manual_seed(0)
     w = torch.randn(40, 100)
     pw = pack.pack_gemm_weight(w, torch.arange(40.0))
-    assert pw.BN == 48 and pw.n_tiles == 1 and pw.k_stages == 2
+    assert pw.BN == 64 and pw.n_tiles == 1 and pw.k_stages == 2
     img = pw.data.view(torch.bfloat16).view(pw.n_tiles, pw.k_stages, pw.BN, 8, 8)
     wb = w.to(torch.bfloat16)
     for (r, k) in [(0, 0), (5, 17), (39, 99), (13, 64), (7, 63)]:
