@@ -66,6 +66,22 @@ def tc_gemm(a: torch.Tensor, k: int, w: PackedWeight, out: torch.Tensor, *, act:
     _count("tc_gemm", 2.0 * m * k * w.N, _t)
 
 
+def swin_mlp(y: torch.Tensor, c: int, pm, z: torch.Tensor, stats_in: tuple, m: Optional[int] = None) -> None:
+    """z[:, :c] = y + fc2(GELU(fc1(LayerNorm(y[:, :c]))))  -- one fused kernel (csrc/swin_mlp.cu); `pm` from
+    pack.pack_swin_mlp, stats_in = (fp32 [M, S, 2] partial (sum, sumsq) of the rows of y, slots to add up)."""
+    _cuda(y, "y")
+    _cuda(z, "z")
+    if y.data_ptr() == z.data_ptr():
+        raise ValueError("swin_mlp: y and z must not alias")
+    m = y.shape[0] if m is None else m
+    si_t, si_n = stats_in
+    _t = _begin()
+    check(lib().adsr_swin_mlp_bf16(ptr(y), y.stride(0), m, c, ptr(pm.data), ptr(pm.bias1), ptr(pm.colsum1), ptr(pm.bias2),
+                                   pm.plan.data_ptr(), pm.plan.numel(), pm.ln_eps, ptr(si_t), si_n, si_t.shape[1],
+                                   ptr(z), z.stride(0), _abi.num_sms(), stream_ptr()), "adsr_swin_mlp_bf16")
+    _count("swin_mlp", 4.0 * m * pm.C * pm.H, _t)
+
+
 def conv3x3(x: torch.Tensor, b: int, h: int, wd: int, cin: int, w: PackedWeight, out: torch.Tensor, *, stride: int = 1,
             act: int = ACT_NONE, slope: float = 0.0, alpha: float = 1.0, res: Optional[torch.Tensor] = None,
             out_mode: int = OUT_ROWS, n_store: Optional[int] = None, ocol0: int = 0) -> None:

@@ -144,3 +144,115 @@ def pack_proj_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: 
     w2 = torch.zeros(w.shape[0], heads, hdp, dtype=torch.float32, device=w.device)
     w2[:, :, :hd] = w.view(w.shape[0], heads, hd)
     return pack_gemm_weight(w2.view(w.shape[0], heads * hdp), bias)
+
+
+# ------------------------------------------------------------------------------------------------ fused Swin MLP
+MLP_STAGE_FIRST, MLP_STAGE_ACC1_DONE, MLP_STAGE_ACC2_DONE, MLP_STAGE_WAIT_H = 1, 2, 4, 8
+_SMEM_LIMIT = 232448            # 227 KB of shared memory per CTA
+_MLP_CONST_BYTES = (2 * 512 + 320) * 4 + 232   # bias1 / colsum1 / bias2 caches + barriers (swin_mlp.cu)
+
+
+@dataclass
+class PackedMlp:
+    data: torch.Tensor        # uint8: weight slabs [rows x 64 bf16], 128-byte swizzle, in schedule order
+    bias1: torch.Tensor       # fp32 [nc * hc]
+    colsum1: torch.Tensor     # fp32 [nc * hc]
+    bias2: torch.Tensor       # fp32 [n2]
+    plan: torch.Tensor        # int32 (host): see include/adsr_b200.h, adsr_swin_mlp_bf16
+    ln_eps: float
+    C: int
+    H: int
+
+
+def swin_mlp_plan(c: int, h: int) -> dict:
+    """Static tiling of one fused MLP (swin_mlp.cu): hidden chunks of <= 128 columns (two fp32 chunk accumulators plus the
+    fc2 accumulator must fit the 512 TMEM columns), fc2 output split into pieces of >= 128 rows when it is wider than 255,
+    and the slab schedule in the order the MMA warp consumes it (fc1 of chunk j+1 is issued before fc2 of chunk j)."""
+    n2 = round_up(c, 16)
+    k1steps = (c + 15) // 16
+    ks1 = (c + 63) // 64
+    hc_max = min(128, ((512 - n2) // 2) // 16 * 16)
+    nc = (h + hc_max - 1) // hc_max
+    hc = round_up((h + nc - 1) // nc, 16)
+    widths = [hc] * (nc - 1) + [round_up(h - hc * (nc - 1), 16)]
+    if n2 >= 256:
+        p0 = round_up(n2 // 2, 16)
+        pieces = [(0, p0), (p0, n2 - p0)]
+    else:
+        pieces = [(0, n2)]
+    slot_bytes = round_up(max(hc, max(r for _, r in pieces)) * 128, 1024)
+    n_slots = min(8, (_SMEM_LIMIT - 2 * ks1 * 16384 - _MLP_CONST_BYTES) // slot_bytes)
+    if n_slots < 2 or nc > 8 or n2 > 320 or nc * hc > 512:
+        raise ValueError(f"fused MLP does not fit: C={c} H={h}")
+    stages = []   # (bytes, rows, ksteps, kind, chunk, kidx, dcol, flags)
+
+    def fc1(j):
+        for s in range(ks1):
+            fl = (MLP_STAGE_FIRST if s == 0 else 0) | (MLP_STAGE_ACC1_DONE if s == ks1 - 1 else 0)
+            stages.append((widths[j] * 128, widths[j], min(4, k1steps - 4 * s), 0, j, s, 0, fl))
+
+    def fc2(j):
+        ksl = (widths[j] + 63) // 64
+        for s in range(ksl):
+            for pi, (dcol, rows) in enumerate(pieces):
+                fl = (MLP_STAGE_WAIT_H if (s == 0 and pi == 0) else 0) | (MLP_STAGE_FIRST if (j == 0 and s == 0) else 0)
+                if j == nc - 1 and s == ksl - 1 and pi == len(pieces) - 1:
+                    fl |= MLP_STAGE_ACC2_DONE
+                stages.append((rows * 128, rows, min(4, widths[j] // 16 - 4 * s), 1, j, s, dcol, fl))
+
+    fc1(0)
+    for j in range(nc):
+        if j + 1 < nc:
+            fc1(j + 1)
+        fc2(j)
+    return dict(ks1=ks1, nc=nc, hc=hc, n2=n2, widths=widths, pieces=pieces, slot_bytes=slot_bytes, n_slots=n_slots,
+                acc1_col=(n2, n2 + hc), stages=stages)
+
+
+def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
+    """[rows, 64] fp32 -> uint8 image, row r at r*128 B with its 16-byte chunk c at position c ^ (r % 8)."""
+    rows = block.shape[0]
+    t = block.to(torch.bfloat16).view(rows, 8, 8)
+    r = torch.arange(rows, device=block.device)
+    pos = torch.arange(8, device=block.device)
+    src = (pos[None, :] ^ (r[:, None] % 8))[:, :, None].expand(rows, 8, 8)
+    return torch.gather(t, 1, src).contiguous().view(torch.uint8).reshape(-1)
+
+
+def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b) -> PackedMlp:
+    """norm2 + fc1 + GELU + fc2 of one Swin block (src/drct.py:438-441, 173-190) for adsr_swin_mlp_bf16: gamma folded into
+    fc1 (pack_ln_gemm_weight's algebra), the 0.5 of GELU folded into fc2 (exact in bf16)."""
+    w1 = fc1_w.detach().float()
+    w2 = fc2_w.detach().float() * 0.5
+    h, c = w1.shape
+    dev = w1.device
+    pl = swin_mlp_plan(c, h)
+    hc, nc, n2 = pl["hc"], pl["nc"], pl["n2"]
+    w1g = torch.zeros(nc * hc, pl["ks1"] * 64, device=dev)
+    w1g[:h, :c] = w1 * gamma.detach().float()[None, :]
+    w2p = torch.zeros(n2, nc * hc + 64, device=dev)
+    w2p[:c, :h] = w2
+    bias1 = torch.zeros(nc * hc, device=dev)
+    bias1[:h] = w1 @ beta.detach().float() + (fc1_b.detach().float() if fc1_b is not None else 0.0)
+    colsum1 = w1g.to(torch.bfloat16).float().sum(dim=1)
+    bias2 = torch.zeros(n2, device=dev)
+    if fc2_b is not None:
+        bias2[:c] = fc2_b.detach().float()
+    slabs = []
+    for (_bytes, rows, _ks, kind, j, s, dcol, _fl) in pl["stages"]:
+        if kind == 0:
+            blk = w1g[j * hc:j * hc + rows, 64 * s:64 * s + 64]
+        else:
+            k0 = j * hc + 64 * s
+            blk = w2p[dcol:dcol + rows, k0:k0 + 64].clone()
+            valid = pl["widths"][j] - 64 * s          # hidden columns of this slab that belong to chunk j
+            if valid < 64:
+                blk[:, valid:] = 0.0
+        slabs.append(_swizzle_slab(blk.contiguous()))
+    plan = [pl["ks1"], nc, hc, n2, pl["acc1_col"][0], pl["acc1_col"][1], pl["n_slots"], pl["slot_bytes"]]
+    plan += pl["widths"] + [0] * (8 - nc)
+    plan += [len(pl["stages"])]
+    for st in pl["stages"]:
+        plan += list(st)
+    return PackedMlp(torch.cat(slabs).contiguous(), bias1, colsum1, bias2, torch.tensor(plan, dtype=torch.int32),
+                     float(eps), c, h)

@@ -1,0 +1,60 @@
+"""GPU parity of the fused Swin MLP kernel (norm2 + fc1 + GELU + fc2 + residual, csrc/swin_mlp.cu) against fp32 torch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_common import mod, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _mlp_case(M, C, H, seed=0):
+    ops, pack = mod("ops"), mod("pack")
+    torch.manual_seed(seed)
+    ld = 320
+    y = torch.full((M, ld), 5.0, device=DEV, dtype=torch.bfloat16)            # poison beyond C
+    y[:, :C] = (torch.randn(M, C, device=DEV) * 1.5 + 0.3).to(torch.bfloat16)
+    z = torch.full((M, ld), -7.0, device=DEV, dtype=torch.bfloat16)
+    w1 = torch.randn(H, C, device=DEV) * 0.08
+    b1 = torch.randn(H, device=DEV) * 0.2
+    w2 = torch.randn(C, H, device=DEV) * 0.08
+    b2 = torch.randn(C, device=DEV) * 0.2
+    gamma = 1.0 + 0.2 * torch.randn(C, device=DEV)
+    beta = 0.1 * torch.randn(C, device=DEV)
+    pm = pack.pack_swin_mlp(w1, b1, gamma, beta, 1e-5, w2, b2)
+    yf = y[:, :C].float()
+    stats = torch.zeros(M, 3, 2, device=DEV)                                  # two partial slots + one unused
+    half = C // 2
+    stats[:, 0, 0], stats[:, 0, 1] = yf[:, :half].sum(1), (yf[:, :half] ** 2).sum(1)
+    stats[:, 1, 0], stats[:, 1, 1] = yf[:, half:].sum(1), (yf[:, half:] ** 2).sum(1)
+    stats[:, 2] = 1e9
+    ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2))
+    torch.cuda.synchronize()
+    want = yf + F.linear(F.gelu(F.linear(F.layer_norm(yf, (C,), gamma, beta, 1e-5), w1, b1)), w2, b2)
+    err = rel_err(z[:, :C], want)
+    assert err < 0.012, f"M={M} C={C} H={H}: rel err {err}"
+    # the TMA store clips at the tensor-map width C rounded up to a 16-byte chunk: pad columns inside that chunk receive
+    # exact zeros (zero weight rows, zero bias, zero-filled residual), everything beyond stays untouched
+    c8 = (C + 7) // 8 * 8
+    tail = z[:, C:c8].float()
+    assert bool(((tail == 0.0) | (tail == -7.0)).all()), "pad columns must be zero or untouched"
+    assert float((z[:, c8:].float() + 7.0).abs().max()) == 0.0, "wrote past the 16-byte chunk holding column C-1"
+
+
+@pytest.mark.parametrize("C,H", [(180, 360), (212, 424), (244, 488), (276, 276), (308, 308)])
+def test_mlp_drct_shapes(C, H):
+    _mlp_case(128 * 5 + 37, C, H, seed=C)
+
+
+def test_mlp_single_tile():
+    _mlp_case(128, 180, 360)
+
+
+def test_mlp_small_dims():
+    _mlp_case(300, 60, 120)        # DRCT-small widths: one hidden chunk, one K panel
+    _mlp_case(300, 92, 184)
+
+
+def test_mlp_many_tiles_per_cta():
+    _mlp_case(128 * 148 * 3 + 5, 180, 360, seed=3)

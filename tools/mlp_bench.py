@@ -1,0 +1,32 @@
+"""Timing of the fused Swin MLP kernel per DRCT block shape (CUDA events, L2 flushed), next to the unfused GEMM pair."""
+import importlib, sys, os
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+PKG = "anomaly-detection-super-resolution_b200"
+ops = importlib.import_module(PKG + ".ops"); pack = importlib.import_module(PKG + ".pack")
+dev = "cuda"
+M = int(os.environ.get("M", 262144))
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+def timeit(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return min(ts), sum(ts) / len(ts)
+
+shapes = [(180, 360), (212, 424), (244, 488), (276, 276), (308, 308)]
+if os.environ.get('MLP_ONLY'):
+    shapes = [s for s in shapes if s[0] == int(os.environ['MLP_ONLY'])]
+for (C, H) in shapes:
+    y = torch.randn(M, 320, device=dev).to(torch.bfloat16); z = torch.empty_like(y)
+    pm = pack.pack_swin_mlp(torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
+                            torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev))
+    stats = torch.zeros(M, 2, 2, device=dev)
+    yf = y[:, :C].float(); stats[:, 0, 0] = yf.sum(1); stats[:, 0, 1] = (yf * yf).sum(1)
+    best, avg = timeit(lambda: ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2)))
+    fl = 4.0 * M * C * H
+    print(f"swin_mlp C={C} H={H}: {best*1e3:8.1f} us (avg {avg*1e3:8.1f})  {fl/best/1e9:7.1f} TFLOP/s  {4.0*M*C/best/1e6:7.1f} GB/s(y+z)")
