@@ -124,21 +124,26 @@ extern "C" int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int
     return launch_tc_gemm(p, num_sms, static_cast<cudaStream_t>(stream));
 }
 
+// tuning hook (not part of the public header): device buffer that receives the CTA-0 timeline of the next fused-MLP launches
+static long long* g_mlp_trace = nullptr;
+extern "C" void adsr_debug_set_mlp_trace(void* device_buffer) { g_mlp_trace = static_cast<long long*>(device_buffer); }
+
 extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, const void* w_packed, const float* bias1,
                                   const float* colsum1, const float* bias2, const int32_t* plan, int plan_len, float ln_eps,
                                   const float* ln_stats_in, int stats_in_slots, int stats_in_stride, void* z, int64_t ldz,
                                   int num_sms, void* stream) {
     if (M <= 0) return ADSR_OK;
-    if (plan == nullptr || plan_len < 17 || C <= 0 || ldy < C || ldz < C || ln_stats_in == nullptr || stats_in_slots <= 0)
+    if (plan == nullptr || plan_len < 18 || C <= 0 || ldy < C || ldz < C || ln_stats_in == nullptr || stats_in_slots <= 0)
         return ADSR_ERR_BAD_SHAPE;
     SwinMlpParams p{};
     p.ks1 = plan[0]; p.nc = plan[1]; p.hc = plan[2]; p.n2 = plan[3];
     p.acc1_col[0] = plan[4]; p.acc1_col[1] = plan[5]; p.n_slots = plan[6]; p.slot_bytes = plan[7];
     for (int j = 0; j < 8; ++j) p.hcw[j] = plan[8 + j];
     p.n_stages = plan[16];
-    if (p.n_stages <= 0 || p.n_stages > kMlpMaxStages || plan_len < 17 + 8 * p.n_stages) return ADSR_ERR_BAD_SHAPE;
+    p.n_prologue = plan[17];
+    if (p.n_stages <= 0 || p.n_stages > kMlpMaxStages || plan_len < 18 + 8 * p.n_stages) return ADSR_ERR_BAD_SHAPE;
     for (int t = 0; t < p.n_stages; ++t) {
-        const int32_t* e = plan + 17 + 8 * t;
+        const int32_t* e = plan + 18 + 8 * t;
         MlpStage& s = p.stages[t];
         s.bytes = static_cast<uint32_t>(e[0]); s.rows = static_cast<uint16_t>(e[1]); s.ksteps = static_cast<uint8_t>(e[2]);
         s.kind = static_cast<uint8_t>(e[3]); s.chunk = static_cast<uint8_t>(e[4]); s.kidx = static_cast<uint8_t>(e[5]);
@@ -150,5 +155,6 @@ extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, cons
     p.stats_in = reinterpret_cast<const float2*>(ln_stats_in);
     p.stats_in_slots = stats_in_slots; p.stats_in_stride = stats_in_stride;
     p.ln_eps = ln_eps; p.C = C; p.M = M;
+    p.trace = g_mlp_trace;
     return launch_swin_mlp(p, y, ldy, z, ldz, num_sms, static_cast<cudaStream_t>(stream));
 }

@@ -63,7 +63,8 @@ enum : uint8_t {
     MLP_STAGE_FIRST = 1,      // first MMA of the stage overwrites its accumulator
     MLP_STAGE_ACC1_DONE = 2,  // last fc1 stage of a hidden chunk: commit acc1_full
     MLP_STAGE_ACC2_DONE = 4,  // last fc2 stage of the tile: commit acc2_full
-    MLP_STAGE_WAIT_H = 8      // first fc2 stage of a hidden chunk: wait for the activations (and, chunk 0, a drained acc2)
+    MLP_STAGE_WAIT_H = 8,     // first fc2 stage of a 64-column slab of a chunk: wait for its activations (chunk 0: a drained acc2)
+    MLP_STAGE_NEXT_TILE = 16  // fc1 of chunk 0 of the FOLLOWING tile, issued before the last fc2 of this one
 };
 struct MlpStage {
     uint32_t bytes;   // rows * 128
@@ -93,9 +94,11 @@ struct SwinMlpParams {
     int hcw[8];           // MMA N of each chunk (multiple of 16, <= 128)
     int n2;               // fc2 accumulator columns (C rounded up to 16)
     int acc1_col[2];
-    int n_stages, n_slots, slot_bytes, a_buf_bytes;
+    int n_stages, n_prologue, t_prefetch, n_slots, slot_bytes, a_buf_bytes;
+    long long* trace;     // optional [3 roles][8 tiles][64][8] clock64 timeline of CTA 0 (tools/mlp_trace.py), else nullptr
     MlpStage stages[kMlpMaxStages];
 };
+int swin_mlp_barrier_bytes();
 int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, long long ldz, int num_sms, cudaStream_t stream);
 
 }  // namespace adsr

@@ -185,6 +185,13 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one lane of a CONVERGED warp (the warp keeps uniform control flow, so descriptors stay in uniform registers and the
+// compiler does not wrap every tcgen05 / bulk-copy instruction in a lane-serialising loop)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }

@@ -147,9 +147,9 @@ def pack_proj_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: 
 
 
 # ------------------------------------------------------------------------------------------------ fused Swin MLP
-MLP_STAGE_FIRST, MLP_STAGE_ACC1_DONE, MLP_STAGE_ACC2_DONE, MLP_STAGE_WAIT_H = 1, 2, 4, 8
+MLP_STAGE_FIRST, MLP_STAGE_ACC1_DONE, MLP_STAGE_ACC2_DONE, MLP_STAGE_WAIT_H, MLP_STAGE_NEXT_TILE = 1, 2, 4, 8, 16
 _SMEM_LIMIT = 232448            # 227 KB of shared memory per CTA
-_MLP_CONST_BYTES = (2 * 512 + 320) * 4 + 232   # bias1 / colsum1 / bias2 caches + barriers (swin_mlp.cu)
+_MLP_CONST_BYTES = (2 * 512 + 320) * 4 + 1024  # bias1 / colsum1 / bias2 caches + stage words and barriers (swin_mlp.cu)
 
 
 @dataclass
@@ -186,27 +186,32 @@ def swin_mlp_plan(c: int, h: int) -> dict:
         raise ValueError(f"fused MLP does not fit: C={c} H={h}")
     stages = []   # (bytes, rows, ksteps, kind, chunk, kidx, dcol, flags)
 
-    def fc1(j):
+    def fc1(j, extra=0):
         for s in range(ks1):
-            fl = (MLP_STAGE_FIRST if s == 0 else 0) | (MLP_STAGE_ACC1_DONE if s == ks1 - 1 else 0)
+            fl = (MLP_STAGE_FIRST if s == 0 else 0) | (MLP_STAGE_ACC1_DONE if s == ks1 - 1 else 0) | extra
             stages.append((widths[j] * 128, widths[j], min(4, k1steps - 4 * s), 0, j, s, 0, fl))
 
     def fc2(j):
         ksl = (widths[j] + 63) // 64
         for s in range(ksl):
             for pi, (dcol, rows) in enumerate(pieces):
-                fl = (MLP_STAGE_WAIT_H if (s == 0 and pi == 0) else 0) | (MLP_STAGE_FIRST if (j == 0 and s == 0) else 0)
+                fl = (MLP_STAGE_WAIT_H if pi == 0 else 0) | (MLP_STAGE_FIRST if (j == 0 and s == 0) else 0)
                 if j == nc - 1 and s == ksl - 1 and pi == len(pieces) - 1:
                     fl |= MLP_STAGE_ACC2_DONE
                 stages.append((rows * 128, rows, min(4, widths[j] // 16 - 4 * s), 1, j, s, dcol, fl))
 
-    fc1(0)
+    # software pipeline over the whole chunk stream: fc1 of the NEXT chunk (chunk 0 of the following tile after the last
+    # one) is issued before fc2 of the current chunk; the prologue (fc1 of chunk 0) runs once per CTA
+    fc1(0, MLP_STAGE_NEXT_TILE)
+    n_prologue = len(stages)
     for j in range(nc):
         if j + 1 < nc:
             fc1(j + 1)
+        else:
+            fc1(0, MLP_STAGE_NEXT_TILE)
         fc2(j)
     return dict(ks1=ks1, nc=nc, hc=hc, n2=n2, widths=widths, pieces=pieces, slot_bytes=slot_bytes, n_slots=n_slots,
-                acc1_col=(n2, n2 + hc), stages=stages)
+                acc1_col=(n2, n2 + hc), stages=stages, n_prologue=n_prologue)
 
 
 def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
@@ -251,7 +256,7 @@ def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b) -> PackedMlp:
         slabs.append(_swizzle_slab(blk.contiguous()))
     plan = [pl["ks1"], nc, hc, n2, pl["acc1_col"][0], pl["acc1_col"][1], pl["n_slots"], pl["slot_bytes"]]
     plan += pl["widths"] + [0] * (8 - nc)
-    plan += [len(pl["stages"])]
+    plan += [len(pl["stages"]), pl["n_prologue"]]
     for st in pl["stages"]:
         plan += list(st)
     return PackedMlp(torch.cat(slabs).contiguous(), bias1, colsum1, bias2, torch.tensor(plan, dtype=torch.int32),

@@ -68,8 +68,8 @@ int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K,
  * replaces norm2 + Mlp.forward + the second residual of SwinTransformerBlock.forward (src/drct.py:510, 173-190).
  * w_packed / bias1 / colsum1 / bias2 / plan come from pack.pack_swin_mlp(): the fc1 weights carry the LayerNorm gamma,
  * fc2 carries the 0.5 of GELU; `plan` (host memory, int32) is the static schedule of weight slabs:
- *   [ks1, nc, hc, n2, acc1_col0, acc1_col1, n_slots, slot_bytes, hcw[8], n_stages, n_stages x {bytes, rows, ksteps,
- *    kind, chunk, kidx, dcol, flags}].
+ *   [ks1, nc, hc, n2, acc1_col0, acc1_col1, n_slots, slot_bytes, hcw[8], n_stages, n_prologue, n_stages x {bytes, rows,
+ *    ksteps, kind, chunk, kidx, dcol, flags}]  (the first n_prologue stages run once per CTA, the rest once per tile).
  * Row mean / rstd come from ln_stats_in exactly as in adsr_tc_gemm_bf16.  y and z must not alias. */
 int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C,
                        const void* w_packed, const float* bias1, const float* colsum1, const float* bias2,
