@@ -24,8 +24,8 @@ _SIGNATURES = {
     "adsr_tc_gemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_float, c_float, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_float,
                                   c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "adsr_swin_mlp_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                   c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "adsr_swin_mlp_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "adsr_conv3x3_igemm_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                         c_int, c_int, c_int, c_float, c_float, c_void_p, c_int64, c_void_p, c_int64,
                                         c_int, c_int, c_int, c_int, c_void_p]),

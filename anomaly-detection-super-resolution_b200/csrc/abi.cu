@@ -128,29 +128,23 @@ extern "C" int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int
 static long long* g_mlp_trace = nullptr;
 extern "C" void adsr_debug_set_mlp_trace(void* device_buffer) { g_mlp_trace = static_cast<long long*>(device_buffer); }
 
-extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, const void* w_packed, const float* bias1,
-                                  const float* colsum1, const float* bias2, const int32_t* plan, int plan_len, float ln_eps,
-                                  const float* ln_stats_in, int stats_in_slots, int stats_in_stride, void* z, int64_t ldz,
-                                  int num_sms, void* stream) {
+extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, const void* w1_packed, const void* w2_packed,
+                                  const float* bias1, const float* colsum1, const float* bias2, const int32_t* plan, int plan_len,
+                                  float ln_eps, const float* ln_stats_in, int stats_in_slots, int stats_in_stride, void* z,
+                                  int64_t ldz, int num_sms, void* stream) {
     if (M <= 0) return ADSR_OK;
-    if (plan == nullptr || plan_len < 18 || C <= 0 || ldy < C || ldz < C || ln_stats_in == nullptr || stats_in_slots <= 0)
+    if (plan == nullptr || plan_len < 22 || C <= 0 || ldy < C || ldz < C || ln_stats_in == nullptr || stats_in_slots <= 0)
         return ADSR_ERR_BAD_SHAPE;
     SwinMlpParams p{};
-    p.ks1 = plan[0]; p.nc = plan[1]; p.hc = plan[2]; p.n2 = plan[3];
-    p.acc1_col[0] = plan[4]; p.acc1_col[1] = plan[5]; p.n_slots = plan[6]; p.slot_bytes = plan[7];
-    for (int j = 0; j < 8; ++j) p.hcw[j] = plan[8 + j];
-    p.n_stages = plan[16];
-    p.n_prologue = plan[17];
-    if (p.n_stages <= 0 || p.n_stages > kMlpMaxStages || plan_len < 18 + 8 * p.n_stages) return ADSR_ERR_BAD_SHAPE;
-    for (int t = 0; t < p.n_stages; ++t) {
-        const int32_t* e = plan + 18 + 8 * t;
-        MlpStage& s = p.stages[t];
-        s.bytes = static_cast<uint32_t>(e[0]); s.rows = static_cast<uint16_t>(e[1]); s.ksteps = static_cast<uint8_t>(e[2]);
-        s.kind = static_cast<uint8_t>(e[3]); s.chunk = static_cast<uint8_t>(e[4]); s.kidx = static_cast<uint8_t>(e[5]);
-        s.dcol = static_cast<uint16_t>(e[6]); s.flags = static_cast<uint8_t>(e[7]);
-    }
-    if (p.ks1 != (C + 63) / 64 || p.n2 != (C + 15) / 16 * 16) return ADSR_ERR_BAD_SHAPE;
-    p.wp = static_cast<const uint8_t*>(w_packed);
+    p.ks1 = plan[0]; p.k1steps = plan[1]; p.nc = plan[2]; p.hc = plan[3]; p.n2 = plan[4];
+    p.acc1_col[0] = plan[5]; p.acc1_col[1] = plan[6];
+    p.n_pieces = plan[7]; p.piece_rows[0] = plan[8]; p.piece_rows[1] = plan[9];
+    p.piece_col[0] = 0; p.piece_col[1] = plan[8];
+    p.w1_slots = plan[10]; p.w1_slot_bytes = plan[11]; p.w2_slots = plan[12]; p.w2_slot_bytes = plan[13];
+    for (int j = 0; j < 8; ++j) p.hcw[j] = plan[14 + j];
+    if (p.ks1 != (C + 63) / 64 || p.k1steps != (C + 15) / 16 || p.n2 != (C + 15) / 16 * 16) return ADSR_ERR_BAD_SHAPE;
+    p.w1p = static_cast<const uint8_t*>(w1_packed);
+    p.w2p = static_cast<const uint8_t*>(w2_packed);
     p.bias1 = bias1; p.colsum1 = colsum1; p.bias2 = bias2;
     p.stats_in = reinterpret_cast<const float2*>(ln_stats_in);
     p.stats_in_slots = stats_in_slots; p.stats_in_stride = stats_in_stride;

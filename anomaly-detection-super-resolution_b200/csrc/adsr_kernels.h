@@ -57,31 +57,12 @@ int launch_tc_gemm_manual(const TcGemmParams& p, int grid, cudaStream_t stream);
 // Encodes the TMA descriptor of a row-major bf16 matrix (driver entry point resolved at run time).
 int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems);
 
-// ---- fused Swin MLP (swin_mlp.cu): static schedule of weight slabs, one ring slot / up to 4 MMAs each
-constexpr int kMlpMaxStages = 48;
-enum : uint8_t {
-    MLP_STAGE_FIRST = 1,      // first MMA of the stage overwrites its accumulator
-    MLP_STAGE_ACC1_DONE = 2,  // last fc1 stage of a hidden chunk: commit acc1_full
-    MLP_STAGE_ACC2_DONE = 4,  // last fc2 stage of the tile: commit acc2_full
-    MLP_STAGE_WAIT_H = 8,     // first fc2 stage of a 64-column slab of a chunk: wait for its activations (chunk 0: a drained acc2)
-    MLP_STAGE_NEXT_TILE = 16  // fc1 of chunk 0 of the FOLLOWING tile, issued before the last fc2 of this one
-};
-struct MlpStage {
-    uint32_t bytes;   // rows * 128
-    uint32_t goff;    // byte offset in the packed weight stream (filled by launch_swin_mlp)
-    uint16_t rows;    // MMA N
-    uint16_t dcol;    // fc2: column offset inside the fc2 accumulator
-    uint8_t ksteps;   // K=16 steps in this slab (1..4)
-    uint8_t kind;     // 0 = fc1 (A = y tile in shared memory), 1 = fc2 (A = activations in TMEM)
-    uint8_t chunk;    // hidden chunk
-    uint8_t kidx;     // 64-wide K slab index inside the operand
-    uint8_t flags;
-    uint8_t pad_[3];
-};
+// ---- fused Swin MLP (swin_mlp.cu)
 struct SwinMlpParams {
     CUtensorMap tmap_y;   // [M x C] bf16, box 64 x 128, 128-byte swizzle (loads)
     CUtensorMap tmap_z;   // same geometry on the output (stores)
-    const uint8_t* wp;    // packed weight slabs in schedule order
+    const uint8_t* w1p;   // fc1 slabs [hcw[j] rows x 64 bf16] in (chunk j, K slab s) order
+    const uint8_t* w2p;   // fc2 slabs [piece rows x 64 bf16] in (chunk j, K slab s, piece) order
     const float* bias1;   // [nc * hc]  beta W1^T + b1, chunk-strided
     const float* colsum1; // [nc * hc]  sum_k gamma_k W1[n,k] of the bf16-rounded packed weights
     const float* bias2;   // [n2]
@@ -89,16 +70,17 @@ struct SwinMlpParams {
     int stats_in_slots, stats_in_stride;
     float ln_eps;
     int C, M, m_tiles;
-    int ks1;              // 64-wide panels of the y tile
+    int ks1, k1steps;     // 64-wide panels / K=16 steps of the y tile
     int nc, hc;           // hidden chunks, chunk stride in bias1 / colsum1 (= TMEM columns per fc1 accumulator)
     int hcw[8];           // MMA N of each chunk (multiple of 16, <= 128)
     int n2;               // fc2 accumulator columns (C rounded up to 16)
+    int n_pieces;         // the fc2 N dimension is issued in 1 or 2 pieces (each <= 256 rows)
+    int piece_rows[2], piece_col[2];
     int acc1_col[2];
-    int n_stages, n_prologue, t_prefetch, n_slots, slot_bytes, a_buf_bytes;
-    long long* trace;     // optional [3 roles][8 tiles][64][8] clock64 timeline of CTA 0 (tools/mlp_trace.py), else nullptr
-    MlpStage stages[kMlpMaxStages];
+    int w1_slots, w1_slot_bytes, w2_slots, w2_slot_bytes, a_buf_bytes;
+    long long* trace;     // optional [4 roles][8 tiles][64][8] clock64 timeline of CTA 0 (tools/mlp_trace.py), else nullptr
 };
-int swin_mlp_barrier_bytes();
+int swin_mlp_fixed_smem_bytes();
 int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, long long ldz, int num_sms, cudaStream_t stream);
 
 }  // namespace adsr

@@ -1,19 +1,20 @@
 // Fused Swin MLP half for sm_100a:   z = y + fc2( GELU_erf( fc1( LayerNorm(y) ) ) )      (src/drct.py:510, 173-190)
 //
-// One persistent, warp-specialised kernel (grid = #SMs, 20 warps).  A CTA owns 128 token rows at a time; the hidden
+// One persistent, warp-specialised kernel (grid = #SMs, 21 warps).  A CTA owns 128 token rows at a time; the hidden
 // activations [128 x H] never leave the SM:
 //   * the y tile [128 x C] arrives by TMA (128-byte swizzle, K / M tails zero-filled) into one of TWO shared-memory
-//     buffers (prefetched a tile ahead); it is the A operand of fc1, the residual of the last epilogue, and --
-//     overwritten in place with z -- the source of the TMA store of the result;
-//   * the weights of fc1 (gamma-folded) and fc2 stream from L2 through a ring of shared-memory slots, one
-//     [rows x 64] slab per slot, in exactly the order a host-built static schedule consumes them;
+//     buffers; it is the A operand of fc1, the residual of the last epilogue, and -- overwritten in place with z -- the
+//     source of the TMA store of the result.  The warp that stores tile i reloads the freed buffer with tile i+2;
+//   * the weights of fc1 (gamma-folded) and fc2 stream from L2 through two rings of shared-memory slots (one
+//     [rows x 64] slab per slot), each fed by its own loader warp in the fixed order its consumer uses them;
 //   * fc1 is computed in hidden chunks of <= 128 columns into a double-buffered TMEM accumulator (tcgen05.mma, SS);
 //     16 epilogue warps turn a chunk into bf16 GELU activations (LayerNorm folded: rstd * (acc - mean * colsum) + b),
 //     16 columns (one K=16 step of fc2) at a time, and write them back IN PLACE into the first 8 of those 16 TMEM
 //     columns (tcgen05.st), from where fc2 consumes them as its TMEM A operand (tcgen05.mma, TS);
 //   * fc2 accumulates over the chunks into a third TMEM region; the last epilogue adds bias and the residual.
-// The MMA stream is software-pipelined over the whole chunk sequence, across tile borders: fc1 of chunk g+1 is issued
-// before fc2 of chunk g, so the tensor core always has work while the epilogue warps turn chunk g around.
+// TWO MMA-issuing warps (one for fc1, one for fc2) keep the tensor core fed: the per-slab bookkeeping of one stream
+// (mbarrier waits, commits) overlaps the MMAs of the other, and fc1 runs up to two chunks ahead of fc2 -- across tile
+// borders -- limited only by the two chunk accumulators (barrier acc1_free, committed by the fc2 issuer).
 // The 0.5 of GELU is folded into the packed fc2 weights.
 #include "adsr_kernels.h"
 #include "ptx.cuh"
@@ -22,10 +23,13 @@ namespace adsr {
 
 namespace {
 
-constexpr int kThreads = 608;                 // warps 0..15 epilogue, 16 loader, 17 MMA issuer, 18 TMEM alloc + TMA store
-constexpr int kLoaderWarp = 16, kMmaWarp = 17, kStoreWarp = 18;   // control warps get the HIGHEST ids: the SMSP arbiter favours
-                                                                   // high warp ids, and a starved MMA issuer idles the tensor core
-constexpr int kEpiWarps = 16;
+constexpr int kEpiWarps = 16;                 // warps 0..15: epilogue (TMEM lane quadrant = warp % 4)
+constexpr int kW1LoaderWarp = 16;             // fc1 weight slabs
+constexpr int kFc1Warp = 17;                  // fc1 MMA issuer
+constexpr int kFc2Warp = 18;                  // fc2 MMA issuer
+constexpr int kW2LoaderWarp = 19;             // fc2 weight slabs
+constexpr int kTileWarp = 20;                 // TMEM alloc, y-tile loads, z-tile stores
+constexpr int kThreads = 21 * 32;
 constexpr int kPanelBytes = 128 * 128;        // 128 rows x 64 bf16
 constexpr int kMaxHidden = 512;               // padded hidden columns (sum of chunk strides)
 constexpr int kMaxN2 = 320;
@@ -33,12 +37,12 @@ constexpr int kConstBytes = (2 * kMaxHidden + kMaxN2) * 4;
 constexpr int kSmemLimit = 232448;            // 227 KB
 
 struct __align__(16) MlpBarriers {
-    uint64_t w_full[8];
-    uint64_t w_empty[8];
+    uint64_t w1_full[8], w1_empty[8];
+    uint64_t w2_full[8], w2_empty[8];
     uint64_t a_full[2];
-    uint64_t a_empty[2];
     uint64_t z_ready[2];
     uint64_t acc1_full[2];
+    uint64_t acc1_free[2];
     uint64_t h_ready[2][2];                   // [accumulator buffer][64-column slab of the chunk]
     uint64_t acc2_full;
     uint64_t acc2_free;
@@ -66,10 +70,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
                  : "memory");
 }
 
+// optional timeline of CTA 0 (tools/mlp_trace.py): trace[((role * 8 + tile) * 64 + index) * 8 + k] = clock64()
 template <bool TRACE>
 __device__ __forceinline__ void trace_ev(long long* trace, int role, int it, int idx, int k) {
     if constexpr (TRACE) {
-        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it >= 0 && it < 8 && idx < 64) trace[((role * 8 + it) * 64 + idx) * 8 + k] = clock64();
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it < 8 && idx < 64) trace[((role * 8 + it) * 64 + idx) * 8 + k] = clock64();
     }
 }
 
@@ -77,8 +82,9 @@ template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_constant__ SwinMlpParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_buf = smem;                                            // 2 x a_buf_bytes
-    uint8_t* ring = smem + 2 * p.a_buf_bytes;                         // n_slots x slot_bytes
-    float* s_bias1 = reinterpret_cast<float*>(ring + p.n_slots * p.slot_bytes);
+    uint8_t* ring1 = smem + 2 * p.a_buf_bytes;                        // w1_slots x w1_slot_bytes
+    uint8_t* ring2 = ring1 + p.w1_slots * p.w1_slot_bytes;            // w2_slots x w2_slot_bytes
+    float* s_bias1 = reinterpret_cast<float*>(ring2 + p.w2_slots * p.w2_slot_bytes);
     float* s_colsum1 = s_bias1 + kMaxHidden;
     float* s_bias2 = s_colsum1 + kMaxHidden;
     MlpBarriers* bars = reinterpret_cast<MlpBarriers*>(s_bias2 + kMaxN2);
@@ -94,16 +100,19 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         s_colsum1[i] = p.colsum1[i];
     }
     for (int i = threadIdx.x; i < p.n2; i += kThreads) s_bias2[i] = p.bias2[i];
-    if (warp == kMmaWarp && lane == 0) {
-        for (int s = 0; s < p.n_slots; ++s) {
-            mbar_init(&bars->w_full[s], 1);
-            mbar_init(&bars->w_empty[s], 1);
+
+    if (warp == kFc1Warp && lane == 0) {
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(&bars->w1_full[s], 1);
+            mbar_init(&bars->w1_empty[s], 1);
+            mbar_init(&bars->w2_full[s], 1);
+            mbar_init(&bars->w2_empty[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->a_full[b], 1);
-            mbar_init(&bars->a_empty[b], 1);
             mbar_init(&bars->z_ready[b], kEpiWarps);
             mbar_init(&bars->acc1_full[b], 1);
+            mbar_init(&bars->acc1_free[b], 1);
             mbar_init(&bars->h_ready[b][0], kEpiWarps);
             mbar_init(&bars->h_ready[b][1], kEpiWarps);
         }
@@ -111,137 +120,170 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         mbar_init(&bars->acc2_free, kEpiWarps);
         fence_barrier_init();
     }
-    if (warp == kStoreWarp) tmem_alloc<512>(&bars->tmem_base);
+    if (warp == kTileWarp) tmem_alloc<512>(&bars->tmem_base);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = bars->tmem_base;
 
-    // The static schedule: stages [0, n_prologue) = fc1 of chunk 0 (first tile only); stages [n_prologue, n_stages) = the
-    // per-tile body; body stages flagged NEXT_TILE are fc1 of chunk 0 of the FOLLOWING tile (skipped after the last tile).
-    if (warp == kLoaderWarp) {
-        // ============================================================ loader (converged warp, one elected lane issues)
-        if (my_tiles > 0) {
-            if (lane == 0) tma_prefetch_desc(&p.tmap_y);
-            auto load_a = [&](int it) {
-                const int ab = it & 1;
-                const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
-                if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(&bars->a_full[ab], static_cast<uint32_t>(p.a_buf_bytes));
-                    for (int pn = 0; pn < p.ks1; ++pn)
-                        tma_load_2d(a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, &p.tmap_y, pn * 64, m0, &bars->a_full[ab]);
-                }
-                __syncwarp();
-            };
-            load_a(0);
-            if (my_tiles > 1) load_a(1);
-            int slot = 0;
-            uint32_t phase = 0;
-            auto load_w = [&](int t) {
-                const uint32_t bytes = p.stages[t].bytes;
-                const uint32_t goff = p.stages[t].goff;
-                mbar_wait(&bars->w_empty[slot], phase ^ 1);
-                if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
-                    bulk_g2s(ring + slot * p.slot_bytes, p.wp + goff, bytes, &bars->w_full[slot]);
-                }
-                __syncwarp();
-                if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
-            };
-            for (int t = 0; t < p.n_prologue; ++t) load_w(t);
-            for (int it = 0; it < my_tiles; ++it) {
-                const bool has_next = it + 1 < my_tiles;
-                for (int t = p.n_prologue; t < p.n_stages; ++t) {
-                    if (t == p.t_prefetch && it >= 1 && has_next) {
-                        // tile it+1 reuses the buffer of tile it-1: its TMA store must have finished reading it
-                        mbar_wait(&bars->a_empty[(it + 1) & 1], (static_cast<uint32_t>((it - 1) >> 1) & 1));
-                        load_a(it + 1);
+    // The control warps below stay CONVERGED (uniform control flow, one elected lane issues): descriptors then live in
+    // uniform registers and no tcgen05 / bulk-copy instruction gets wrapped in a lane-serialising loop.
+    if (warp == kW1LoaderWarp) {
+        // ============================================================ fc1 weight slabs: (chunk j, K slab s) in order, every tile
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            uint32_t goff = 0;
+            for (int j = 0; j < p.nc; ++j) {
+                const uint32_t bytes = static_cast<uint32_t>(p.hcw[j]) * 128u;
+                for (int s = 0; s < p.ks1; ++s) {
+                    mbar_wait(&bars->w1_empty[slot], phase ^ 1);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(&bars->w1_full[slot], bytes);
+                        bulk_g2s(ring1 + slot * p.w1_slot_bytes, p.w1p + goff, bytes, &bars->w1_full[slot]);
                     }
-                    if ((p.stages[t].flags & MLP_STAGE_NEXT_TILE) && !has_next) continue;
-                    load_w(t);
+                    __syncwarp();
+                    goff += bytes;
+                    if (++slot == p.w1_slots) { slot = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ============================================================ MMA issuer (converged warp, one elected lane issues)
-        if (my_tiles > 0) {
-            int slot = 0;
-            uint32_t phase = 0;
-            const uint32_t slot_units = static_cast<uint32_t>(p.slot_bytes >> 4);
-            const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring));
-            const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(a_buf));
-            const uint32_t a_units = static_cast<uint32_t>(p.a_buf_bytes >> 4);
-
-            auto issue = [&](int it, int t) {
-                const uint32_t flags = p.stages[t].flags, ksteps = p.stages[t].ksteps, kind = p.stages[t].kind;
-                const int chunk = p.stages[t].chunk, slab = p.stages[t].kidx;
-                const uint32_t idesc = umma_idesc_bf16_m128(p.stages[t].rows);
-                const int tile_of = it + ((flags & MLP_STAGE_NEXT_TILE) ? 1 : 0);
-                const int cg = tile_of * p.nc + chunk;            // running chunk counter: buffer = cg & 1, use = cg >> 1
-                const int b = cg & 1;
-                trace_ev<TRACE>(p.trace, 1, it, t, 0);
-                if (kind == 0) {
-                    if ((flags & MLP_STAGE_FIRST) && chunk == 0) {    // first fc1 slab of a tile: its y tile must have landed
-                        mbar_wait(&bars->a_full[tile_of & 1], static_cast<uint32_t>(tile_of >> 1) & 1);
+    } else if (warp == kW2LoaderWarp) {
+        // ============================================================ fc2 weight slabs: (chunk j, K slab s, N piece) in order
+        int slot = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            uint32_t goff = 0;
+            for (int j = 0; j < p.nc; ++j) {
+                const int nslab = (p.hcw[j] + 63) >> 6;
+                for (int s = 0; s < nslab; ++s) {
+                    for (int pc = 0; pc < p.n_pieces; ++pc) {
+                        const uint32_t bytes = static_cast<uint32_t>(p.piece_rows[pc]) * 128u;
+                        mbar_wait(&bars->w2_empty[slot], phase ^ 1);
+                        if (elect_one_sync()) {
+                            mbar_arrive_expect_tx(&bars->w2_full[slot], bytes);
+                            bulk_g2s(ring2 + slot * p.w2_slot_bytes, p.w2p + goff, bytes, &bars->w2_full[slot]);
+                        }
+                        __syncwarp();
+                        goff += bytes;
+                        if (++slot == p.w2_slots) { slot = 0; phase ^= 1; }
                     }
-                } else if (flags & MLP_STAGE_WAIT_H) {
-                    mbar_wait(&bars->h_ready[b][slab], static_cast<uint32_t>(cg >> 1) & 1);
-                    if (chunk == 0 && slab == 0) mbar_wait(&bars->acc2_free, (static_cast<uint32_t>(it) & 1) ^ 1);
                 }
-                trace_ev<TRACE>(p.trace, 1, it, t, 1);
-                mbar_wait(&bars->w_full[slot], phase);
-                tc_fence_after_sync();
-                trace_ev<TRACE>(p.trace, 1, it, t, 2);
-                const uint64_t bdesc = ring_desc + static_cast<uint64_t>(static_cast<uint32_t>(slot) * slot_units);
+            }
+        }
+    } else if (warp == kFc1Warp) {
+        // ============================================================ fc1 MMA issuer: acc1[cg & 1] = y_tile . W1_chunk^T
+        int slot = 0;
+        uint32_t phase = 0;
+        const uint32_t slot_units = static_cast<uint32_t>(p.w1_slot_bytes >> 4);
+        const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring1));
+        const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(a_buf));
+        const uint32_t a_units = static_cast<uint32_t>(p.a_buf_bytes >> 4);
+        for (int it = 0; it < my_tiles; ++it) {
+            mbar_wait(&bars->a_full[it & 1], static_cast<uint32_t>(it >> 1) & 1);
+            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((it & 1) * a_units);
+            for (int j = 0; j < p.nc; ++j) {
+                const int cg = it * p.nc + j;                         // running chunk counter: buffer = cg & 1, use = cg >> 1
+                const int b = cg & 1;
+                const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.hcw[j]));
                 const uint32_t acc1 = tmem + static_cast<uint32_t>(p.acc1_col[b]);
-                const uint32_t first_acc = (flags & MLP_STAGE_FIRST) ? 0u : 1u;
-                if (elect_one_sync()) {
-                    if (kind == 0) {
-                        const uint64_t adesc = a_desc0 + static_cast<uint64_t>((tile_of & 1) * a_units + slab * (kPanelBytes >> 4));
-                        umma_bf16(acc1, adesc, bdesc, idesc, first_acc);
+                trace_ev<TRACE>(p.trace, 1, it, j, 0);
+                mbar_wait(&bars->acc1_free[b], (static_cast<uint32_t>(cg >> 1) & 1) ^ 1);   // fc2 of chunk cg-2 has consumed it
+                trace_ev<TRACE>(p.trace, 1, it, j, 1);
+                for (int s = 0; s < p.ks1; ++s) {
+                    const int ksteps = min(4, p.k1steps - 4 * s);
+                    mbar_wait(&bars->w1_full[slot], phase);
+                    tc_fence_after_sync();
+                    if (elect_one_sync()) {
+                        const uint64_t adesc = a_desc + static_cast<uint64_t>(s * (kPanelBytes >> 4));
+                        const uint64_t bdesc = ring_desc + static_cast<uint64_t>(static_cast<uint32_t>(slot) * slot_units);
+                        umma_bf16(acc1, adesc, bdesc, idesc, s == 0 ? 0u : 1u);
                         if (ksteps > 1) umma_bf16(acc1, adesc + 2, bdesc + 2, idesc, 1u);
                         if (ksteps > 2) umma_bf16(acc1, adesc + 4, bdesc + 4, idesc, 1u);
                         if (ksteps > 3) umma_bf16(acc1, adesc + 6, bdesc + 6, idesc, 1u);
-                    } else {
-                        const uint32_t d = tmem + p.stages[t].dcol;
-                        const uint32_t at = acc1 + static_cast<uint32_t>(64 * slab);   // K=16 step s lives at chunk column 16 s
-                        umma_bf16_ts(d, at, bdesc, idesc, first_acc);
-                        if (ksteps > 1) umma_bf16_ts(d, at + 16, bdesc + 2, idesc, 1u);
-                        if (ksteps > 2) umma_bf16_ts(d, at + 32, bdesc + 4, idesc, 1u);
-                        if (ksteps > 3) umma_bf16_ts(d, at + 48, bdesc + 6, idesc, 1u);
+                        umma_commit(&bars->w1_empty[slot]);
+                        if (s == p.ks1 - 1) umma_commit(&bars->acc1_full[b]);
                     }
-                    umma_commit(&bars->w_empty[slot]);
-                    if (flags & MLP_STAGE_ACC1_DONE) umma_commit(&bars->acc1_full[b]);
-                    if (flags & MLP_STAGE_ACC2_DONE) umma_commit(&bars->acc2_full);
+                    __syncwarp();
+                    if (++slot == p.w1_slots) { slot = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++slot == p.n_slots) { slot = 0; phase ^= 1; }
-                trace_ev<TRACE>(p.trace, 1, it, t, 3);
-            };
-            for (int t = 0; t < p.n_prologue; ++t) issue(-1, t);      // tile_of = 0 through the NEXT_TILE flag
-            for (int it = 0; it < my_tiles; ++it) {
-                const bool has_next = it + 1 < my_tiles;
-                for (int t = p.n_prologue; t < p.n_stages; ++t) {
-                    if ((p.stages[t].flags & MLP_STAGE_NEXT_TILE) && !has_next) continue;
-                    issue(it, t);
+                trace_ev<TRACE>(p.trace, 1, it, j, 2);
+            }
+        }
+    } else if (warp == kFc2Warp) {
+        // ============================================================ fc2 MMA issuer: acc2 += gelu_chunk (TMEM) . W2_chunk^T
+        int slot = 0;
+        uint32_t phase = 0;
+        const uint32_t slot_units = static_cast<uint32_t>(p.w2_slot_bytes >> 4);
+        const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring2));
+        for (int it = 0; it < my_tiles; ++it) {
+            for (int j = 0; j < p.nc; ++j) {
+                const int cg = it * p.nc + j;
+                const int b = cg & 1;
+                const int nslab = (p.hcw[j] + 63) >> 6;
+                const uint32_t acc1 = tmem + static_cast<uint32_t>(p.acc1_col[b]);
+                for (int s = 0; s < nslab; ++s) {
+                    const int ksteps = min(4, (p.hcw[j] >> 4) - 4 * s);
+                    trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 0);
+                    mbar_wait(&bars->h_ready[b][s], static_cast<uint32_t>(cg >> 1) & 1);
+                    if (j == 0 && s == 0) mbar_wait(&bars->acc2_free, (static_cast<uint32_t>(it) & 1) ^ 1);
+                    trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 1);
+                    const uint32_t at = acc1 + static_cast<uint32_t>(64 * s);     // K=16 step u of the chunk lives at column 16 u
+                    const uint32_t first_acc = (j == 0 && s == 0) ? 0u : 1u;
+                    for (int pc = 0; pc < p.n_pieces; ++pc) {
+                        const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.piece_rows[pc]));
+                        const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[pc]);
+                        mbar_wait(&bars->w2_full[slot], phase);
+                        tc_fence_after_sync();
+                        if (elect_one_sync()) {
+                            const uint64_t bdesc = ring_desc + static_cast<uint64_t>(static_cast<uint32_t>(slot) * slot_units);
+                            umma_bf16_ts(d, at, bdesc, idesc, first_acc);
+                            if (ksteps > 1) umma_bf16_ts(d, at + 16, bdesc + 2, idesc, 1u);
+                            if (ksteps > 2) umma_bf16_ts(d, at + 32, bdesc + 4, idesc, 1u);
+                            if (ksteps > 3) umma_bf16_ts(d, at + 48, bdesc + 6, idesc, 1u);
+                            umma_commit(&bars->w2_empty[slot]);
+                            if (s == nslab - 1 && pc == p.n_pieces - 1) {
+                                umma_commit(&bars->acc1_free[b]);                  // chunk accumulator may be overwritten
+                                if (j == p.nc - 1) umma_commit(&bars->acc2_full);  // tile complete -> last epilogue
+                            }
+                        }
+                        __syncwarp();
+                        if (++slot == p.w2_slots) { slot = 0; phase ^= 1; }
+                    }
+                    trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 2);
                 }
             }
         }
-    } else if (warp == kStoreWarp) {
-        // ============================================================ TMA store of finished tiles (one thread)
-        if (lane == 0) {
-            for (int it = 0; it < my_tiles; ++it) {
-                const int ab = it & 1;
-                const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
-                mbar_wait(&bars->z_ready[ab], static_cast<uint32_t>(it >> 1) & 1);
+    } else if (warp == kTileWarp) {
+        // ============================================================ y-tile loads / z-tile stores (same buffers)
+        auto load_a = [&](int it) {
+            const int ab = it & 1;
+            const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars->a_full[ab], static_cast<uint32_t>(p.a_buf_bytes));
+                for (int pn = 0; pn < p.ks1; ++pn)
+                    tma_load_2d(a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, &p.tmap_y, pn * 64, m0, &bars->a_full[ab]);
+            }
+            __syncwarp();
+        };
+        if (lane == 0) tma_prefetch_desc(&p.tmap_y);
+        if (my_tiles > 0) load_a(0);
+        if (my_tiles > 1) load_a(1);
+        for (int it = 0; it < my_tiles; ++it) {
+            const int ab = it & 1;
+            const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
+            mbar_wait(&bars->z_ready[ab], static_cast<uint32_t>(it >> 1) & 1);
+            if (lane == 0) {        // bulk-group bookkeeping is per thread: the same lane stores and waits
                 for (int pn = 0; pn < p.ks1; ++pn)
                     tma_store_2d_box(&p.tmap_z, a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, pn * 64, m0);
                 bulk_commit_group();
                 bulk_wait_group_read0();
-                mbar_arrive(&bars->a_empty[ab]);
             }
-            bulk_wait_group0();
+            __syncwarp();
+            if (it + 2 < my_tiles) load_a(it + 2);                    // the buffer is free again: fetch the tile after next
         }
+        if (lane == 0) bulk_wait_group0();
+        __syncwarp();
     } else if (warp < kEpiWarps) {
         // ============================================================ epilogue: 4 quadrants (TMEM lanes) x 4 column groups
         const int quad = warp & 3;
@@ -250,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         const int r_in_tile = quad * 32 + lane;
         const uint32_t row_off = static_cast<uint32_t>(r_in_tile * 128);
         const int rsw = r_in_tile & 7;
-        const bool tr = TRACE && warp == 0 && lane == 0;
+        const bool tr = TRACE && warp == 0;
 
         auto row_stats = [&](int it, float& rstd, float& nrm) {
             const int row = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128 + r_in_tile;
@@ -369,7 +411,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             if (tr) trace_ev<TRACE>(p.trace, 2, it, 16, 2);
         };
 
-        // task order mirrors the MMA stream: chunk 0 of tile it+1 is turned around BEFORE the last epilogue of tile it
+        // task order mirrors the MMA streams: chunk 0 of tile it+1 is turned around BEFORE the last epilogue of tile it
+        // (fc1 runs ahead of fc2, so that chunk is ready while the last fc2 MMAs of tile it are still in flight)
         float rstd = 1.f, nrm = 0.f;
         if (my_tiles > 0) {
             row_stats(0, rstd, nrm);
@@ -387,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == kStoreWarp) {
+    if (warp == kTileWarp) {
         tc_fence_after_sync();
         tmem_dealloc<512>(tmem);
     }
@@ -397,31 +440,30 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
 
 int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, long long ldz, int num_sms, cudaStream_t stream) {
     if (p.M <= 0) return ADSR_OK;
-    if (p.n_stages <= 0 || p.n_stages > kMlpMaxStages || p.nc <= 0 || p.nc > 8) return ADSR_ERR_BAD_SHAPE;
-    if (p.n_prologue <= 0 || p.n_prologue >= p.n_stages) return ADSR_ERR_BAD_SHAPE;
+    if (p.nc <= 0 || p.nc > 8 || p.n_pieces < 1 || p.n_pieces > 2) return ADSR_ERR_BAD_SHAPE;
     if (p.n2 > kMaxN2 || (p.n2 % 16) != 0 || p.nc * p.hc > kMaxHidden || (p.hc % 16) != 0) return ADSR_ERR_BAD_SHAPE;
     if (p.n2 + 2 * p.hc > 512 || p.acc1_col[0] < p.n2 || p.acc1_col[1] < p.acc1_col[0] + p.hc || p.acc1_col[1] + p.hc > 512)
         return ADSR_ERR_BAD_SHAPE;
-    if (p.ks1 <= 0 || p.ks1 > 5 || p.n_slots < 2 || p.n_slots > 8 || (p.slot_bytes % 1024) != 0) return ADSR_ERR_BAD_SHAPE;
-    uint32_t goff = 0;
-    for (int t = 0; t < p.n_stages; ++t) {
-        MlpStage& e = p.stages[t];
-        if (e.rows < 16 || e.rows > 256 || (e.rows % 16) != 0 || e.ksteps < 1 || e.ksteps > 4 || e.chunk >= p.nc) return ADSR_ERR_BAD_SHAPE;
-        if (e.bytes != static_cast<uint32_t>(e.rows) * 128u || static_cast<int>(e.bytes) > p.slot_bytes) return ADSR_ERR_BAD_SHAPE;
-        if (e.kind == 0 && (e.kidx >= p.ks1 || e.rows != p.hcw[e.chunk])) return ADSR_ERR_BAD_SHAPE;
-        if (e.kind == 1 && (e.dcol + e.rows > p.n2 || e.kidx > 1 || 16 * (4 * e.kidx + e.ksteps) > p.hcw[e.chunk])) return ADSR_ERR_BAD_SHAPE;
-        if (t < p.n_prologue && (e.kind != 0 || e.chunk != 0 || !(e.flags & MLP_STAGE_NEXT_TILE))) return ADSR_ERR_BAD_SHAPE;
-        e.goff = goff;
-        goff += e.bytes;
+    if (p.ks1 <= 0 || p.ks1 > 5 || p.k1steps <= 4 * (p.ks1 - 1) || p.k1steps > 4 * p.ks1) return ADSR_ERR_BAD_SHAPE;
+    if (p.w1_slots < 2 || p.w1_slots > 8 || p.w2_slots < 2 || p.w2_slots > 8 || (p.w1_slot_bytes % 1024) || (p.w2_slot_bytes % 1024))
+        return ADSR_ERR_BAD_SHAPE;
+    int col = 0;
+    for (int pc = 0; pc < p.n_pieces; ++pc) {
+        if (p.piece_rows[pc] < 16 || p.piece_rows[pc] > 256 || (p.piece_rows[pc] % 16) || p.piece_col[pc] != col ||
+            p.piece_rows[pc] * 128 > p.w2_slot_bytes)
+            return ADSR_ERR_BAD_SHAPE;
+        col += p.piece_rows[pc];
     }
+    if (col != p.n2) return ADSR_ERR_BAD_SHAPE;
     for (int j = 0; j < p.nc; ++j)
-        if (p.hcw[j] <= 0 || p.hcw[j] > p.hc || p.hcw[j] > 128 || (p.hcw[j] % 16) != 0) return ADSR_ERR_BAD_SHAPE;
+        if (p.hcw[j] <= 0 || p.hcw[j] > p.hc || p.hcw[j] > 128 || (p.hcw[j] % 16) != 0 || p.hcw[j] * 128 > p.w1_slot_bytes)
+            return ADSR_ERR_BAD_SHAPE;
     p.a_buf_bytes = p.ks1 * kPanelBytes;
-    p.t_prefetch = p.n_prologue + (p.n_stages - p.n_prologue) / 2;
-    const int smem_bytes = 2 * p.a_buf_bytes + p.n_slots * p.slot_bytes + kConstBytes + static_cast<int>(sizeof(MlpBarriers));
+    const int smem_bytes = 2 * p.a_buf_bytes + p.w1_slots * p.w1_slot_bytes + p.w2_slots * p.w2_slot_bytes + kConstBytes +
+                           static_cast<int>(sizeof(MlpBarriers));
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
     if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(z) & 15) || (ldy % 8) || (ldz % 8) ||
-        (reinterpret_cast<uintptr_t>(p.wp) & 15))
+        (reinterpret_cast<uintptr_t>(p.w1p) & 15) || (reinterpret_cast<uintptr_t>(p.w2p) & 15))
         return ADSR_ERR_BAD_ALIGN;
     int st = encode_tmap_rows_bf16(&p.tmap_y, y, p.M, p.C, ldy);
     if (st != ADSR_OK) return st;
@@ -437,6 +479,6 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
     return p.trace != nullptr ? launch(swin_mlp_kernel<true>) : launch(swin_mlp_kernel<false>);
 }
 
-int swin_mlp_barrier_bytes() { return static_cast<int>(sizeof(MlpBarriers)); }
+int swin_mlp_fixed_smem_bytes() { return kConstBytes + static_cast<int>(sizeof(MlpBarriers)); }
 
 }  // namespace adsr

@@ -104,7 +104,7 @@ class _PatchNorm(nn.Module):
 class _Block:
     """Packed weights + geometry of one Swin block and its adjust conv."""
     __slots__ = ("dim", "heads", "hd", "hdp", "shift", "ws", "hidden", "adjust_out", "n1w", "n1b", "n2w", "n2b", "table",
-                 "qkv", "proj", "fc1", "fc2", "adjust", "last")
+                 "qkv", "proj", "mlp", "adjust", "last")
 
 
 class DRCT(nn.Module):
@@ -189,9 +189,8 @@ class DRCT(nn.Module):
                 b.qkv = pack.pack_qkv_weight(sw.attn.qkv.weight, sw.attn.qkv.bias, b.heads, sw.norm1.weight, sw.norm1.bias,
                                              sw.norm1.eps)
                 b.proj = pack.pack_proj_weight(sw.attn.proj.weight, sw.attn.proj.bias, b.heads)
-                b.fc1 = pack.pack_ln_gemm_weight(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias,
-                                                 sw.norm2.eps)
-                b.fc2 = pack.pack_gemm_weight(sw.mlp.fc2.weight, sw.mlp.fc2.bias)
+                b.mlp = pack.pack_swin_mlp(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias, sw.norm2.eps,
+                                           sw.mlp.fc2.weight, sw.mlp.fc2.bias)
                 b.adjust = pack.pack_gemm_weight(adj.weight, adj.bias)
                 blocks.append(b)
             P["blocks"].append(blocks)
@@ -285,9 +284,9 @@ class DRCT(nn.Module):
                 ops.tc_gemm(slab, C, b.qkv, qkv, stats_in=(st_slab, 2 * (k + 1)))
                 ops.window_attention(qkv, att, b.table, B, H, W, b.ws, b.shift, b.heads, b.hd, b.hdp)
                 ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0))
-                # ---- MLP half (src/drct.py:510, 185-189); norm2 folded into fc1
-                ops.tc_gemm(y, C, b.fc1, hb, act=ops.ACT_GELU, stats_in=(st_y, 2 * b.proj.n_tiles))
-                ops.tc_gemm(hb, b.hidden, b.fc2, z, res=y)
+                # ---- MLP half (src/drct.py:510, 185-189): norm2 + fc1 + GELU + fc2 + residual in ONE kernel, the hidden
+                #      activations never leave the SM
+                ops.swin_mlp(y, C, b.mlp, z, stats_in=(st_y, 2 * b.proj.n_tiles))
                 # ---- adjust 1x1 conv (+LeakyReLU 0.2) into the slab slice / 0.2*x5 + x  (src/drct.py:389-396)
                 if not b.last:
                     ops.tc_gemm(z, C, b.adjust, slab, act=ops.ACT_LRELU, slope=0.2, ocol0=C, n_store=b.adjust_out,

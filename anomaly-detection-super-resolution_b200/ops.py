@@ -76,7 +76,7 @@ def swin_mlp(y: torch.Tensor, c: int, pm, z: torch.Tensor, stats_in: tuple, m: O
     m = y.shape[0] if m is None else m
     si_t, si_n = stats_in
     _t = _begin()
-    check(lib().adsr_swin_mlp_bf16(ptr(y), y.stride(0), m, c, ptr(pm.data), ptr(pm.bias1), ptr(pm.colsum1), ptr(pm.bias2),
+    check(lib().adsr_swin_mlp_bf16(ptr(y), y.stride(0), m, c, ptr(pm.w1), ptr(pm.w2), ptr(pm.bias1), ptr(pm.colsum1), ptr(pm.bias2),
                                    pm.plan.data_ptr(), pm.plan.numel(), pm.ln_eps, ptr(si_t), si_n, si_t.shape[1],
                                    ptr(z), z.stride(0), _abi.num_sms(), stream_ptr()), "adsr_swin_mlp_bf16")
     _count("swin_mlp", 4.0 * m * pm.C * pm.H, _t)

@@ -147,14 +147,14 @@ def pack_proj_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: 
 
 
 # ------------------------------------------------------------------------------------------------ fused Swin MLP
-MLP_STAGE_FIRST, MLP_STAGE_ACC1_DONE, MLP_STAGE_ACC2_DONE, MLP_STAGE_WAIT_H, MLP_STAGE_NEXT_TILE = 1, 2, 4, 8, 16
 _SMEM_LIMIT = 232448            # 227 KB of shared memory per CTA
-_MLP_CONST_BYTES = (2 * 512 + 320) * 4 + 1024  # bias1 / colsum1 / bias2 caches + stage words and barriers (swin_mlp.cu)
+_MLP_FIXED_BYTES = (2 * 512 + 320) * 4 + 512   # bias1 / colsum1 / bias2 caches + barriers (swin_mlp.cu)
 
 
 @dataclass
 class PackedMlp:
-    data: torch.Tensor        # uint8: weight slabs [rows x 64 bf16], 128-byte swizzle, in schedule order
+    w1: torch.Tensor          # uint8: fc1 slabs [hcw[j] rows x 64 bf16], 128-byte swizzle, (chunk, K slab) order
+    w2: torch.Tensor          # uint8: fc2 slabs [piece rows x 64 bf16], (chunk, K slab, piece) order
     bias1: torch.Tensor       # fp32 [nc * hc]
     colsum1: torch.Tensor     # fp32 [nc * hc]
     bias2: torch.Tensor       # fp32 [n2]
@@ -166,8 +166,8 @@ class PackedMlp:
 
 def swin_mlp_plan(c: int, h: int) -> dict:
     """Static tiling of one fused MLP (swin_mlp.cu): hidden chunks of <= 128 columns (two fp32 chunk accumulators plus the
-    fc2 accumulator must fit the 512 TMEM columns), fc2 output split into pieces of >= 128 rows when it is wider than 255,
-    and the slab schedule in the order the MMA warp consumes it (fc1 of chunk j+1 is issued before fc2 of chunk j)."""
+    fc2 accumulator must fit the 512 TMEM columns), the fc2 output issued in two pieces of >= 128 rows when it is wider
+    than 255, and the shared memory left after the two y-tile buffers split between the fc1 and fc2 weight rings."""
     n2 = round_up(c, 16)
     k1steps = (c + 15) // 16
     ks1 = (c + 63) // 64
@@ -177,41 +177,31 @@ def swin_mlp_plan(c: int, h: int) -> dict:
     widths = [hc] * (nc - 1) + [round_up(h - hc * (nc - 1), 16)]
     if n2 >= 256:
         p0 = round_up(n2 // 2, 16)
-        pieces = [(0, p0), (p0, n2 - p0)]
+        pieces = [p0, n2 - p0]
     else:
-        pieces = [(0, n2)]
-    slot_bytes = round_up(max(hc, max(r for _, r in pieces)) * 128, 1024)
-    n_slots = min(8, (_SMEM_LIMIT - 2 * ks1 * 16384 - _MLP_CONST_BYTES) // slot_bytes)
-    if n_slots < 2 or nc > 8 or n2 > 320 or nc * hc > 512:
+        pieces = [n2]
+    s1 = round_up(hc * 128, 1024)
+    s2 = round_up(max(pieces) * 128, 1024)
+    avail = _SMEM_LIMIT - 2 * ks1 * 16384 - _MLP_FIXED_BYTES
+    # bytes per tile through each ring decide how the slots are shared out (at least 2 each)
+    n1, n2s = 2, 2
+    if avail < n1 * s1 + n2s * s2 or nc > 8 or n2 > 320 or nc * hc > 512:
         raise ValueError(f"fused MLP does not fit: C={c} H={h}")
-    stages = []   # (bytes, rows, ksteps, kind, chunk, kidx, dcol, flags)
-
-    def fc1(j, extra=0):
-        for s in range(ks1):
-            fl = (MLP_STAGE_FIRST if s == 0 else 0) | (MLP_STAGE_ACC1_DONE if s == ks1 - 1 else 0) | extra
-            stages.append((widths[j] * 128, widths[j], min(4, k1steps - 4 * s), 0, j, s, 0, fl))
-
-    def fc2(j):
-        ksl = (widths[j] + 63) // 64
-        for s in range(ksl):
-            for pi, (dcol, rows) in enumerate(pieces):
-                fl = (MLP_STAGE_WAIT_H if pi == 0 else 0) | (MLP_STAGE_FIRST if (j == 0 and s == 0) else 0)
-                if j == nc - 1 and s == ksl - 1 and pi == len(pieces) - 1:
-                    fl |= MLP_STAGE_ACC2_DONE
-                stages.append((rows * 128, rows, min(4, widths[j] // 16 - 4 * s), 1, j, s, dcol, fl))
-
-    # software pipeline over the whole chunk stream: fc1 of the NEXT chunk (chunk 0 of the following tile after the last
-    # one) is issued before fc2 of the current chunk; the prologue (fc1 of chunk 0) runs once per CTA
-    fc1(0, MLP_STAGE_NEXT_TILE)
-    n_prologue = len(stages)
-    for j in range(nc):
-        if j + 1 < nc:
-            fc1(j + 1)
-        else:
-            fc1(0, MLP_STAGE_NEXT_TILE)
-        fc2(j)
-    return dict(ks1=ks1, nc=nc, hc=hc, n2=n2, widths=widths, pieces=pieces, slot_bytes=slot_bytes, n_slots=n_slots,
-                acc1_col=(n2, n2 + hc), stages=stages, n_prologue=n_prologue)
+    while True:
+        grew = False
+        for which in ((1, 2) if n1 * s1 <= n2s * s2 else (2, 1)):
+            if which == 1 and n1 < 8 and avail >= (n1 + 1) * s1 + n2s * s2:
+                n1 += 1
+                grew = True
+                break
+            if which == 2 and n2s < 8 and avail >= n1 * s1 + (n2s + 1) * s2:
+                n2s += 1
+                grew = True
+                break
+        if not grew:
+            break
+    return dict(ks1=ks1, k1steps=k1steps, nc=nc, hc=hc, n2=n2, widths=widths, pieces=pieces, w1_slots=n1, w1_slot_bytes=s1,
+                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(n2, n2 + hc))
 
 
 def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
@@ -232,8 +222,8 @@ def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b) -> PackedMlp:
     h, c = w1.shape
     dev = w1.device
     pl = swin_mlp_plan(c, h)
-    hc, nc, n2 = pl["hc"], pl["nc"], pl["n2"]
-    w1g = torch.zeros(nc * hc, pl["ks1"] * 64, device=dev)
+    hc, nc, n2, ks1 = pl["hc"], pl["nc"], pl["n2"], pl["ks1"]
+    w1g = torch.zeros(nc * hc, ks1 * 64, device=dev)
     w1g[:h, :c] = w1 * gamma.detach().float()[None, :]
     w2p = torch.zeros(n2, nc * hc + 64, device=dev)
     w2p[:c, :h] = w2
@@ -243,21 +233,22 @@ def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b) -> PackedMlp:
     bias2 = torch.zeros(n2, device=dev)
     if fc2_b is not None:
         bias2[:c] = fc2_b.detach().float()
-    slabs = []
-    for (_bytes, rows, _ks, kind, j, s, dcol, _fl) in pl["stages"]:
-        if kind == 0:
-            blk = w1g[j * hc:j * hc + rows, 64 * s:64 * s + 64]
-        else:
+    slabs1, slabs2 = [], []
+    for j, wj in enumerate(pl["widths"]):
+        for s in range(ks1):
+            slabs1.append(_swizzle_slab(w1g[j * hc:j * hc + wj, 64 * s:64 * s + 64].contiguous()))
+        for s in range((wj + 63) // 64):
             k0 = j * hc + 64 * s
-            blk = w2p[dcol:dcol + rows, k0:k0 + 64].clone()
-            valid = pl["widths"][j] - 64 * s          # hidden columns of this slab that belong to chunk j
-            if valid < 64:
-                blk[:, valid:] = 0.0
-        slabs.append(_swizzle_slab(blk.contiguous()))
-    plan = [pl["ks1"], nc, hc, n2, pl["acc1_col"][0], pl["acc1_col"][1], pl["n_slots"], pl["slot_bytes"]]
-    plan += pl["widths"] + [0] * (8 - nc)
-    plan += [len(pl["stages"]), pl["n_prologue"]]
-    for st in pl["stages"]:
-        plan += list(st)
-    return PackedMlp(torch.cat(slabs).contiguous(), bias1, colsum1, bias2, torch.tensor(plan, dtype=torch.int32),
-                     float(eps), c, h)
+            valid = wj - 64 * s                      # hidden columns of this slab that belong to chunk j
+            dcol = 0
+            for rows in pl["pieces"]:
+                blk = w2p[dcol:dcol + rows, k0:k0 + 64].clone()
+                if valid < 64:
+                    blk[:, valid:] = 0.0
+                slabs2.append(_swizzle_slab(blk))
+                dcol += rows
+    pieces = pl["pieces"] + [0] * (2 - len(pl["pieces"]))
+    plan = [ks1, pl["k1steps"], nc, hc, n2, pl["acc1_col"][0], pl["acc1_col"][1], len(pl["pieces"]), pieces[0], pieces[1],
+            pl["w1_slots"], pl["w1_slot_bytes"], pl["w2_slots"], pl["w2_slot_bytes"]] + pl["widths"] + [0] * (8 - nc)
+    return PackedMlp(torch.cat(slabs1).contiguous(), torch.cat(slabs2).contiguous(), bias1, colsum1, bias2,
+                     torch.tensor(plan, dtype=torch.int32), float(eps), c, h)

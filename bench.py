@@ -302,8 +302,9 @@ def main():
             best_ws, a_ssim, a_mse, a_psnr = metrics.aucs_from_scores(y, np.asarray(table), wss)
             auc = {"best_ws": int(best_ws), "ssim": a_ssim, "mse": a_mse, "psnr": a_psnr}
 
-    # ---- roofline of the dominant kernel (tc_gemm_kernel): per-launch CUDA events in one extra, untimed step
+    # ---- roofline of the dominant (tcgen05) kernels: per-launch CUDA events in one extra, untimed step
     roofline = None
+    TENSOR_KINDS = ("tc_gemm", "conv3x3", "swin_mlp", "swin_attn")
     if rank == 0:
         ops.PROFILE = []
         barrier() if world == 1 else torch.cuda.synchronize()
@@ -311,7 +312,7 @@ def main():
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         peaks = load_peaks()
-        gemm = [(p[1], p[2].elapsed_time(p[3])) for p in prof if p[0] in ("tc_gemm", "conv3x3")]
+        gemm = [(p[1], p[2].elapsed_time(p[3])) for p in prof if p[0] in TENSOR_KINDS]
         allk = [(p[0], p[2].elapsed_time(p[3])) for p in prof]
         flops = sum(f for f, _ in gemm)
         tms = sum(d for _, d in gemm)
@@ -320,7 +321,7 @@ def main():
         by_kind = {}
         for k, d in allk:
             by_kind[k] = by_kind.get(k, 0.0) + d
-        roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 GEMM + implicit-GEMM conv)", "achieved": achieved,
+        roofline = {"bound": "tensor", "kernel": "tcgen05 kernels: " + ", ".join(TENSOR_KINDS), "achieved": achieved,
                     "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["sustained"],
                     "frac_of_burst": achieved / peaks["burst"], "peak_source": peaks["source"] + " (sustained bf16)",
                     "traffic": None, "launches": len(gemm), "flops_per_step": flops, "kernel_ms_per_step": tms,

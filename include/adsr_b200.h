@@ -66,13 +66,14 @@ int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K,
 
 /* ---- fused Swin MLP half: z = y + fc2(GELU(fc1(LayerNorm(y))))   (one kernel, hidden activations stay in TMEM) ----
  * replaces norm2 + Mlp.forward + the second residual of SwinTransformerBlock.forward (src/drct.py:510, 173-190).
- * w_packed / bias1 / colsum1 / bias2 / plan come from pack.pack_swin_mlp(): the fc1 weights carry the LayerNorm gamma,
- * fc2 carries the 0.5 of GELU; `plan` (host memory, int32) is the static schedule of weight slabs:
- *   [ks1, nc, hc, n2, acc1_col0, acc1_col1, n_slots, slot_bytes, hcw[8], n_stages, n_prologue, n_stages x {bytes, rows,
- *    ksteps, kind, chunk, kidx, dcol, flags}]  (the first n_prologue stages run once per CTA, the rest once per tile).
+ * w1_packed / w2_packed / bias1 / colsum1 / bias2 / plan come from pack.pack_swin_mlp(): the fc1 weights carry the
+ * LayerNorm gamma, fc2 carries the 0.5 of GELU; `plan` (host memory, int32) is the static tiling
+ *   [ks1, k1steps, nc, hc, n2, acc1_col0, acc1_col1, n_pieces, piece_rows0, piece_rows1, w1_slots, w1_slot_bytes,
+ *    w2_slots, w2_slot_bytes, hcw[8]].
  * Row mean / rstd come from ln_stats_in exactly as in adsr_tc_gemm_bf16.  y and z must not alias. */
 int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C,
-                       const void* w_packed, const float* bias1, const float* colsum1, const float* bias2,
+                       const void* w1_packed, const void* w2_packed,
+                       const float* bias1, const float* colsum1, const float* bias2,
                        const int32_t* plan, int plan_len, float ln_eps,
                        const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
                        void* z, int64_t ldz, int num_sms, void* stream);
