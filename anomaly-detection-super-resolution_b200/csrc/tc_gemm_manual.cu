@@ -123,10 +123,10 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
 
     if (warp == 0) {
         // ================================ B loader: one bulk copy per ring stage =================
-        if (lane == 0) {
+        {   // converged warp, one elected lane issues (keeps descriptors in uniform registers)
             const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
             const uint32_t tx_bytes = b_bytes + (!CONV ? static_cast<uint32_t>(kAStageBytes) : 0u);
-            if (!CONV) tma_prefetch_desc(&p.tmap_a);
+            if (!CONV && lane == 0) tma_prefetch_desc(&p.tmap_a);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -135,17 +135,20 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
                 const uint8_t* src = p.Bp + static_cast<size_t>(n_tile) * p.num_k_stages * b_bytes;
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
-                    if (!CONV) tma_load_2d(smem_a + stage * kAStageBytes, &p.tmap_a, ks * 64, m0, &bars->full[stage]);
-                    bulk_g2s(smem_b + stage * kBStageBytes, src + static_cast<size_t>(ks) * b_bytes, b_bytes,
-                             &bars->full[stage]);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
+                        if (!CONV) tma_load_2d(smem_a + stage * kAStageBytes, &p.tmap_a, ks * 64, m0, &bars->full[stage]);
+                        bulk_g2s(smem_b + stage * kBStageBytes, src + static_cast<size_t>(ks) * b_bytes, b_bytes,
+                                 &bars->full[stage]);
+                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (single thread) ================================
-        if (lane == 0) {
+        {   // converged warp, one elected lane issues
             const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.BN));
             int stage = 0;
             uint32_t phase = 0;
@@ -168,15 +171,18 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
                     tc_fence_after_sync();
                     const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * kAStageBytes));
                     const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * kBStageBytes));
-                    for (int k = 0; k < steps; ++k) {
+                    if (elect_one_sync()) {
                         // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
-                        umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                                  (ks | k) != 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
+                        if (steps > 1) umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                        if (steps > 2) umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                        if (steps > 3) umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                        umma_commit(&bars->empty[stage]);      // frees the ring slot when the MMAs retire
+                        if (ks == p.num_k_stages - 1) umma_commit(&bars->tmem_full[buf]);   // accumulator complete -> epilogue
                     }
-                    umma_commit(&bars->empty[stage]);          // frees the ring slot when the MMAs retire
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&bars->tmem_full[buf]);            // accumulator complete -> epilogue
             }
         }
     } else if (warp >= 4 && warp < 4 + kEpiWarps) {
