@@ -57,6 +57,10 @@ int launch_tc_gemm_manual(const TcGemmParams& p, int grid, cudaStream_t stream);
 // Encodes the TMA descriptor of a row-major bf16 matrix (driver entry point resolved at run time).
 int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems);
 
+// ---- tcgen05 window attention for 8x8 windows (attention_tc.cu); ADSR_ERR_BAD_SHAPE = shape not covered, use the mma.sync kernel
+int launch_window_attention_tc(const void* qkv, long long ldq, void* out, long long ldo, const float* table, int B, int H, int W,
+                               int shift, int nH, int hd, int hdp, int num_sms, cudaStream_t stream);
+
 // ---- fused Swin MLP (swin_mlp.cu)
 struct SwinMlpParams {
     CUtensorMap tmap_y;   // [M x C] bf16, box 64 x 128, 128-byte swizzle (loads)

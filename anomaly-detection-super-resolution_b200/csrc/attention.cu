@@ -449,6 +449,11 @@ int launch_attn(const AttnParams& p, cudaStream_t stream) {
 }  // namespace
 }  // namespace adsr
 
+// tuning / test hook (not part of the public header): 0 forces the mma.sync kernels even for 8x8 windows, 2 forces the tcgen05
+// kernel for every head width it supports
+static int g_attn_tc_enabled = 1;
+extern "C" void adsr_debug_set_attention_tc(int enabled) { g_attn_tc_enabled = enabled; }
+
 extern "C" int adsr_window_attention(const void* qkv, int64_t ldq, void* out, int64_t ldo, const float* bias_table,
                                      int B, int H, int W, int ws, int shift, int nH, int hd, int hdp, void* stream) {
     using namespace adsr;
@@ -471,6 +476,19 @@ extern "C" int adsr_window_attention(const void* qkv, int64_t ldq, void* out, in
     p.total_slots = B * p.nW * N;
     p.scale_log2e = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ws == 8 && (g_attn_tc_enabled == 2 || (g_attn_tc_enabled == 1 && hdp <= 64))) {
+        // (heads wider than 64 channels need two panels per operand and only a 2-deep ring: the mma.sync kernel is still faster there)
+        // DRCT-L shape: tcgen05 kernel (S and O in TMEM); shapes it does not cover fall through to the mma.sync kernels
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess ||
+                cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+                return ADSR_ERR_CUDA;
+        }
+        const int rc = launch_window_attention_tc(qkv, ldq, out, ldo, bias_table, B, H, W, shift, nH, hd, hdp, num_sms, st);
+        if (rc != ADSR_ERR_BAD_SHAPE) return rc;
+    }
     if (N == 64) {
         switch (hdp / 16) {
             case 1: return dispatch_attn64<1>(p, st);

@@ -59,3 +59,37 @@ def test_window_attention(H, ws, shift, heads, hd):
     assert err < 0.03, f"attention max abs err {err}"
     if hdp > hd:
         assert float(got[:, :, hd:].abs().max()) == 0.0, "head padding columns must be exact zeros"
+
+
+@pytest.mark.parametrize("heads,hd,shift", [(6, 30, 0), (6, 30, 4), (4, 53, 4), (2, 122, 0), (2, 122, 4), (6, 46, 4), (4, 77, 0)])
+@pytest.mark.parametrize("mode", [0, 2])
+def test_window_attention_both_kernels(heads, hd, shift, mode):
+    """ws = 8: the tcgen05 kernel (mode 2, forced for every head width) and the mma.sync kernel (mode 0) against torch,
+    several tiles per CTA (B = 40 -> 320 window pairs on 148 SMs)."""
+    import ctypes
+    ops, pack, abi = mod("ops"), mod("pack"), mod("_abi")
+    setter = abi.lib().adsr_debug_set_attention_tc
+    setter.restype, setter.argtypes = None, [ctypes.c_int]
+    torch.manual_seed(hd + shift)
+    B, H, ws = 40, 32, 8
+    M = B * H * H
+    hdp = pack.head_pad(hd)
+    q, k, v = (torch.randn(M, heads, hd, device=DEV) for _ in range(3))
+    table = torch.randn((2 * ws - 1) ** 2, heads, device=DEV) * 0.5
+    qkv = torch.zeros(M, 3 * heads * hdp, device=DEV, dtype=torch.bfloat16)
+    for i, t in enumerate((q, k, v)):
+        qkv.view(M, 3, heads, hdp)[:, i, :, :hd] = t.to(torch.bfloat16)
+    out = torch.full((M, heads * hdp), 3.0, device=DEV, dtype=torch.bfloat16)
+    setter(mode)
+    try:
+        ops.window_attention(qkv, out, table, B, H, H, ws, shift, heads, hd, hdp)
+        torch.cuda.synchronize()
+    finally:
+        setter(1)
+    r = lambda t: t.to(torch.bfloat16).float()
+    want = _attention_want(r(q), r(k), r(v), table, B, H, H, ws, shift, heads, hd)
+    got = out.view(M, heads, hdp).float()
+    err = float((got[:, :, :hd] - want).abs().max())
+    assert err < 0.03, f"mode {mode}: attention max abs err {err}"
+    if hdp > hd:
+        assert float(got[:, :, hd:].abs().max()) == 0.0
