@@ -54,6 +54,8 @@ struct TcGemmParams {
 
 int launch_tc_gemm(TcGemmParams& p, int num_sms, cudaStream_t stream);
 int launch_tc_gemm_manual(const TcGemmParams& p, int grid, cudaStream_t stream);   // tc_gemm_manual.cu
+bool tc_gemm_rows_eligible(const TcGemmParams& p);                                  // tc_gemm_rows.cu
+int launch_tc_gemm_rows(TcGemmParams& p, int num_sms, cudaStream_t stream);
 // Encodes the TMA descriptor of a row-major bf16 matrix (driver entry point resolved at run time).
 int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems);
 

@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(256) drct_head_kernel(const float* __restrict_
             osq = warp_sum(osq);
             if (lane == 0) {
                 stats_out[pix * stats_stride] = make_float2(osum, osq);
-                stats_out[pix * stats_stride + 1] = make_float2(0.f, 0.f);
+                for (int s = 1; s < stats_stride && s < 4; ++s)     // the slots later written by the adjust5 epilogue
+                    stats_out[pix * stats_stride + s] = make_float2(0.f, 0.f);
             }
         }
     }

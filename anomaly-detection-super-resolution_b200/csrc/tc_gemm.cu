@@ -587,6 +587,9 @@ int launch_tc_gemm(TcGemmParams& p, int num_sms, cudaStream_t stream) {
         ((p.BN % 32) != 0 || (p.ldo % 8) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15)))
         return ADSR_ERR_BAD_SHAPE;
 
+    // short-K row outputs packed with BN = 128: the row-tile kernel (tc_gemm_rows.cu)
+    if (tc_gemm_rows_eligible(p)) return launch_tc_gemm_rows(p, num_sms, stream);
+
     // TMA epilogue when there is a residual to add (row-major output at a 16-byte aligned column, chunks never straddle
     // N tiles).  Without a residual the manual epilogue is faster today: with two staging tiles per warp the TMA-store
     // latency caps the store bandwidth of wide outputs (measured 1.9 vs 2.4 TB/s on the qkv shape).

@@ -191,7 +191,7 @@ class DRCT(nn.Module):
                 b.proj = pack.pack_proj_weight(sw.attn.proj.weight, sw.attn.proj.bias, b.heads)
                 b.mlp = pack.pack_swin_mlp(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias, sw.norm2.eps,
                                            sw.mlp.fc2.weight, sw.mlp.fc2.bias)
-                b.adjust = pack.pack_gemm_weight(adj.weight, adj.bias)
+                b.adjust = pack.pack_gemm_weight(adj.weight, adj.bias, rows_kernel=(k == 4))
                 blocks.append(b)
             P["blocks"].append(blocks)
         P["norm_w"], P["norm_b"] = f32(self.norm.weight), f32(self.norm.bias)
@@ -232,7 +232,7 @@ class DRCT(nn.Module):
             "h": torch.zeros(M, hid_w, **bf), "x0": torch.zeros(M, e16, **bf), "body": torch.zeros(M, e16, **bf),
             "f": torch.zeros(M, 64, **bf),
             # per-row (sum, sumsq) partials for the folded LayerNorms: slab = x (2 slots) + x1..x4 (2 slots each); y = proj
-            "st_slab": torch.zeros(M, 10, 2, dtype=torch.float32, device=dev),
+            "st_slab": torch.zeros(M, 12, 2, dtype=torch.float32, device=dev),
             "st_y": torch.zeros(M, 8, 2, dtype=torch.float32, device=dev),
         }
         ups, m = [], M
@@ -277,11 +277,12 @@ class DRCT(nn.Module):
                       stats_out=st_slab)
 
         for blocks in P["blocks"]:
+            xs = 2 * blocks[-1].adjust.n_tiles        # st_slab: x owns the first xs slots (written by adjust5), each x_j two more
             for k, b in enumerate(blocks):
                 C = b.dim
                 # ---- W-MSA / SW-MSA half (src/drct.py:478-509); norm1 is folded into the qkv GEMM, its row statistics
-                #      are the partial sums the producing epilogues left in st_slab (x: 2 slots, each x_j: 2 slots)
-                ops.tc_gemm(slab, C, b.qkv, qkv, stats_in=(st_slab, 2 * (k + 1)))
+                #      are the partial sums the producing epilogues left in st_slab
+                ops.tc_gemm(slab, C, b.qkv, qkv, stats_in=(st_slab, xs + 2 * k))
                 ops.window_attention(qkv, att, b.table, B, H, W, b.ws, b.shift, b.heads, b.hd, b.hdp)
                 ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0))
                 # ---- MLP half (src/drct.py:510, 185-189): norm2 + fc1 + GELU + fc2 + residual in ONE kernel, the hidden
@@ -290,7 +291,7 @@ class DRCT(nn.Module):
                 # ---- adjust 1x1 conv (+LeakyReLU 0.2) into the slab slice / 0.2*x5 + x  (src/drct.py:389-396)
                 if not b.last:
                     ops.tc_gemm(z, C, b.adjust, slab, act=ops.ACT_LRELU, slope=0.2, ocol0=C, n_store=b.adjust_out,
-                                stats_out=(st_slab, 2 + 2 * k))
+                                stats_out=(st_slab, xs + 2 * k))
                 else:
                     ops.tc_gemm(z, C, b.adjust, slab, alpha=0.2, res=slab, stats_out=(st_slab, 0))
 

@@ -73,11 +73,12 @@ def _pad_bias(bias: Optional[torch.Tensor], n: int, total: int, device) -> torch
     return b
 
 
-def pack_gemm_weight(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedWeight:
-    """weight: [N, K] (nn.Linear / 1x1 conv layout)."""
+def pack_gemm_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], rows_kernel: bool = False) -> PackedWeight:
+    """weight: [N, K] (nn.Linear / 1x1 conv layout).  rows_kernel=True packs N tiles of 128 rows, the layout the row-tile
+    kernel (csrc/tc_gemm_rows.cu, K <= 320, 16-byte aligned output columns) streams."""
     w = weight.detach().float().reshape(weight.shape[0], -1)
     n, k = w.shape
-    bn, n_tiles = choose_bn(n)
+    bn, n_tiles = (128, (n + 127) // 128) if (rows_kernel and k <= 320) else choose_bn(n)
     kpad = round_up(k, 64)
     w2 = torch.zeros(n, kpad, dtype=torch.float32, device=w.device)
     w2[:, :k] = w
@@ -86,7 +87,7 @@ def pack_gemm_weight(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> Pack
 
 
 def pack_ln_gemm_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
-                        eps: float = 1e-5) -> PackedWeight:
+                        eps: float = 1e-5, rows_kernel: bool = False) -> PackedWeight:
     """Linear applied to LayerNorm(x) with the normalisation folded into the GEMM:
          LN(x) W^T + b = rstd * (x (gamma*W)^T - mean * s) + t,   s_n = sum_k gamma_k W_nk,   t_n = sum_k beta_k W_nk + b_n.
     The kernel multiplies RAW rows with the packed gamma*W and applies mean / rstd / s / t in its epilogue; s is taken from
@@ -94,7 +95,7 @@ def pack_ln_gemm_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], gamm
     w = weight.detach().float().reshape(weight.shape[0], -1)
     wg = w * gamma.detach().float()[None, :]
     t = w @ beta.detach().float() + (bias.detach().float() if bias is not None else 0.0)
-    pw = pack_gemm_weight(wg, t)
+    pw = pack_gemm_weight(wg, t, rows_kernel)
     s = wg.to(torch.bfloat16).float().sum(dim=1)
     pw.colsum = _pad_bias(s, w.shape[0], pw.BN * pw.n_tiles, w.device)
     pw.ln_eps = float(eps)
@@ -131,8 +132,8 @@ def pack_qkv_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: i
     if bias is not None:
         b3[:, :, :hd] = bias.detach().float().view(3, heads, hd)
     if gamma is not None:                       # norm1 folded into the qkv GEMM
-        return pack_ln_gemm_weight(w3.view(3 * heads * hdp, c), b3.view(-1), gamma, beta, eps)
-    return pack_gemm_weight(w3.view(3 * heads * hdp, c), b3.view(-1))
+        return pack_ln_gemm_weight(w3.view(3 * heads * hdp, c), b3.view(-1), gamma, beta, eps, rows_kernel=True)
+    return pack_gemm_weight(w3.view(3 * heads * hdp, c), b3.view(-1), rows_kernel=True)
 
 
 def pack_proj_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: int) -> PackedWeight:
@@ -143,7 +144,7 @@ def pack_proj_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: 
     hdp = head_pad(hd)
     w2 = torch.zeros(w.shape[0], heads, hdp, dtype=torch.float32, device=w.device)
     w2[:, :, :hd] = w.view(w.shape[0], heads, hd)
-    return pack_gemm_weight(w2.view(w.shape[0], heads * hdp), bias)
+    return pack_gemm_weight(w2.view(w.shape[0], heads * hdp), bias, rows_kernel=True)
 
 
 # ------------------------------------------------------------------------------------------------ fused Swin MLP

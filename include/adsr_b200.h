@@ -118,7 +118,8 @@ int adsr_window_reverse_unshift(const void* windows, int64_t ldw, void* x, int64
 
 /* ---- DRCT head: (x - mean)*img_range -> conv_first 3x3 -> x0 (long skip) and LayerNorm(x0) -> slab -------
  * src/drct.py:887-892, 650-654 (patch_embed.norm).  x: fp32 NCHW, weights fp32 [C, nc, 3, 3].
- * stats_out (optional): (sum, sumsq) of each slab row in slot 0 and zeros in slot 1, for the first folded LayerNorm. */
+ * stats_out (optional): (sum, sumsq) of each slab row in slot 0 and zeros in slots 1..3 (the slots the adjust5 epilogue
+ * fills from the second RDG on), for the first folded LayerNorm. */
 int adsr_drct_head(const float* x_nchw, int B, int nc, int H, int W,
                    const float* weight, const float* bias, const float* mean, float img_range,
                    const float* ln_gamma, const float* ln_beta, float eps, int C,

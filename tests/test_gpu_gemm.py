@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _gemm_case(M, K, N, act="none", res=False, alpha=1.0, ocol0=0, n_store=None, seed=0):
+def _gemm_case(M, K, N, act="none", res=False, alpha=1.0, ocol0=0, n_store=None, seed=0, rows=False):
     ops, pack = mod("ops"), mod("pack")
     torch.manual_seed(seed)
     lda = (K + 63) // 64 * 64 + 64
@@ -19,7 +19,7 @@ def _gemm_case(M, K, N, act="none", res=False, alpha=1.0, ocol0=0, n_store=None,
     a[:, K:k8] = 3.0                                                          # finite junk in the K tail
     w = torch.randn(N, K, device=DEV) * 0.1
     bias = torch.randn(N, device=DEV)
-    pw = pack.pack_gemm_weight(w, bias)
+    pw = pack.pack_gemm_weight(w, bias, rows_kernel=rows)
     ldo = 1024
     out = torch.full((M, ldo), -7.0, device=DEV, dtype=torch.bfloat16)
     r = torch.randn(M, 512, device=DEV).to(torch.bfloat16) if res else None
@@ -69,6 +69,26 @@ def test_gemm_epilogues():
     _gemm_case(300, 308, 180, act="none", res=True, alpha=0.2, seed=7)
     _gemm_case(300, 180, 32, act="lrelu", ocol0=180, n_store=32, seed=8)     # slab slice at an 8-byte aligned column
     _gemm_case(300, 276, 276, act="relu", seed=9)
+
+
+@pytest.mark.parametrize("K", [64, 180, 212, 244, 276, 308])
+@pytest.mark.parametrize("N", [32, 180, 308, 576, 864, 960])
+def test_gemm_rows_kernel_shapes(K, N):
+    """row-tile kernel (tc_gemm_rows.cu): weights packed in 128-row N tiles, M tail, several tiles per CTA on small grids"""
+    _gemm_case(128 * 3 + 77, K, N, seed=K + N, rows=True)
+
+
+def test_gemm_rows_kernel_many_tiles_per_cta():
+    _gemm_case(128 * 148 * 5 + 9, 180, 576, seed=31, rows=True)            # 5 N tiles x 3 K slabs, A double buffered
+    _gemm_case(128 * 148 * 4 + 9, 308, 308, res=True, seed=32, rows=True)  # 5 K slabs, single A buffer, residual
+
+
+def test_gemm_rows_kernel_epilogues():
+    _gemm_case(128 * 160 + 5, 256, 244, act="none", res=True, seed=16, rows=True)       # proj: residual, > 148 tiles
+    _gemm_case(700, 308, 180, act="none", res=True, alpha=0.2, seed=17, rows=True)      # adjust5: 0.2 * v + x
+    _gemm_case(700, 180, 360, act="gelu", seed=18, rows=True)
+    _gemm_case(700, 192, 96, act="lrelu", ocol0=64, n_store=96, seed=19, rows=True)     # column offset, exact n_store
+    _gemm_case(700, 276, 276, act="relu", res=True, seed=20, rows=True)
 
 
 def _conv_case(B, H, W, Cin, Cout, stride=1, act="none", res=False, ps=False, seed=0):
@@ -134,8 +154,9 @@ def _row_stats(t: torch.Tensor, slots: int) -> torch.Tensor:
     return st
 
 
+@pytest.mark.parametrize("rows", [False, True])
 @pytest.mark.parametrize("K,N,act", [(180, 576, "none"), (212, 424, "gelu"), (308, 960, "none"), (60, 120, "gelu")])
-def test_gemm_with_folded_layernorm(K, N, act):
+def test_gemm_with_folded_layernorm(K, N, act, rows):
     """LayerNorm(K) folded into the GEMM: raw rows in, row statistics from the (sum, sumsq) slots."""
     ops, pack = mod("ops"), mod("pack")
     torch.manual_seed(K + N)
@@ -144,7 +165,7 @@ def test_gemm_with_folded_layernorm(K, N, act):
     a[:, :K] = (torch.randn(M, K, device=DEV) * 2.5 + 1.5 * torch.randn(M, 1, device=DEV)).to(torch.bfloat16)
     w, b = torch.randn(N, K, device=DEV) * 0.1, torch.randn(N, device=DEV)
     g, bt = torch.rand(K, device=DEV) + 0.5, torch.randn(K, device=DEV) * 0.3
-    pw = pack.pack_ln_gemm_weight(w, b, g, bt, 1e-5)
+    pw = pack.pack_ln_gemm_weight(w, b, g, bt, 1e-5, rows_kernel=rows)
     st = _row_stats(a[:, :K], 4)
     st[:, 1] = st[:, 0] * 0.25                                                  # statistics split over two slots
     st[:, 0] = st[:, 0] * 0.75
@@ -158,15 +179,16 @@ def test_gemm_with_folded_layernorm(K, N, act):
     assert err < 0.015, f"LN-folded GEMM K={K} N={N}: rel err {err}"
 
 
+@pytest.mark.parametrize("rows", [False, True])
 @pytest.mark.parametrize("N,res", [(32, False), (180, True), (308, True)])
-def test_gemm_emits_row_statistics(N, res):
+def test_gemm_emits_row_statistics(N, res, rows):
     """stats_out: per-row (sum, sumsq) partials of the stored output, in deterministic slots."""
     ops, pack = mod("ops"), mod("pack")
     torch.manual_seed(N)
     M, K = 1000, 244
     a = torch.randn(M, 256, device=DEV).to(torch.bfloat16)
     w, b = torch.randn(N, K, device=DEV) * 0.1, torch.randn(N, device=DEV)
-    pw = pack.pack_gemm_weight(w, b)
+    pw = pack.pack_gemm_weight(w, b, rows_kernel=rows)
     r = torch.randn(M, 320, device=DEV).to(torch.bfloat16) if res else None
     out = torch.zeros(M, 320, device=DEV, dtype=torch.bfloat16)
     st = torch.full((M, 10, 2), 7.0, device=DEV)

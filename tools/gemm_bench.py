@@ -20,7 +20,7 @@ def timeit(fn, reps=5):
 
 def gemm(K, N, act=0, res=False, name=""):
     a = torch.randn(M, ((K + 63) // 64) * 64, device=dev).to(torch.bfloat16)
-    w = pack.pack_gemm_weight(torch.randn(N, K, device=dev) * 0.05, torch.randn(N, device=dev))
+    w = pack.pack_gemm_weight(torch.randn(N, K, device=dev) * 0.05, torch.randn(N, device=dev), rows_kernel=bool(int(os.environ.get('ROWS', '1'))))
     out = torch.empty(M, ((N + 63) // 64) * 64, device=dev, dtype=torch.bfloat16)
     r = torch.randn(M, 320, device=dev).to(torch.bfloat16) if res else None
     best, avg = timeit(lambda: ops.tc_gemm(a, K, w, out, act=act, res=r))
