@@ -28,9 +28,12 @@ def gemm(K, N, act=0, res=False, name=""):
     byt = 2.0 * M * (K + N + (N if res else 0))
     print(f"gemm {name:10s} K={K:4d} N={N:4d} BN={w.BN:3d}x{w.n_tiles} : {best*1e3:8.1f} us  {fl/best/1e9:7.1f} TFLOP/s  {byt/best/1e6:7.1f} GB/s(min traffic)")
 
-for (K, N, act, res, nm) in [(180, 576, 0, False, "qkv1"), (192, 180, 0, True, "proj1"), (180, 360, 2, False, "fc1_1"), (360, 180, 0, True, "fc2_1"), (180, 32, 1, False, "adj1"),
+_shapes = [(180, 576, 0, False, "qkv1"), (192, 180, 0, True, "proj1"), (180, 360, 2, False, "fc1_1"), (360, 180, 0, True, "fc2_1"), (180, 32, 1, False, "adj1"),
                              (244, 768, 0, False, "qkv3"), (256, 244, 0, True, "proj3"), (244, 488, 2, False, "fc1_3"), (488, 244, 0, True, "fc2_3"),
-                             (308, 960, 0, False, "qkv5"), (308, 180, 0, True, "adj5")]:
+                             (308, 960, 0, False, "qkv5"), (308, 180, 0, True, "adj5")]
+if os.environ.get("GEMM_SHAPE"):
+    _shapes = [s_ for s_ in _shapes if s_[4] == os.environ["GEMM_SHAPE"]]
+for (K, N, act, res, nm) in _shapes:
     gemm(K, N, act, res, nm)
 
 if os.environ.get("GEMM_ONLY"):
