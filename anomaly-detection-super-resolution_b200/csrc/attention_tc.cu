@@ -245,48 +245,109 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_tc_kernel(const __gri
         const uint32_t n_pv = static_cast<uint32_t>(p.hpl * p.hdp);     // pairs: both heads' V columns in one N = 64 MMA
         const uint32_t idesc_pv = idesc_bf16_m128(n_pv, 1);
         const int ksteps_s = p.hdp >> 4;
-        for (int u = 0; u <= n_units; ++u) {
-            if (u < n_units) {
-                // ---- S(u) = Q K^T
-                const int it = u / p.nH, h = u - it * p.nH;
-                const int g = it * groups_per_tile + h / p.hpl;
-                const int buf = g % p.nbuf;
-                const int sb = u & 1;
-                if ((h % p.hpl) == 0) mbar_wait(&bars->full[buf], static_cast<uint32_t>(g / p.nbuf) & 1);
-                tc_fence_after_sync();
-                const uint32_t qa = smem_u32(bufs + buf * buf_bytes);
-                const uint32_t k0 = static_cast<uint32_t>((h % p.hpl) * ksteps_s);   // first K=16 step of this head in the panel
-                if (elect_one_sync()) {
-                    for (int k = 0; k < ksteps_s; ++k) {
-                        const uint32_t ks = k0 + static_cast<uint32_t>(k);
-                        const uint32_t off = (ks >> 2) * kPanelBytes + (ks & 3) * 32;
-                        umma_bf16(tmem + static_cast<uint32_t>(sb * 128), umma_desc_k_sw128(qa + off),
-                                  umma_desc_k_sw128(qa + op_bytes + off), idesc_s, k == 0 ? 0u : 1u);
+        if (p.hpl == 2) {
+            // head pairs (3 load groups per tile): the fixed order S(u), P V(u - 1) measured faster than the opportunistic one
+            for (int u = 0; u <= n_units; ++u) {
+                if (u < n_units) {
+                    // ---- S(u) = Q K^T
+                    const int it = u / p.nH, h = u - it * p.nH;
+                    const int g = it * groups_per_tile + h / p.hpl;
+                    const int buf = g % p.nbuf;
+                    const int sb = u & 1;
+                    if ((h % p.hpl) == 0) mbar_wait(&bars->full[buf], static_cast<uint32_t>(g / p.nbuf) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t qa = smem_u32(bufs + buf * buf_bytes);
+                    const uint32_t k0 = static_cast<uint32_t>((h % p.hpl) * ksteps_s);   // first K=16 step of this head in the panel
+                    if (elect_one_sync()) {
+                        for (int k = 0; k < ksteps_s; ++k) {
+                            const uint32_t ks = k0 + static_cast<uint32_t>(k);
+                            const uint32_t off = (ks >> 2) * kPanelBytes + (ks & 3) * 32;
+                            umma_bf16(tmem + static_cast<uint32_t>(sb * 128), umma_desc_k_sw128(qa + off),
+                                      umma_desc_k_sw128(qa + op_bytes + off), idesc_s, k == 0 ? 0u : 1u);
+                        }
+                        umma_commit(&bars->s_full[sb]);
                     }
-                    umma_commit(&bars->s_full[sb]);
+                    __syncwarp();
                 }
-                __syncwarp();
+                if (u >= 1) {
+                    // ---- O(v) = P V
+                    const int v = u - 1;
+                    const int it = v / p.nH, h = v - it * p.nH;
+                    const int g = it * groups_per_tile + h / p.hpl;
+                    const int buf = g % p.nbuf;
+                    const int sb = v & 1;
+                    mbar_wait(&bars->p_ready[sb], static_cast<uint32_t>(v >> 1) & 1);
+                    mbar_wait(&bars->o_free[sb], (static_cast<uint32_t>(v >> 1) & 1) ^ 1);
+                    tc_fence_after_sync();
+                    const uint32_t va = smem_u32(bufs + buf * buf_bytes) + 2u * static_cast<uint32_t>(op_bytes);
+                    if (elect_one_sync()) {
+    #pragma unroll
+                        for (int k = 0; k < 8; ++k)                         // 16 keys per step: 16 rows x 128 B further down the panel
+                            umma_bf16_ts(tmem + 256u + static_cast<uint32_t>(sb * 128), tmem + static_cast<uint32_t>(sb * 128 + 8 * k),
+                                         umma_desc_mn_sw128(va + static_cast<uint32_t>(k * 2048), kPanelBytes), idesc_pv, k == 0 ? 0u : 1u);
+                        umma_commit(&bars->o_full[sb]);
+                        umma_commit(&bars->empty[buf]);
+                    }
+                    __syncwarp();
+                }
             }
-            if (u >= 1) {
-                // ---- O(v) = P V
-                const int v = u - 1;
-                const int it = v / p.nH, h = v - it * p.nH;
-                const int g = it * groups_per_tile + h / p.hpl;
-                const int buf = g % p.nbuf;
-                const int sb = v & 1;
-                mbar_wait(&bars->p_ready[sb], static_cast<uint32_t>(v >> 1) & 1);
-                mbar_wait(&bars->o_free[sb], (static_cast<uint32_t>(v >> 1) & 1) ^ 1);
-                tc_fence_after_sync();
-                const uint32_t va = smem_u32(bufs + buf * buf_bytes) + 2u * static_cast<uint32_t>(op_bytes);
-                if (elect_one_sync()) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)                         // 16 keys per step: 16 rows x 128 B further down the panel
-                        umma_bf16_ts(tmem + 256u + static_cast<uint32_t>(sb * 128), tmem + static_cast<uint32_t>(sb * 128 + 8 * k),
-                                     umma_desc_mn_sw128(va + static_cast<uint32_t>(k * 2048), kPanelBytes), idesc_pv, k == 0 ? 0u : 1u);
-                    umma_commit(&bars->o_full[sb]);
-                    umma_commit(&bars->empty[buf]);
+        } else {
+            // S(u) needs its load group, P V(u) needs the softmax of unit u: whichever is ready first is issued first, so that a
+            // late load never holds back a P V whose probabilities are waiting in TMEM (and the other way round).  The S buffer of
+            // unit u is the one of unit u - 2: S(u) may only be issued once P V(u - 2) has been (the tensor pipe runs in order).
+            auto ready = [&](uint64_t* bar, uint32_t parity) -> bool {     // one lane polls, the warp stays converged
+                uint32_t ok = 0;
+                if (lane == 0) ok = mbar_test_wait(bar, parity) ? 1u : 0u;
+                return __shfl_sync(0xffffffffu, ok, 0) != 0;
+            };
+            int us = 0, up = 0;                                            // next S unit / next P V unit to issue
+            while (up < n_units) {
+                if (us < n_units && us < up + 2) {
+                    const int it = us / p.nH, h = us - it * p.nH;
+                    const int g = it * groups_per_tile + h / p.hpl;
+                    const int buf = g % p.nbuf;
+                    if ((h % p.hpl) != 0 || ready(&bars->full[buf], static_cast<uint32_t>(g / p.nbuf) & 1)) {
+                        // ---- S(us) = Q K^T
+                        const int sb = us & 1;
+                        tc_fence_after_sync();
+                        const uint32_t qa = smem_u32(bufs + buf * buf_bytes);
+                        const uint32_t k0 = static_cast<uint32_t>((h % p.hpl) * ksteps_s);   // first K=16 step of this head in the panel
+                        if (elect_one_sync()) {
+                            for (int k = 0; k < ksteps_s; ++k) {
+                                const uint32_t ks = k0 + static_cast<uint32_t>(k);
+                                const uint32_t off = (ks >> 2) * kPanelBytes + (ks & 3) * 32;
+                                umma_bf16(tmem + static_cast<uint32_t>(sb * 128), umma_desc_k_sw128(qa + off),
+                                          umma_desc_k_sw128(qa + op_bytes + off), idesc_s, k == 0 ? 0u : 1u);
+                            }
+                            umma_commit(&bars->s_full[sb]);
+                        }
+                        __syncwarp();
+                        ++us;
+                    }
                 }
-                __syncwarp();
+                if (up < us) {
+                    const int v = up;
+                    const int sb = v & 1;
+                    if (ready(&bars->p_ready[sb], static_cast<uint32_t>(v >> 1) & 1) &&
+                        ready(&bars->o_free[sb], (static_cast<uint32_t>(v >> 1) & 1) ^ 1)) {
+                        // ---- O(v) = P V
+                        const int it = v / p.nH, h = v - it * p.nH;
+                        const int g = it * groups_per_tile + h / p.hpl;
+                        const int buf = g % p.nbuf;
+                        tc_fence_after_sync();
+                        const uint32_t va = smem_u32(bufs + buf * buf_bytes) + 2u * static_cast<uint32_t>(op_bytes);
+                        if (elect_one_sync()) {
+    #pragma unroll
+                            for (int k = 0; k < 8; ++k)                     // 16 keys per step: 16 rows x 128 B further down the panel
+                                umma_bf16_ts(tmem + 256u + static_cast<uint32_t>(sb * 128), tmem + static_cast<uint32_t>(sb * 128 + 8 * k),
+                                             umma_desc_mn_sw128(va + static_cast<uint32_t>(k * 2048), kPanelBytes), idesc_pv, k == 0 ? 0u : 1u);
+                            umma_commit(&bars->o_full[sb]);
+                            umma_commit(&bars->empty[buf]);
+                        }
+                        __syncwarp();
+                        ++up;
+                    }
+                }
             }
         }
     } else if (warp < kSoftmaxWarps) {
