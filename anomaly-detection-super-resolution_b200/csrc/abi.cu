@@ -152,3 +152,41 @@ extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, cons
     p.trace = g_mlp_trace;
     return launch_swin_mlp(p, y, ldy, z, ldz, num_sms, static_cast<cudaStream_t>(stream));
 }
+
+static long long* g_attn_trace = nullptr;
+extern "C" void adsr_debug_set_attn_trace(void* device_buffer) { g_attn_trace = static_cast<long long*>(device_buffer); }
+
+extern "C" int adsr_swin_attn_mode(int C, int heads, int head_dim_padded, int allow_proj) {
+    SwinAttnParams p{};
+    return swin_attn_plan(p, C, heads, head_dim_padded, allow_proj);
+}
+
+extern "C" int adsr_swin_attn_bf16(const void* x, int64_t ldx, int B, int H, int W, int C, int shift, int heads, int head_dim,
+                                   int head_dim_padded, const void* w1_packed, const void* w2_packed, const float* bias_qkv,
+                                   const float* colsum_qkv, const float* bias_proj, const float* bias_table, float ln_eps,
+                                   const float* ln_stats_in, int stats_in_slots, int stats_in_stride, int fuse_proj, void* out,
+                                   int64_t ldo, float* stats_out, int stats_out_slot0, int stats_out_stride, int num_sms,
+                                   void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (head_dim <= 0 || head_dim > head_dim_padded || ln_stats_in == nullptr || stats_in_slots <= 0 || x == nullptr || out == nullptr ||
+        w1_packed == nullptr || bias_qkv == nullptr || colsum_qkv == nullptr || bias_table == nullptr)
+        return ADSR_ERR_BAD_SHAPE;
+    SwinAttnParams p{};
+    const int mode = swin_attn_plan(p, C, heads, head_dim_padded, fuse_proj);
+    if (mode == 0 || (fuse_proj != 0) != (mode == 2)) return ADSR_ERR_BAD_SHAPE;
+    if (mode == 2 && (w2_packed == nullptr || bias_proj == nullptr)) return ADSR_ERR_BAD_SHAPE;
+    if (stats_out != nullptr && (mode != 2 || stats_out_slot0 >= stats_out_stride)) return ADSR_ERR_BAD_SHAPE;
+    p.x = static_cast<const __nv_bfloat16*>(x); p.ldx = ldx;
+    p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo;
+    p.w1p = static_cast<const uint8_t*>(w1_packed); p.w2p = static_cast<const uint8_t*>(w2_packed);
+    p.bias_qkv = bias_qkv; p.colsum_qkv = colsum_qkv; p.bias_p = bias_proj; p.table = bias_table;
+    p.stats_in = reinterpret_cast<const float2*>(ln_stats_in);
+    p.stats_in_slots = stats_in_slots; p.stats_in_stride = stats_in_stride;
+    p.stats_out = reinterpret_cast<float2*>(stats_out);
+    p.stats_out_slot0 = stats_out_slot0; p.stats_out_stride = stats_out_stride;
+    p.ln_eps = ln_eps;
+    p.scale_log2e = (1.0f / sqrtf(static_cast<float>(head_dim))) * 1.4426950408889634f;
+    p.B = B; p.H = H; p.W = W; p.shift = shift;
+    p.trace = g_attn_trace;
+    return launch_swin_attn(p, num_sms, static_cast<cudaStream_t>(stream));
+}

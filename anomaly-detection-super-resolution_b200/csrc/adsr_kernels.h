@@ -89,4 +89,36 @@ struct SwinMlpParams {
 int swin_mlp_fixed_smem_bytes();
 int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, long long ldz, int num_sms, cudaStream_t stream);
 
+// ---- fused attention half of a Swin block (swin_attn.cu)
+struct SwinAttnParams {
+    const __nv_bfloat16* x;   // [M, >= C] raw token rows: A operand of the (norm1-folded) qkv Linear and the shortcut
+    long long ldx;
+    __nv_bfloat16* out;       // fuse_proj: y [M, >= C] = x + proj(attention);  else attention rows [M, nH * hdp]
+    long long ldo;
+    const uint8_t* w1p;       // qkv slabs [3 hdp rows (q_h | k_h | v_h) x 64 bf16] in (head, K slab) order, gamma folded
+    const uint8_t* w2p;       // proj slabs [cp rows x 64 bf16] (K = the head's hdp channels), one per head
+    const float* bias_qkv;    // [nH * 3 * hdp]  W beta + b in the slab row order
+    const float* colsum_qkv;  // [nH * 3 * hdp]  sum_k gamma_k W_nk of the bf16-rounded packed weights
+    const float* bias_p;      // [cp]
+    const float* table;       // [225, nH] relative position bias table
+    const float2* stats_in;   // per-row (sum, sumsq) partials of x
+    int stats_in_slots, stats_in_stride;
+    float2* stats_out;        // per-row (sum, sumsq) of y -> stats_out[row * stride + slot0]   (fuse_proj only; may be null)
+    int stats_out_slot0, stats_out_stride;
+    float ln_eps, scale_log2e;
+    int B, H, W, C, shift, nH, hdp;
+    int n_tiles;              // window pairs
+    int ks, k16;              // 64-wide panels / K=16 steps of the x tile
+    int pan;                  // 64-column panels per k / v operand
+    int fuse_proj;
+    int cp;                   // proj accumulator columns (C rounded up to 16)
+    int n_pp, pp_rows[2];     // proj N issued in 1 or 2 pieces
+    int qkv_pieces, qp_rows[2];
+    int col_proj, col_r, col_s, col_o;   // TMEM columns: proj accumulator, q|k|v region, S / P, O
+    int w1_slots, w1_slot_bytes, w2_slots, w2_slot_bytes;
+    long long* trace;         // optional clock64 timeline of CTA 0 (tools/attn_trace.py), else nullptr
+};
+int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj);   // 0 = not covered, 1 = qkv + attention, 2 = + proj
+int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream);
+
 }  // namespace adsr

@@ -18,6 +18,7 @@ Evaluation semantics only (DropPath = identity, as `model.eval()`); see DESIGN.m
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -27,6 +28,7 @@ from . import ops, pack
 from .pack import PackedWeight, round_up
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # src/drct.py:774
+_FUSED_ATTN = os.environ.get("ADSR_FUSED_ATTN", "1") != "0"    # A/B switch for profiling: 0 = separate qkv / attention / proj kernels
 
 
 def _heads_for(dim: int, k: int, nh: int) -> int:
@@ -104,7 +106,7 @@ class _PatchNorm(nn.Module):
 class _Block:
     """Packed weights + geometry of one Swin block and its adjust conv."""
     __slots__ = ("dim", "heads", "hd", "hdp", "shift", "ws", "hidden", "adjust_out", "n1w", "n1b", "n2w", "n2b", "table",
-                 "qkv", "proj", "mlp", "adjust", "last")
+                 "qkv", "proj", "mlp", "adjust", "last", "attn", "attn_mode")
 
 
 class DRCT(nn.Module):
@@ -189,6 +191,11 @@ class DRCT(nn.Module):
                 b.qkv = pack.pack_qkv_weight(sw.attn.qkv.weight, sw.attn.qkv.bias, b.heads, sw.norm1.weight, sw.norm1.bias,
                                              sw.norm1.eps)
                 b.proj = pack.pack_proj_weight(sw.attn.proj.weight, sw.attn.proj.bias, b.heads)
+                # fused attention half (csrc/swin_attn.cu): 2 = qkv + attention + proj + residual in one kernel,
+                # 1 = qkv + attention (proj stays a row-tile GEMM), 0 = shape not covered (separate kernels)
+                b.attn_mode = ops.swin_attn_mode(b.dim, b.heads, b.hdp) if (b.ws == 8 and _FUSED_ATTN) else 0
+                b.attn = pack.pack_swin_attn(sw.attn.qkv.weight, sw.attn.qkv.bias, sw.norm1.weight, sw.norm1.bias, sw.norm1.eps,
+                                             sw.attn.proj.weight, sw.attn.proj.bias, b.heads) if b.attn_mode else None
                 b.mlp = pack.pack_swin_mlp(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias, sw.norm2.eps,
                                            sw.mlp.fc2.weight, sw.mlp.fc2.bias)
                 b.adjust = pack.pack_gemm_weight(adj.weight, adj.bias, rows_kernel=(k == 4))
@@ -282,12 +289,21 @@ class DRCT(nn.Module):
                 C = b.dim
                 # ---- W-MSA / SW-MSA half (src/drct.py:478-509); norm1 is folded into the qkv GEMM, its row statistics
                 #      are the partial sums the producing epilogues left in st_slab
-                ops.tc_gemm(slab, C, b.qkv, qkv, stats_in=(st_slab, xs + 2 * k))
-                ops.window_attention(qkv, att, b.table, B, H, W, b.ws, b.shift, b.heads, b.hd, b.hdp)
-                ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0))
+                fused = b.attn_mode if (H % 8 == 0 and W % 8 == 0 and (B * (H // 8) * (W // 8)) % 2 == 0) else 0
+                y_slots = 2 * b.proj.n_tiles
+                if fused == 2:
+                    ops.swin_attn(slab, b.attn, b.table, y, B, H, W, b.shift, (st_slab, xs + 2 * k), True, stats_out=(st_y, 0))
+                    y_slots = 1
+                elif fused == 1:
+                    ops.swin_attn(slab, b.attn, b.table, att, B, H, W, b.shift, (st_slab, xs + 2 * k), False)
+                    ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0))
+                else:
+                    ops.tc_gemm(slab, C, b.qkv, qkv, stats_in=(st_slab, xs + 2 * k))
+                    ops.window_attention(qkv, att, b.table, B, H, W, b.ws, b.shift, b.heads, b.hd, b.hdp)
+                    ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0))
                 # ---- MLP half (src/drct.py:510, 185-189): norm2 + fc1 + GELU + fc2 + residual in ONE kernel, the hidden
                 #      activations never leave the SM
-                ops.swin_mlp(y, C, b.mlp, z, stats_in=(st_y, 2 * b.proj.n_tiles))
+                ops.swin_mlp(y, C, b.mlp, z, stats_in=(st_y, y_slots))
                 # ---- adjust 1x1 conv (+LeakyReLU 0.2) into the slab slice / 0.2*x5 + x  (src/drct.py:389-396)
                 if not b.last:
                     ops.tc_gemm(z, C, b.adjust, slab, act=ops.ACT_LRELU, slope=0.2, ocol0=C, n_store=b.adjust_out,

@@ -82,6 +82,31 @@ def swin_mlp(y: torch.Tensor, c: int, pm, z: torch.Tensor, stats_in: tuple, m: O
     _count("swin_mlp", 4.0 * m * pm.C * pm.H, _t)
 
 
+def swin_attn_mode(c: int, heads: int, hdp: int, allow_proj: bool = True) -> int:
+    """What adsr_swin_attn_bf16 covers for this block shape: 2 = whole attention half, 1 = qkv + attention, 0 = nothing."""
+    return int(lib().adsr_swin_attn_mode(c, heads, hdp, int(allow_proj)))
+
+
+def swin_attn(x: torch.Tensor, pa, table: torch.Tensor, out: torch.Tensor, b: int, h: int, w: int, shift: int, stats_in: tuple,
+              fuse_proj: bool, stats_out: Optional[tuple] = None) -> None:
+    """fuse_proj: out[:, :C] = x + proj(W-MSA(LayerNorm(x[:, :C])))  else  out = attention rows [M, heads*hdp]
+    -- one fused kernel (csrc/swin_attn.cu); `pa` from pack.pack_swin_attn, stats as in tc_gemm (stats_out: ONE slot)."""
+    _cuda(x, "x")
+    _cuda(out, "out")
+    if x.data_ptr() == out.data_ptr():
+        raise ValueError("swin_attn: x and out must not alias")
+    si_t, si_n = stats_in
+    so_t, so_0 = stats_out if stats_out is not None else (None, 0)
+    m = b * h * w
+    _t = _begin()
+    check(lib().adsr_swin_attn_bf16(ptr(x), x.stride(0), b, h, w, pa.C, shift, pa.heads, pa.hd, pa.hdp, ptr(pa.w1), ptr(pa.w2),
+                                    ptr(pa.bias_qkv), ptr(pa.colsum_qkv), ptr(pa.bias_p), ptr(table), pa.ln_eps, ptr(si_t), si_n,
+                                    si_t.shape[1], int(fuse_proj), ptr(out), out.stride(0), ptr(so_t), so_0,
+                                    so_t.shape[1] if so_t is not None else 0, _abi.num_sms(), stream_ptr()), "adsr_swin_attn_bf16")
+    flops = 2.0 * m * pa.C * 3 * pa.C + 4.0 * m * 64 * pa.C + (2.0 * m * pa.C * pa.C if fuse_proj else 0.0)
+    _count("swin_attn", flops, _t)
+
+
 def conv3x3(x: torch.Tensor, b: int, h: int, wd: int, cin: int, w: PackedWeight, out: torch.Tensor, *, stride: int = 1,
             act: int = ACT_NONE, slope: float = 0.0, alpha: float = 1.0, res: Optional[torch.Tensor] = None,
             out_mode: int = OUT_ROWS, n_store: Optional[int] = None, ocol0: int = 0) -> None:

@@ -253,3 +253,56 @@ def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b) -> PackedMlp:
             pl["w1_slots"], pl["w1_slot_bytes"], pl["w2_slots"], pl["w2_slot_bytes"]] + pl["widths"] + [0] * (8 - nc)
     return PackedMlp(torch.cat(slabs1).contiguous(), torch.cat(slabs2).contiguous(), bias1, colsum1, bias2,
                      torch.tensor(plan, dtype=torch.int32), float(eps), c, h)
+
+
+# ------------------------------------------------------------------------------------------------ fused attention half
+@dataclass
+class PackedAttn:
+    w1: torch.Tensor          # uint8: qkv slabs [3*hdp rows (q_h | k_h | v_h) x 64 bf16], (head, K slab) order, gamma folded
+    w2: torch.Tensor          # uint8: proj slabs [cp rows x 64 bf16] (K = the head's channels), one per head
+    bias_qkv: torch.Tensor    # fp32 [heads * 3 * hdp]
+    colsum_qkv: torch.Tensor  # fp32 [heads * 3 * hdp]
+    bias_p: torch.Tensor      # fp32 [cp]
+    ln_eps: float
+    C: int
+    heads: int
+    hd: int
+    hdp: int
+
+
+def pack_swin_attn(qkv_w, qkv_b, gamma, beta, eps, proj_w, proj_b, heads: int) -> PackedAttn:
+    """norm1 + qkv Linear + proj Linear of one Swin block (src/drct.py:432, 245-249, 278, 300) for adsr_swin_attn_bf16:
+    qkv rows regrouped per head as q_h | k_h | v_h (each padded to head_pad(hd) zero rows), gamma folded in
+    (pack_ln_gemm_weight's algebra); proj columns split per head into [cp x 64] slabs."""
+    w = qkv_w.detach().float()
+    c = w.shape[1]
+    dev = w.device
+    hd = c // heads
+    hdp = head_pad(hd)
+    ks = (c + 63) // 64
+    cp = round_up(c, 16)
+    g, bt = gamma.detach().float(), beta.detach().float()
+    wg = torch.zeros(heads, 3, hdp, ks * 64, device=dev)
+    wg[:, :, :hd, :c] = (w * g[None, :]).view(3, heads, hd, c).permute(1, 0, 2, 3)
+    t = w @ bt + (qkv_b.detach().float() if qkv_b is not None else 0.0)
+    bias = torch.zeros(heads, 3, hdp, device=dev)
+    bias[:, :, :hd] = t.view(3, heads, hd).permute(1, 0, 2)
+    colsum = wg.to(torch.bfloat16).float().sum(dim=-1)
+    slabs1 = []
+    for h in range(heads):
+        wh = wg[h].reshape(3 * hdp, ks * 64)
+        for s in range(ks):
+            slabs1.append(_swizzle_slab(wh[:, 64 * s:64 * s + 64].contiguous()))
+    pw = proj_w.detach().float()
+    slabs2 = []
+    if hdp <= 64:
+        for h in range(heads):
+            blk = torch.zeros(cp, 64, device=dev)
+            blk[:c, :hd] = pw[:, h * hd:(h + 1) * hd]
+            slabs2.append(_swizzle_slab(blk))
+    bias_p = torch.zeros(cp, device=dev)
+    if proj_b is not None:
+        bias_p[:c] = proj_b.detach().float()
+    w2 = torch.cat(slabs2).contiguous() if slabs2 else torch.zeros(16, dtype=torch.uint8, device=dev)
+    return PackedAttn(torch.cat(slabs1).contiguous(), w2, bias.reshape(-1).contiguous(), colsum.reshape(-1).contiguous(),
+                      bias_p, float(eps), c, heads, hd, hdp)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 5
+#define ADSR_ABI_VERSION 6
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -77,6 +77,29 @@ int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C,
                        const int32_t* plan, int plan_len, float ln_eps,
                        const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
                        void* z, int64_t ldz, int num_sms, void* stream);
+
+/* ---- fused attention half of a Swin block for 8 x 8 windows ------------------------------------------------------
+ *   y = x + proj( WindowAttention( LayerNorm(x) ) )
+ * replaces norm1 + torch.roll + window_partition + WindowAttention.forward (qkv Linear, q k^T * scale + relative position
+ * bias + shift mask, softmax, P v, proj Linear) + window_reverse + torch.roll + the first residual of
+ * SwinTransformerBlock.forward (src/drct.py:478-509, 271-302, 193-220, 449-470) in ONE kernel: q | k | v and the
+ * attention output stay in tensor memory / shared memory.
+ * x: [B*H*W, >= C] bf16 raw token rows (row pitch ldx >= C rounded up to 16), row statistics from ln_stats_in exactly as
+ * in adsr_tc_gemm_bf16.  w1_packed / w2_packed / bias_qkv / colsum_qkv / bias_proj come from pack.pack_swin_attn().
+ * adsr_swin_attn_mode(C, heads, head_dim_padded, allow_proj) tells what the kernel covers for a block shape:
+ *   2 = the whole half (fuse_proj = 1: out = y [M, >= C], stats_out receives the per-row (sum, sumsq) of y for the norm2
+ *       fold of adsr_swin_mlp_bf16),
+ *   1 = qkv + attention only (fuse_proj = 0: out = attention rows [M, heads * head_dim_padded]; the proj Linear and the
+ *       residual are then one adsr_tc_gemm_bf16 call),
+ *   0 = shape not covered (use adsr_tc_gemm_bf16 + adsr_window_attention).
+ * Requires H % 8 == W % 8 == 0 and an even number of windows; x and out must not alias. */
+int adsr_swin_attn_mode(int C, int heads, int head_dim_padded, int allow_proj);
+int adsr_swin_attn_bf16(const void* x, int64_t ldx, int B, int H, int W, int C, int shift, int heads, int head_dim,
+                        int head_dim_padded, const void* w1_packed, const void* w2_packed,
+                        const float* bias_qkv, const float* colsum_qkv, const float* bias_proj, const float* bias_table,
+                        float ln_eps, const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
+                        int fuse_proj, void* out, int64_t ldo,
+                        float* stats_out, int stats_out_slot0, int stats_out_stride, int num_sms, void* stream);
 
 /* ---- tcgen05 implicit-GEMM 3x3 convolution (pad 1, stride 1|2) on NHWC bf16 -------------------------
  * replaces conv_after_body / conv_before_upsample(+LeakyReLU) / Upsample convs + nn.PixelShuffle(2)
