@@ -91,6 +91,7 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
 
 // ---- fused attention half of a Swin block (swin_attn.cu)
 struct SwinAttnParams {
+    CUtensorMap tmap_x;       // x as [B, H, W, C] bf16, box 64 channels x R x R tokens, 128-byte swizzle (x-tile loads)
     const __nv_bfloat16* x;   // [M, >= C] raw token rows: A operand of the (norm1-folded) qkv Linear and the shortcut
     long long ldx;
     __nv_bfloat16* out;       // fuse_proj: y [M, >= C] = x + proj(attention);  else attention rows [M, nH * hdp]
@@ -108,16 +109,20 @@ struct SwinAttnParams {
     float ln_eps, scale_log2e;
     int B, H, W, C, shift, nH, hdp;
     int n_tiles;              // window pairs
+    int box_r;                // side of the square token boxes a window is fetched in: 8 (no shift) or 4 (shift 4, wrapped windows)
     int ks, k16;              // 64-wide panels / K=16 steps of the x tile
     int pan;                  // 64-column panels per k / v operand
     int fuse_proj;
     int cp;                   // proj accumulator columns (C rounded up to 16)
-    int n_pp, pp_rows[2];     // proj N issued in 1 or 2 pieces
-    int qkv_pieces, qp_rows[2];
-    int col_proj, col_r, col_s, col_o;   // TMEM columns: proj accumulator, q|k|v region, S / P, O
-    int w1_slots, w1_slot_bytes, w2_slots, w2_slot_bytes;
+    int n_pp, pp_rows[4];     // a head's proj slab is issued in n_pp N pieces (each fits a ring slot)
+    int qkv_pieces, qp_rows[4];  // a qkv slab is issued in N pieces of <= 128 rows (one ring slot each)
+    int rsz, nreg;            // TMEM: columns per head region, number of regions (2 = next head's q|k|v runs one head ahead)
+    int col_o;                // TMEM column of O (fuse_proj: behind the region; else O overlays the region's q columns)
+    int w_slots, w_slot_bytes;   // qkv weight ring
+    int p_slots, p_slot_bytes;   // proj weight ring (fuse_proj)
     long long* trace;         // optional clock64 timeline of CTA 0 (tools/attn_trace.py), else nullptr
 };
+int encode_tmap_nhwc_box_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int R);
 int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj);   // 0 = not covered, 1 = qkv + attention, 2 = + proj
 int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream);
 

@@ -5,21 +5,24 @@
 // q|k|v rows (1.1 - 1.9 KB per token) nor the attention output ever touch HBM.
 //
 // A CTA owns one TILE = two consecutive windows = 128 token rows and walks over the heads:
-//   * 4 producer warps gather the raw x rows of the tile through the closed-form shifted-window index map
-//     (src/drct.py:483, 193-204) with zero-filling 16-byte cp.async into K-major 128-byte-swizzled panels (A operand);
-//   * per head h the MMA warp computes  [q_h | k_h | v_h] = x W_h^T  (tcgen05.mma SS, N = 3 hdp, weights streamed from
-//     L2 through a ring of [3 hdp x 64] slabs); 16 epilogue warps apply the folded LayerNorm + bias and write q back
-//     IN PLACE into TMEM as bf16 (A operand of S), k and v as bf16 into shared-memory operand panels;
+//   * the loader warp fetches the raw x rows of the tile with 4-D TMA boxes of [R x R tokens x 64 channels] (R = 8: a whole
+//     window; R = 4 when the cyclic shift makes windows wrap; closed-form index map of src/drct.py:483, 193-204) into
+//     K-major 128-byte-swizzled panels (A operand of qkv); channels >= C are zero-filled by the tensor map;
+//   * per head h the MMA warp computes  [q_h | k_h | v_h] = x W_h^T  (tcgen05.mma SS, N = 3 hdp) into a TMEM region (two
+//     alternating regions when proj is not fused: the next head's q|k|v then runs one head ahead); the weights of the whole
+//     half (qkv and proj slabs) stream from L2 through ONE ring in the fixed order of use;
+//   * 16 epilogue warps apply the folded LayerNorm + bias and write q back IN PLACE into TMEM as bf16 (A operand of S), k and
+//     v as bf16 into shared-memory operand panels;
 //   * S = q k^T (tcgen05.mma TS, M = N = 128; the off-diagonal 64 x 64 blocks belong to the other window and are never
-//     used) lands on the dead k|v accumulator columns; softmax: four threads per query row, relative-position bias from a
-//     shared-memory table, -100 mask from per-row 64-bit same-region words (src/drct.py:449-470); unnormalised bf16
-//     probabilities go back in place into TMEM;  O = P v  (TS, v as MN-major B operand);
-//   * fuse_proj: O is normalised and written back in place as bf16 and  Y += O_h Wp_h^T  (TS) accumulates the proj
-//     Linear over the heads in a persistent TMEM accumulator; the last epilogue adds bias and the shortcut (re-read from
-//     L2), stores y at the ORIGINAL token rows (window_reverse + un-shift are the inverse permutation) and leaves the
-//     per-row (sum, sumsq) for the norm2 fold of the MLP kernel.
-//     Otherwise (heads of 80 / 128 padded channels: TMEM cannot hold the proj accumulator next to q|k|v) the normalised
-//     O rows are stored to `out` [M, nH * hdp] and the row-tile GEMM applies proj.
+//     used) lands on the dead k|v accumulator columns of the region; softmax: four threads per query row, relative-position
+//     bias from a shared-memory table, -100 mask from closed-form region ids (src/drct.py:449-470); unnormalised bf16
+//     probabilities go back in place into TMEM;  O = P v  (TS, v as MN-major B operand) lands on the dead q columns;
+//   * fuse_proj: the normalised O_h is written back in place as bf16 and  Y += O_h Wp_h^T  (TS) accumulates the proj Linear
+//     over the heads in a persistent TMEM accumulator; the last epilogue adds bias and the shortcut
+//     (fetched as coalesced 128-byte row pieces into the idle k / v panels), stores y at the ORIGINAL token rows
+//     (window_reverse + un-shift are the inverse permutation) and leaves the per-row (sum, sumsq) for the norm2 fold of
+//     the MLP kernel.  Otherwise (heads of 80 / 128 padded channels: TMEM cannot hold everything) the normalised O rows are
+//     stored to `out` [M, nH * hdp] and the row-tile GEMM applies proj.
 #include "adsr_kernels.h"
 #include "ptx.cuh"
 
@@ -28,21 +31,21 @@ namespace adsr {
 namespace {
 
 constexpr int kEpiWarps = 16;                 // warps 0..15: quadrant (TMEM lanes) = warp & 3, column group = warp >> 2
-constexpr int kProducerWarp0 = 16;            // warps 16..19: x-tile gather
-constexpr int kMmaWarp = 20;
-constexpr int kW1LoaderWarp = 21;             // qkv weight slabs, TMEM alloc
-constexpr int kW2LoaderWarp = 22;             // proj weight slabs
-constexpr int kThreads = 23 * 32;
+constexpr int kXLoaderWarp = 16;              // x-tile TMA loads
+constexpr int kMmaWarp = 17;
+constexpr int kWLoaderWarp = 18;              // qkv weight slabs, TMEM alloc
+constexpr int kPLoaderWarp = 19;              // proj weight slabs
+constexpr int kThreads = 20 * 32;
 constexpr int kPanelBytes = 128 * 128;
-constexpr int kMaxSlots = 8;
+constexpr int kMaxSlots = 10;
 constexpr int kSmemLimit = 232448;
 
 struct __align__(8) AttnBlockBarriers {
-    uint64_t w1_full[kMaxSlots], w1_empty[kMaxSlots];
-    uint64_t w2_full[2], w2_empty[2];
+    uint64_t w_full[kMaxSlots], w_empty[kMaxSlots];
+    uint64_t p_full[4], p_empty[4];
     uint64_t x_full, x_empty;
-    uint64_t meta_free[2];
-    uint64_t qkv_full, qkv_ready, s_full, p_ready, o_full, o_ready;
+    uint64_t qkv_full[2];                     // per TMEM region
+    uint64_t qkv_ready, s_full, p_ready, o_full, o_ready;
     uint64_t proj_full, proj_free;
     uint32_t tmem_base;
 };
@@ -63,7 +66,6 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit_() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st8_(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -80,7 +82,7 @@ __device__ __forceinline__ int region_1d_(int t, int L, int shift) { return (t >
 __device__ __forceinline__ float2 f2_(float a, float b) { return make_float2(a, b); }
 
 // optional timeline of CTA 0 (tools/attn_trace.py): trace[(((role * 4 + tile) * 9 + head) * 8 + k)] = clock64()
-// roles: 0 = MMA warp, 1 = epilogue warp 0, 2 = producer warp 0; head slot 8 = per-tile events
+// roles: 0 = MMA warp, 1 = epilogue warp 0, 2 = x loader warp; head slot 8 = per-tile events
 template <bool TRACE>
 __device__ __forceinline__ void tr_ev(long long* trace, int role, int it, int h, int k) {
     if constexpr (TRACE) {
@@ -97,15 +99,14 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
     uint8_t* x_buf = smem;                                             // [ks panels] raw x rows of the tile (A operand of qkv)
     uint8_t* k_buf = x_buf + x_bytes;                                  // [pan panels] k of the current head (K-major B operand of S)
     uint8_t* v_buf = k_buf + op_bytes;                                 // [pan panels] v of the current head (MN-major B operand of P V)
-    uint8_t* ring1 = v_buf + op_bytes;                                 // w1_slots x w1_slot_bytes
-    uint8_t* ring2 = ring1 + p.w1_slots * p.w1_slot_bytes;             // w2_slots x w2_slot_bytes
-    float* s_bq = reinterpret_cast<float*>(ring2 + p.w2_slots * p.w2_slot_bytes);   // [nqkv] folded qkv bias, per-head q|k|v order
+    uint8_t* ring = v_buf + op_bytes;                                  // qkv slabs: w_slots x w_slot_bytes
+    uint8_t* pring = ring + p.w_slots * p.w_slot_bytes;                // proj slabs: p_slots x p_slot_bytes
+    float* s_bq = reinterpret_cast<float*>(pring + p.p_slots * p.p_slot_bytes);     // [nqkv] folded qkv bias, per-head q|k|v order
     float* s_cq = s_bq + nqkv;                                         // [nqkv] column sums of the gamma-folded weights
     float* s_bp = s_cq + nqkv;                                         // [cp] proj bias
     float* s_bias = s_bp + p.cp;                                       // [nH][232] rel-pos table * log2(e)
     int* s_tok = reinterpret_cast<int*>(s_bias + p.nH * 232);          // [2][128] token row of each tile row
-    uint32_t* s_msk = reinterpret_cast<uint32_t*>(s_tok + 256);        // [2][128][2] "same mask region" bits of the row's 64 keys
-    float* s_max = reinterpret_cast<float*>(s_msk + 512);              // [4][128] partial row maxima
+    float* s_max = reinterpret_cast<float*>(s_tok + 256);              // [4][128] partial row maxima
     float* s_sum = s_max + 512;                                        // [4][128] partial row sums
     float2* s_stat = reinterpret_cast<float2*>(s_max);                 // [4][128] (sum, sumsq) partials of y -- aliases s_max | s_sum
     AttnBlockBarriers* bars = reinterpret_cast<AttnBlockBarriers*>(s_sum + 512);
@@ -127,17 +128,17 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
     }
     if (warp == kMmaWarp && lane == 0) {
         for (int s = 0; s < kMaxSlots; ++s) {
-            mbar_init(&bars->w1_full[s], 1);
-            mbar_init(&bars->w1_empty[s], 1);
+            mbar_init(&bars->w_full[s], 1);
+            mbar_init(&bars->w_empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->w2_full[s], 1);
-            mbar_init(&bars->w2_empty[s], 1);
-            mbar_init(&bars->meta_free[s], kEpiWarps);
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(&bars->p_full[s], 1);
+            mbar_init(&bars->p_empty[s], 1);
         }
-        mbar_init(&bars->x_full, 128);
+        mbar_init(&bars->x_full, 1);
         mbar_init(&bars->x_empty, 1);
-        mbar_init(&bars->qkv_full, 1);
+        mbar_init(&bars->qkv_full[0], 1);
+        mbar_init(&bars->qkv_full[1], 1);
         mbar_init(&bars->qkv_ready, kEpiWarps);
         mbar_init(&bars->s_full, 1);
         mbar_init(&bars->p_ready, kEpiWarps);
@@ -147,216 +148,290 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         mbar_init(&bars->proj_free, kEpiWarps);
         fence_barrier_init();
     }
-    if (warp == kW1LoaderWarp) tmem_alloc<512>(&bars->tmem_base);
+    if (warp == kWLoaderWarp) tmem_alloc<512>(&bars->tmem_base);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = bars->tmem_base;
     const int uq = p.hdp >> 4;                                         // 16-column units (= K16 steps) per head operand
+    const int nwx = p.W >> 3, nW = (p.H >> 3) * nwx;
 
-    if (warp >= kProducerWarp0 && warp < kProducerWarp0 + 4) {
-        // ============================================================ producers: thread = tile row for the index math,
-        // a warp walks along one row's 16-byte chunks for the copies
-        const int pw = warp - kProducerWarp0;
-        const int r = pw * 32 + lane;
-        const int chunks = p.k16 * 2;                                  // 16-byte chunks per row up to the K16 boundary
-        const int nwx = p.W >> 3, nW = (p.H >> 3) * nwx;
-        const uint32_t x_base = smem_u32(x_buf);
+    if (warp == kXLoaderWarp) {
+        // ============================================================ x tile: one TMA box per (window, R x R token block, panel).
+        // Tile row of a token = window * 64 + block * R*R + y' * R + x'  (block-major slot order; R = 8: the usual y * 8 + x).
+        // Attention is invariant under a permutation of a window's tokens as long as the bias / mask / output row use the
+        // same slot -> (y, x) map, which the epilogue warps do.
+        if (lane == 0) tma_prefetch_desc(&p.tmap_x);
+        const int R = p.box_r, nb = 8 / R;
+        const int combos = 2 * nb * nb;
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
-            const int mb = it & 1;
-            const int win = tile * 2 + (r >> 6);
-            const int b = win / nW, w = win - b * nW;
-            const int n = r & 63;
-            const int ys = (w / nwx) * 8 + (n >> 3), xs = (w % nwx) * 8 + (n & 7);
-            int y = ys + p.shift; if (y >= p.H) y -= p.H;
-            int x = xs + p.shift; if (x >= p.W) x -= p.W;
-            const int tok = (b * p.H + y) * p.W + x;
-            uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
-            if (p.shift > 0) {
-                const int wy = (w / nwx) * 8, wx = (w % nwx) * 8;
-                const int my = 3 * region_1d_(ys, p.H, p.shift) + region_1d_(xs, p.W, p.shift);
-                m0 = m1 = 0u;
-                for (int k = 0; k < 64; ++k) {
-                    const int rk = 3 * region_1d_(wy + (k >> 3), p.H, p.shift) + region_1d_(wx + (k & 7), p.W, p.shift);
-                    if (rk == my) { if (k < 32) m0 |= 1u << k; else m1 |= 1u << (k - 32); }
-                }
-            }
-            mbar_wait(&bars->meta_free[mb], (static_cast<uint32_t>(it >> 1) & 1) ^ 1);
-            s_tok[mb * 128 + r] = tok;
-            s_msk[(mb * 128 + r) * 2] = m0;
-            s_msk[(mb * 128 + r) * 2 + 1] = m1;
-            __syncwarp();
-            if (pw == 0) tr_ev<TRACE>(p.trace, 2, it, 8, 0);
+            tr_ev<TRACE>(p.trace, 2, it, 8, 0);
             mbar_wait(&bars->x_empty, (static_cast<uint32_t>(it) & 1) ^ 1);
-            if (pw == 0) tr_ev<TRACE>(p.trace, 2, it, 8, 1);
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-                const int row = pw * 32 + i;
-                const __nv_bfloat16* src = p.x + static_cast<long long>(s_tok[mb * 128 + row]) * p.ldx;
-                for (int c = lane; c < chunks; c += 32) {
-                    int valid = p.C * 2 - c * 16;
-                    valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
-                    const uint32_t d = x_base + static_cast<uint32_t>((c >> 3) * kPanelBytes) + static_cast<uint32_t>(row * 128) +
-                                       static_cast<uint32_t>((((c & 7) ^ (row & 7)) << 4));
-                    cp_async16_zfill(d, src + c * 8, valid);
-                }
+            tr_ev<TRACE>(p.trace, 2, it, 8, 1);
+            if (lane == 0) mbar_arrive_expect_tx(&bars->x_full, static_cast<uint32_t>(x_bytes));
+            __syncwarp();
+            for (int cb = lane; cb < combos; cb += 32) {
+                const int w2 = cb / (nb * nb), blk = cb - w2 * nb * nb;
+                const int by = blk / nb, bx = blk - by * nb;
+                const int win = tile * 2 + w2;
+                const int b = win / nW, w = win - b * nW;
+                int y = (w / nwx) * 8 + by * R + p.shift; if (y >= p.H) y -= p.H;
+                int x = (w % nwx) * 8 + bx * R + p.shift; if (x >= p.W) x -= p.W;
+                uint8_t* dst = x_buf + (w2 * 64 + blk * R * R) * 128;
+                for (int pn = 0; pn < p.ks; ++pn) tma_load_4d(dst + pn * kPanelBytes, &p.tmap_x, pn * 64, x, y, b, &bars->x_full);
             }
-            cp_async_commit_();
-            if (pw == 0) tr_ev<TRACE>(p.trace, 2, it, 8, 2);
-            cp_async_wait_all_();
-            fence_proxy_async_smem();
-            mbar_arrive(&bars->x_full);
-            if (pw == 0) tr_ev<TRACE>(p.trace, 2, it, 8, 3);
+            __syncwarp();
+            tr_ev<TRACE>(p.trace, 2, it, 8, 2);
         }
-    } else if (warp == kW1LoaderWarp) {
+    } else if (warp == kWLoaderWarp) {
         // ============================================================ qkv weight slabs: (head, K slab, N piece) in order, every tile
         int slot = 0;
         uint32_t phase = 0;
         const size_t slab_bytes = static_cast<size_t>(3 * p.hdp) * 128u;
         for (int it = 0; it < my_tiles; ++it) {
             for (int hs = 0; hs < p.nH * p.ks; ++hs) {
+                int row0 = 0;
                 for (int pc = 0; pc < p.qkv_pieces; ++pc) {
                     const uint32_t bytes = static_cast<uint32_t>(p.qp_rows[pc]) * 128u;
-                    const uint8_t* src = p.w1p + static_cast<size_t>(hs) * slab_bytes + (pc ? static_cast<size_t>(p.qp_rows[0]) * 128u : 0u);
-                    mbar_wait(&bars->w1_empty[slot], phase ^ 1);
+                    mbar_wait(&bars->w_empty[slot], phase ^ 1);
                     if (elect_one_sync()) {
-                        mbar_arrive_expect_tx(&bars->w1_full[slot], bytes);
-                        bulk_g2s(ring1 + slot * p.w1_slot_bytes, src, bytes, &bars->w1_full[slot]);
+                        mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
+                        bulk_g2s(ring + slot * p.w_slot_bytes, p.w1p + static_cast<size_t>(hs) * slab_bytes + static_cast<size_t>(row0) * 128u, bytes,
+                                 &bars->w_full[slot]);
                     }
                     __syncwarp();
-                    if (++slot == p.w1_slots) { slot = 0; phase ^= 1; }
+                    row0 += p.qp_rows[pc];
+                    if (++slot == p.w_slots) { slot = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == kW2LoaderWarp) {
-        // ============================================================ proj weight slabs: one [cp x 64] slab per head
+    } else if (warp == kPLoaderWarp) {
+        // ============================================================ proj weight slabs: (head, N piece) in order, every tile
         if (p.fuse_proj) {
             int slot = 0;
             uint32_t phase = 0;
-            const uint32_t bytes = static_cast<uint32_t>(p.cp) * 128u;
+            const size_t pslab_bytes = static_cast<size_t>(p.cp) * 128u;
             for (int it = 0; it < my_tiles; ++it) {
                 for (int h = 0; h < p.nH; ++h) {
-                    mbar_wait(&bars->w2_empty[slot], phase ^ 1);
-                    if (elect_one_sync()) {
-                        mbar_arrive_expect_tx(&bars->w2_full[slot], bytes);
-                        bulk_g2s(ring2 + slot * p.w2_slot_bytes, p.w2p + static_cast<size_t>(h) * bytes, bytes, &bars->w2_full[slot]);
+                    int row0 = 0;
+                    for (int pc = 0; pc < p.n_pp; ++pc) {
+                        const uint32_t bytes = static_cast<uint32_t>(p.pp_rows[pc]) * 128u;
+                        mbar_wait(&bars->p_empty[slot], phase ^ 1);
+                        if (elect_one_sync()) {
+                            mbar_arrive_expect_tx(&bars->p_full[slot], bytes);
+                            bulk_g2s(pring + slot * p.p_slot_bytes, p.w2p + static_cast<size_t>(h) * pslab_bytes + static_cast<size_t>(row0) * 128u, bytes,
+                                     &bars->p_full[slot]);
+                        }
+                        __syncwarp();
+                        row0 += p.pp_rows[pc];
+                        if (++slot == p.p_slots) { slot = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++slot == p.w2_slots) { slot = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == kMmaWarp) {
         // ============================================================ MMA issuer (converged warp, one elected lane issues).
-        // The tensor pipe executes in issue order, which is what lets S overlay the dead k|v accumulator columns and the
-        // next head's q|k|v overwrite the region once P V has been issued.
+        // The tensor pipe executes in issue order, which is what lets S overlay the dead k|v accumulator columns, O the dead
+        // q columns and the proj accumulator the dead regions.
         const uint32_t idesc_s = idesc_m128(128, 0);
         const uint32_t idesc_pv = idesc_m128(static_cast<uint32_t>(p.hdp), 1);
-        const uint32_t idesc_q0 = idesc_m128(static_cast<uint32_t>(p.qp_rows[0]), 0);
-        const uint32_t idesc_q1 = idesc_m128(static_cast<uint32_t>(p.qp_rows[1] > 0 ? p.qp_rows[1] : 16), 0);
-        const uint32_t idesc_p0 = idesc_m128(static_cast<uint32_t>(p.pp_rows[0] > 0 ? p.pp_rows[0] : 16), 0);
-        const uint32_t idesc_p1 = idesc_m128(static_cast<uint32_t>(p.pp_rows[1] > 0 ? p.pp_rows[1] : 16), 0);
         const uint64_t x_desc = umma_desc_k_sw128(smem_u32(x_buf));
         const uint32_t k_addr = smem_u32(k_buf), v_addr = smem_u32(v_buf);
-        const uint64_t ring1_desc = umma_desc_k_sw128(smem_u32(ring1));
-        const uint64_t ring2_desc = umma_desc_k_sw128(smem_u32(ring2));
-        const uint32_t slot1_units = static_cast<uint32_t>(p.w1_slot_bytes >> 4);
-        const uint32_t slot2_units = static_cast<uint32_t>(p.w2_slot_bytes >> 4);
-        const uint32_t t_r = tmem + static_cast<uint32_t>(p.col_r), t_s = tmem + static_cast<uint32_t>(p.col_s);
-        const uint32_t t_o = tmem + static_cast<uint32_t>(p.col_o), t_p = tmem + static_cast<uint32_t>(p.col_proj);
-        int slot1 = 0, slot2 = 0;
-        uint32_t ph1 = 0, ph2 = 0;
-
-        auto issue_qkv = [&](int h) {
-            for (int s = 0; s < p.ks; ++s) {
-                const int ksteps = min(4, p.k16 - 4 * s);
-                for (int pc = 0; pc < p.qkv_pieces; ++pc) {
-                    mbar_wait(&bars->w1_full[slot1], ph1);
-                    tc_fence_after_sync();
-                    if (elect_one_sync()) {
-                        const uint64_t adesc = x_desc + static_cast<uint64_t>(s * (kPanelBytes >> 4));
-                        const uint64_t bdesc = ring1_desc + static_cast<uint64_t>(static_cast<uint32_t>(slot1) * slot1_units);
-                        const uint32_t d = pc ? t_r + static_cast<uint32_t>(p.qp_rows[0]) : t_r;
-                        const uint32_t idesc = pc ? idesc_q1 : idesc_q0;
-                        for (int j = 0; j < ksteps; ++j) umma_bf16(d, adesc + 2 * j, bdesc + 2 * j, idesc, (s > 0 || j > 0) ? 1u : 0u);
-                        umma_commit(&bars->w1_empty[slot1]);
-                        if (s == p.ks - 1 && pc == p.qkv_pieces - 1) {
-                            umma_commit(&bars->qkv_full);
-                            if (h == p.nH - 1) umma_commit(&bars->x_empty);   // the x tile is no longer an operand
-                        }
-                    }
-                    __syncwarp();
-                    if (++slot1 == p.w1_slots) { slot1 = 0; ph1 ^= 1; }
-                }
+        const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring));
+        const uint32_t slot_units = static_cast<uint32_t>(p.w_slot_bytes >> 4);
+        const uint64_t pring_desc = umma_desc_k_sw128(smem_u32(pring));
+        const uint32_t pslot_units = static_cast<uint32_t>(p.p_slot_bytes >> 4);
+        int slot = 0, pslot = 0;
+        uint32_t wph = 0, pph = 0;
+        int o_waited = 0;                                              // o_ready phases consumed so far (they complete in head order)
+        auto ensure_o = [&](int g) {                                   // the epilogue is done with O (and the region) of head counter g
+            while (o_waited <= g) {
+                mbar_wait(&bars->o_ready, static_cast<uint32_t>(o_waited) & 1);
+                ++o_waited;
             }
+            tc_fence_after_sync();
+        };
+        auto region_of = [&](int g) -> uint32_t {                      // fuse_proj: one region behind the proj accumulator
+            return tmem + static_cast<uint32_t>(p.fuse_proj ? p.cp : (p.nreg == 2 ? (g & 1) : 0) * p.rsz);
         };
 
-        for (int it = 0; it < my_tiles; ++it) {
-            tr_ev<TRACE>(p.trace, 0, it, 8, 0);
-            mbar_wait(&bars->x_full, static_cast<uint32_t>(it) & 1);
+        // q|k|v of one head is issued in (K slab, N piece) steps so that the short S / P V MMAs of the current head can cut in
+        // between the steps of the next head's q|k|v (the tensor pipe runs in issue order)
+        int q_g = 0, q_step = 0, q_s = 0, q_pc = 0;
+        const int q_steps = p.ks * p.qkv_pieces;
+        const uint32_t idesc_q0 = idesc_m128(static_cast<uint32_t>(p.qp_rows[0]), 0);
+        const uint32_t idesc_q1 = idesc_m128(static_cast<uint32_t>(p.qp_rows[1] > 0 ? p.qp_rows[1] : 16), 0);
+        uint32_t q_dst = 0;                                            // region of head q_g
+        uint32_t q_full_idx = 0;
+        bool q_last_head = false;
+        auto ready = [&](uint64_t* bar, uint32_t parity) -> bool {     // one lane polls, the warp stays converged
+            uint32_t ok = 0;
+            if (lane == 0) ok = mbar_test_wait(bar, parity) ? 1u : 0u;
+            return __shfl_sync(0xffffffffu, ok, 0) != 0;
+        };
+        auto qkv_step = [&]() {                                        // precondition: the ring slot has landed
             tc_fence_after_sync();
-            tr_ev<TRACE>(p.trace, 0, it, 8, 1);
-            issue_qkv(0);
-            tr_ev<TRACE>(p.trace, 0, it, 8, 2);
+            if (elect_one_sync()) {
+                const int ksteps = min(4, p.k16 - 4 * q_s);
+                const uint32_t d = q_pc ? q_dst + static_cast<uint32_t>(p.qp_rows[0]) : q_dst;
+                const uint64_t adesc = x_desc + static_cast<uint64_t>(q_s * (kPanelBytes >> 4));
+                const uint64_t bdesc = ring_desc + static_cast<uint64_t>(static_cast<uint32_t>(slot) * slot_units);
+                const uint32_t idesc = q_pc ? idesc_q1 : idesc_q0;
+                umma_bf16(d, adesc, bdesc, idesc, q_s > 0 ? 1u : 0u);
+                if (ksteps > 1) umma_bf16(d, adesc + 2, bdesc + 2, idesc, 1u);
+                if (ksteps > 2) umma_bf16(d, adesc + 4, bdesc + 4, idesc, 1u);
+                if (ksteps > 3) umma_bf16(d, adesc + 6, bdesc + 6, idesc, 1u);
+                umma_commit(&bars->w_empty[slot]);
+                if (q_step == q_steps - 1) {
+                    umma_commit(&bars->qkv_full[q_full_idx]);
+                    if (q_last_head) umma_commit(&bars->x_empty);      // the x tile is no longer an operand
+                }
+            }
+            __syncwarp();
+            ++q_step;
+            if (++q_pc == p.qkv_pieces) { q_pc = 0; ++q_s; }
+            if (++slot == p.w_slots) { slot = 0; wph ^= 1; }
+        };
+        auto qkv_begin = [&](int g) {
+            q_g = g; q_step = 0; q_s = 0; q_pc = 0;
+            q_dst = region_of(g);
+            q_full_idx = (!p.fuse_proj && p.nreg == 2) ? static_cast<uint32_t>(g & 1) : 0u;
+            q_last_head = (g % p.nH) == p.nH - 1;
+        };
+        auto qkv_finish = [&]() {
+            while (q_step < q_steps) {
+                mbar_wait(&bars->w_full[slot], wph);
+                qkv_step();
+            }
+        };
+        q_step = q_steps;                                              // nothing pending
+
+        if (my_tiles > 0) {
+            mbar_wait(&bars->x_full, 0);
+            qkv_begin(0);
+            qkv_finish();
+        }
+        for (int it = 0; it < my_tiles; ++it) {
             for (int h = 0; h < p.nH; ++h) {
-                const uint32_t par = static_cast<uint32_t>(it * p.nH + h) & 1;
-                // ---- S = q k^T : q bf16 in TMEM (unit u at column 16 u of the region), k panel in shared memory
-                tr_ev<TRACE>(p.trace, 0, it, h, 0);
-                mbar_wait(&bars->qkv_ready, par);
-                tc_fence_after_sync();
-                tr_ev<TRACE>(p.trace, 0, it, h, 1);
-                if (elect_one_sync()) {
-                    for (int u = 0; u < uq; ++u) {
-                        const uint32_t off = static_cast<uint32_t>((u >> 2) * kPanelBytes + (u & 3) * 32);
-                        umma_bf16_ts(t_s, t_r + static_cast<uint32_t>(16 * u), umma_desc_k_sw128(k_addr + off), idesc_s, u == 0 ? 0u : 1u);
-                    }
-                    umma_commit(&bars->s_full);
-                }
-                __syncwarp();
-                // ---- O = P v : P bf16 in TMEM (16 keys per step = 8 packed columns), v rows as MN-major B operand
-                mbar_wait(&bars->p_ready, par);
-                tc_fence_after_sync();
-                tr_ev<TRACE>(p.trace, 0, it, h, 2);
-                if (elect_one_sync()) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_bf16_ts(t_o, t_s + static_cast<uint32_t>(8 * k), desc_mn_sw128(v_addr + static_cast<uint32_t>(k * 2048), kPanelBytes),
-                                     idesc_pv, k == 0 ? 0u : 1u);
-                    umma_commit(&bars->o_full);
-                }
-                __syncwarp();
-                if (p.fuse_proj) {
-                    tr_ev<TRACE>(p.trace, 0, it, h, 3);
-                    if (h + 1 < p.nH) issue_qkv(h + 1);                  // runs while the epilogue normalises O
-                    tr_ev<TRACE>(p.trace, 0, it, h, 4);
-                    mbar_wait(&bars->o_ready, par);
-                    tr_ev<TRACE>(p.trace, 0, it, h, 5);
-                    if (h == 0) mbar_wait(&bars->proj_free, (static_cast<uint32_t>(it) & 1) ^ 1);
-                    mbar_wait(&bars->w2_full[slot2], ph2);
+                const int g = it * p.nH + h;
+                const uint32_t par = static_cast<uint32_t>(g) & 1;
+                const bool next_in_tile = h + 1 < p.nH;
+                const bool more_tiles = it + 1 < my_tiles;
+                const uint32_t t_r = region_of(g);
+                const uint32_t t_s = t_r + static_cast<uint32_t>(p.hdp);
+                const uint32_t t_o = p.fuse_proj ? tmem + static_cast<uint32_t>(p.col_o) : t_r;
+                auto issue_s = [&]() {
+                    // S = q k^T : q bf16 in TMEM (unit u at column 16 u of the region), k panel in shared memory
                     tc_fence_after_sync();
                     if (elect_one_sync()) {
-                        const uint64_t bdesc = ring2_desc + static_cast<uint64_t>(static_cast<uint32_t>(slot2) * slot2_units);
                         for (int u = 0; u < uq; ++u) {
-                            const uint32_t acc = (h > 0 || u > 0) ? 1u : 0u;
-                            umma_bf16_ts(t_p, t_o + static_cast<uint32_t>(16 * u), bdesc + 2 * u, idesc_p0, acc);
-                            if (p.n_pp > 1)
-                                umma_bf16_ts(t_p + static_cast<uint32_t>(p.pp_rows[0]), t_o + static_cast<uint32_t>(16 * u),
-                                             bdesc + static_cast<uint64_t>(p.pp_rows[0] * 8) + 2 * u, idesc_p1, acc);
+                            const uint32_t off = static_cast<uint32_t>((u >> 2) * kPanelBytes + (u & 3) * 32);
+                            umma_bf16_ts(t_s, t_r + static_cast<uint32_t>(16 * u), umma_desc_k_sw128(k_addr + off), idesc_s, u == 0 ? 0u : 1u);
                         }
-                        umma_commit(&bars->w2_empty[slot2]);
-                        if (h == p.nH - 1) umma_commit(&bars->proj_full);
+                        umma_commit(&bars->s_full);
                     }
                     __syncwarp();
-                    tr_ev<TRACE>(p.trace, 0, it, h, 6);
-                    if (++slot2 == p.w2_slots) { slot2 = 0; ph2 ^= 1; }
-                } else {
-                    tr_ev<TRACE>(p.trace, 0, it, h, 3);
-                    mbar_wait(&bars->o_ready, par);                      // O overlays the q|k|v region: wait until it has been read
+                };
+                auto issue_pv = [&]() {
+                    // O = P v : P bf16 in TMEM (16 keys per step = 8 packed columns), v rows as MN-major B operand; without proj
+                    // fusion O lands on the q columns (q was consumed by S, which has completed: the softmax ran on it)
                     tc_fence_after_sync();
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16_ts(t_o, t_s + static_cast<uint32_t>(8 * k), desc_mn_sw128(v_addr + static_cast<uint32_t>(k * 2048), kPanelBytes),
+                                         idesc_pv, k == 0 ? 0u : 1u);
+                        umma_commit(&bars->o_full);
+                    }
+                    __syncwarp();
+                };
+                tr_ev<TRACE>(p.trace, 0, it, h, 0);
+                if (p.fuse_proj) {
+                    // one region: S / P overlay the k|v accumulators, so the next head's q|k|v follows P V in the pipe; it runs
+                    // while the epilogue normalises O, whose bf16 copy then feeds  Y += O_h Wp_h^T  (persistent accumulator)
+                    mbar_wait(&bars->qkv_ready, par);
+                    tr_ev<TRACE>(p.trace, 0, it, h, 2);
+                    issue_s();
+                    mbar_wait(&bars->p_ready, par);
+                    tr_ev<TRACE>(p.trace, 0, it, h, 3);
+                    issue_pv();
+                    tr_ev<TRACE>(p.trace, 0, it, h, 4);
+                    if (next_in_tile) {
+                        qkv_begin(g + 1);
+                        qkv_finish();
+                    }
+                    tr_ev<TRACE>(p.trace, 0, it, h, 1);
+                    ensure_o(g);
+                    if (h == 0) {
+                        mbar_wait(&bars->proj_free, (static_cast<uint32_t>(it) & 1) ^ 1);
+                        tc_fence_after_sync();
+                    }
+                    uint32_t dcol = 0;
+                    for (int pc = 0; pc < p.n_pp; ++pc) {
+                        mbar_wait(&bars->p_full[pslot], pph);
+                        tc_fence_after_sync();
+                        if (elect_one_sync()) {
+                            const uint64_t bdesc = pring_desc + static_cast<uint64_t>(static_cast<uint32_t>(pslot) * pslot_units);
+                            const uint32_t idesc = idesc_m128(static_cast<uint32_t>(p.pp_rows[pc]), 0);
+                            for (int u = 0; u < uq; ++u)
+                                umma_bf16_ts(tmem + dcol, t_o + static_cast<uint32_t>(16 * u), bdesc + 2 * u, idesc, (h > 0 || u > 0) ? 1u : 0u);
+                            umma_commit(&bars->p_empty[pslot]);
+                            if (h == p.nH - 1 && pc == p.n_pp - 1) umma_commit(&bars->proj_full);
+                        }
+                        __syncwarp();
+                        dcol += static_cast<uint32_t>(p.pp_rows[pc]);
+                        if (++pslot == p.p_slots) { pslot = 0; pph ^= 1; }
+                    }
                     tr_ev<TRACE>(p.trace, 0, it, h, 5);
-                    if (h + 1 < p.nH) issue_qkv(h + 1);
-                    tr_ev<TRACE>(p.trace, 0, it, h, 6);
+                    if (!next_in_tile && more_tiles) {
+                        mbar_wait(&bars->x_full, static_cast<uint32_t>(it + 1) & 1);
+                        qkv_begin(g + 1);                              // next tile's first head: overlaps the last epilogue of this tile
+                        qkv_finish();
+                    }
+                } else if (p.nreg == 2) {
+                    // the other region was last used by head g - 1: once its O has been read it takes the next head's q|k|v, which
+                    // the tensor pipe computes while the epilogue warps turn head g around (also across tile borders)
+                    if (g >= 1) ensure_o(g - 1);
+                    const bool look = next_in_tile || more_tiles;
+                    bool began = false;
+                    if (next_in_tile) { qkv_begin(g + 1); began = true; }
+                    bool s_done = false, pv_done = false;
+                    while (!pv_done) {
+                        if (!s_done) {
+                            if (ready(&bars->qkv_ready, par)) { tr_ev<TRACE>(p.trace, 0, it, h, 2); issue_s(); s_done = true; continue; }
+                        } else if (ready(&bars->p_ready, par)) {
+                            tr_ev<TRACE>(p.trace, 0, it, h, 3);
+                            issue_pv();
+                            pv_done = true;
+                            continue;
+                        }
+                        if (look && !began && ready(&bars->x_full, static_cast<uint32_t>(it + 1) & 1)) { qkv_begin(g + 1); began = true; }
+                        if (began && q_step < q_steps && ready(&bars->w_full[slot], wph)) qkv_step();
+                    }
+                    tr_ev<TRACE>(p.trace, 0, it, h, 4);
+                    if (look) {
+                        if (!began) {
+                            mbar_wait(&bars->x_full, static_cast<uint32_t>(it + 1) & 1);
+                            qkv_begin(g + 1);
+                        }
+                        qkv_finish();
+                    }
+                    tr_ev<TRACE>(p.trace, 0, it, h, 1);
+                } else {
+                    mbar_wait(&bars->qkv_ready, par);
+                    tr_ev<TRACE>(p.trace, 0, it, h, 2);
+                    issue_s();
+                    mbar_wait(&bars->p_ready, par);
+                    tr_ev<TRACE>(p.trace, 0, it, h, 3);
+                    issue_pv();
+                    tr_ev<TRACE>(p.trace, 0, it, h, 4);
+                    ensure_o(g);                                       // single region: strictly one head after the other
+                    if (next_in_tile || more_tiles) {
+                        if (!next_in_tile) mbar_wait(&bars->x_full, static_cast<uint32_t>(it + 1) & 1);
+                        qkv_begin(g + 1);
+                        qkv_finish();
+                    }
                 }
             }
         }
@@ -368,19 +443,45 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         const int rsw = r & 7;
         const int n = r & 63;
         const uint32_t kcol0 = static_cast<uint32_t>((r >> 6) * 64);   // my window's keys inside the 128 S columns
-        const int qb = ((n >> 3) + 7) * 15 + (n & 7) + 7 - grp * 30;   // my keys are 16 grp .. 16 grp + 15 = key rows 2 grp, 2 grp + 1
+        // slot -> (y, x) inside the window (block-major for R = 4, see the x loader); my 16 keys are slots 16 grp .. 16 grp + 15:
+        // R = 8: key rows 2 grp, 2 grp + 1;  R = 4: the 4 x 4 block grp
+        const bool blk4 = p.box_r == 4;
+        const int ny = blk4 ? ((n >> 5) << 2) + ((n >> 2) & 3) : (n >> 3);
+        const int nx = blk4 ? (((n >> 4) & 1) << 2) + (n & 3) : (n & 7);
+        const int ky0 = blk4 ? (grp >> 1) * 4 : 2 * grp, kx0 = blk4 ? (grp & 1) * 4 : 0;   // first key of my 16
+        const int qb = (ny - ky0 + 7) * 15 + (nx - kx0 + 7);           // bias index of that key; key (ky0 + dy, kx0 + dx): - (15 dy + dx)
         const uint32_t k_row = smem_u32(k_buf) + static_cast<uint32_t>(r * 128);
         const uint32_t v_row = smem_u32(v_buf) + static_cast<uint32_t>(r * 128);
         const float2 sc2 = f2_(p.scale_log2e, p.scale_log2e);
-        const uint32_t t_r = tmem + lane_off + static_cast<uint32_t>(p.col_r), t_s = tmem + lane_off + static_cast<uint32_t>(p.col_s);
-        const uint32_t t_o = tmem + lane_off + static_cast<uint32_t>(p.col_o), t_p = tmem + lane_off + static_cast<uint32_t>(p.col_proj);
+        const uint32_t t_base = tmem + lane_off;
+        const int t128 = grp * 32 + lane;
 
         for (int it = 0; it < my_tiles; ++it) {
+            const int tile = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
             const int mb = it & 1;
-            mbar_wait(&bars->x_full, static_cast<uint32_t>(it) & 1);   // s_tok / s_msk of this tile are visible
-            const int tok = s_tok[mb * 128 + r];
-            const uint32_t mword = s_msk[(mb * 128 + r) * 2 + (grp >> 1)];
-            const uint32_t mbits = (mword >> (16 * (grp & 1))) & 0xffffu;
+            // ---- my row: slot -> token (closed form of roll + window_partition) and the mask bits of my 16 keys
+            int tok;
+            uint32_t mbits = 0xffffu;
+            {
+                const int win = tile * 2 + (r >> 6);
+                const int b = win / nW, w = win - b * nW;
+                const int wy = (w / nwx) * 8, wx = (w % nwx) * 8;
+                const int ys = wy + ny, xs = wx + nx;
+                int y = ys + p.shift; if (y >= p.H) y -= p.H;
+                int x = xs + p.shift; if (x >= p.W) x -= p.W;
+                tok = (b * p.H + y) * p.W + x;
+                if (p.shift > 0) {
+                    // key k lies in my mask region iff its row AND its column do (region id = 3 ry + rx, src/drct.py:449-470)
+                    const int my_ry = region_1d_(ys, p.H, p.shift), my_rx = region_1d_(xs, p.W, p.shift);
+                    const int kw = blk4 ? 4 : 8, kh = 16 / kw;         // my keys: kh rows of kw
+                    uint32_t xmask = 0;
+                    for (int j = 0; j < kw; ++j) xmask |= (region_1d_(wx + kx0 + j, p.W, p.shift) == my_rx ? 1u : 0u) << j;
+                    mbits = 0u;
+                    for (int i = 0; i < kh; ++i)
+                        if (region_1d_(wy + ky0 + i, p.H, p.shift) == my_ry) mbits |= xmask << (i * kw);
+                }
+            }
+            if (grp == 0) s_tok[mb * 128 + r] = tok;
             float rstd, nrm;
             {
                 const float2* sp = p.stats_in + static_cast<long long>(tok) * p.stats_in_stride;
@@ -398,10 +499,15 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
             const float2 rstd2 = f2_(rstd, rstd), nrm2 = f2_(nrm, nrm);
 
             for (int h = 0; h < p.nH; ++h) {
-                const uint32_t par = static_cast<uint32_t>(it * p.nH + h) & 1;
+                const int g = it * p.nH + h;
+                const uint32_t par = static_cast<uint32_t>(g) & 1;
+                const int reg = (!p.fuse_proj && p.nreg == 2) ? (g & 1) : 0;
+                const uint32_t t_r = t_base + static_cast<uint32_t>(p.fuse_proj ? p.cp : reg * p.rsz);
+                const uint32_t t_s = t_r + static_cast<uint32_t>(p.hdp);
+                const uint32_t t_o = p.fuse_proj ? t_base + static_cast<uint32_t>(p.col_o) : t_r;
                 // ---- q | k | v of head h: folded LayerNorm + bias -> bf16; q in place (TMEM), k / v into the operand panels
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 0);
-                mbar_wait(&bars->qkv_full, par);
+                mbar_wait(&bars->qkv_full[reg], static_cast<uint32_t>((!p.fuse_proj && p.nreg == 2) ? (g >> 1) : g) & 1);
                 tc_fence_after_sync();
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 1);
                 for (int u = grp; u < 3 * uq; u += 4) {
@@ -451,13 +557,24 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     tmem_ld16(t_s + kcol0 + static_cast<uint32_t>(16 * grp), raw);
                     tmem_ld_wait();
                     const float* bias = s_bias + h * 232 + qb;
+                    if (blk4) {
 #pragma unroll
-                    for (int k = 0; k < 16; k += 2) {
-                        const float2 bv = f2_(bias[-((k >> 3) * 15 + (k & 7))], bias[-(((k + 1) >> 3) * 15 + ((k + 1) & 7))]);
-                        const float2 v = __ffma2_rn(f2_(__uint_as_float(raw[k]), __uint_as_float(raw[k + 1])), sc2, bv);
-                        t[k] = v.x;
-                        t[k + 1] = v.y;
-                        mx = fmaxf(mx, fmaxf(v.x, v.y));
+                        for (int k = 0; k < 16; k += 2) {
+                            const float2 bv = f2_(bias[-((k >> 2) * 15 + (k & 3))], bias[-(((k + 1) >> 2) * 15 + ((k + 1) & 3))]);
+                            const float2 v = __ffma2_rn(f2_(__uint_as_float(raw[k]), __uint_as_float(raw[k + 1])), sc2, bv);
+                            t[k] = v.x;
+                            t[k + 1] = v.y;
+                            mx = fmaxf(mx, fmaxf(v.x, v.y));
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; k += 2) {
+                            const float2 bv = f2_(bias[-((k >> 3) * 15 + (k & 7))], bias[-(((k + 1) >> 3) * 15 + ((k + 1) & 7))]);
+                            const float2 v = __ffma2_rn(f2_(__uint_as_float(raw[k]), __uint_as_float(raw[k + 1])), sc2, bv);
+                            t[k] = v.x;
+                            t[k + 1] = v.y;
+                            mx = fmaxf(mx, fmaxf(v.x, v.y));
+                        }
                     }
                 }
                 s_max[grp * 128 + r] = mx;
@@ -488,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 if (lane == 0) mbar_arrive(&bars->p_ready);
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 4);
 
-                // ---- O = P v done: normalise
+                // ---- O = P v done: normalise; fuse_proj: pack into the persistent bf16 operand, else store the rows
                 mbar_wait(&bars->o_full, par);
                 tc_fence_after_sync();
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 5);
@@ -506,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                             pk[e] = pack_bf16x2(v.x, v.y);
                         }
                         if (p.fuse_proj) {
-                            tmem_st8_(t_o + static_cast<uint32_t>(16 * u), pk);
+                            tmem_st8_(t_o + static_cast<uint32_t>(16 * u), pk);        // in place: A operand of the proj MMAs
                         } else {
                             uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<long long>(tok) * p.ldo + h * p.hdp + 16 * u);
                             dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -529,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 // 32 tile rows) only touches its own panel rows, so quadrant-wide named barriers are all the sync needed.
                 const int nch = (p.cp + 63) >> 6;
                 const uint32_t panel0 = smem_u32(k_buf), panel1 = smem_u32(v_buf);
-                const int t128 = grp * 32 + lane;
+                named_bar_sync(1 + quad, 128);                           // s_tok of the quadrant's rows is visible
                 auto issue_res = [&](int c) {
                     const uint32_t pbase = (c & 1) ? panel1 : panel0;
 #pragma unroll
@@ -556,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     const int col0 = 64 * c + 16 * grp;
                     const bool active = col0 < p.cp;
                     uint32_t raw[16];
-                    if (active) tmem_ld16(t_p + static_cast<uint32_t>(col0), raw);
+                    if (active) tmem_ld16(t_base + static_cast<uint32_t>(col0), raw);
                     if (c + 1 < nch) asm volatile("cp.async.wait_group 1;" ::: "memory");
                     else asm volatile("cp.async.wait_group 0;" ::: "memory");
                     named_bar_sync(1 + quad, 128);                       // the quadrant's shortcut chunk has landed
@@ -588,6 +705,11 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                             st_shared_v4(sa, pack_bf16x2(v0.x, v0.y), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v2.x, v2.y), pack_bf16x2(v3.x, v3.y));
                         }
                     }
+                    if (c == nch - 1) {                                  // the accumulator has been read: the regions may take q|k|v again
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->proj_free);
+                    }
                     named_bar_sync(1 + quad, 128);                       // the quadrant's y chunk is complete
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
@@ -616,12 +738,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                         issue_res(c + 2);
                     }
                 }
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->proj_free);
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, 8, 2);
                 if (p.stats_out != nullptr) {
-                    named_bar_sync(1 + quad, 128);                       // everybody is past the softmax scratch of the last head
                     s_stat[grp * 128 + r] = f2_(st.x + st.y, sq.x + sq.y);
                     named_bar_sync(1 + quad, 128);
                     if (grp == 0) {
@@ -629,25 +747,25 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                         p.stats_out[static_cast<long long>(tok) * p.stats_out_stride + p.stats_out_slot0] =
                             f2_((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y));
                     }
-                    named_bar_sync(1 + quad, 128);                       // s_stat aliases s_max | s_sum of the next tile
                 }
+                named_bar_sync(1 + quad, 128);   // panels copied out / s_stat consumed before the next tile's k, v, s_max, s_sum writes
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->meta_free[mb]);
         }
     }
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == kW1LoaderWarp) {
+    if (warp == kWLoaderWarp) {
         tc_fence_after_sync();
         tmem_dealloc<512>(tmem);
     }
 }
 
 int fixed_smem_bytes(int nH, int hdp, int cp) {
-    return (2 * nH * 3 * hdp + cp + nH * 232) * 4 + 256 * 4 + 512 * 4 + 2 * 512 * 4 + static_cast<int>(sizeof(AttnBlockBarriers)) + 64;
+    return (2 * nH * 3 * hdp + cp + nH * 232) * 4 + 256 * 4 + 2 * 512 * 4 + static_cast<int>(sizeof(AttnBlockBarriers)) + 64;
 }
+
+int round16(int v) { return (v + 15) / 16 * 16; }
 
 }  // namespace
 
@@ -659,27 +777,38 @@ int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj) {
     p.ks = (C + 63) / 64;
     p.k16 = (C + 15) / 16;
     p.pan = (hdp + 63) / 64;
-    p.cp = (C + 15) / 16 * 16;
+    p.cp = round16(C);
+    // attention only: a TMEM region hosts a head from start to end -- q|k|v accumulators (3 hdp) -> q bf16 in place + S / P over
+    // the dead k|v columns (hdp + 128) -> O over the dead q columns; two regions let the next head's q|k|v run one head ahead.
+    // fuse_proj: [proj accumulator cp | region hdp + 128 | O hdp]; q|k|v (3 hdp <= hdp + 128) reuses the region head after head.
+    p.rsz = 3 * hdp > hdp + 128 ? 3 * hdp : hdp + 128;
+    if (p.rsz > 512) return 0;
     p.fuse_proj = (allow_proj && hdp <= 64 && p.cp + 2 * hdp + 128 <= 512) ? 1 : 0;
-    if (p.fuse_proj) {
-        p.col_proj = 0; p.col_r = p.cp; p.col_s = p.cp + hdp; p.col_o = p.cp + hdp + 128;
-    } else {
-        if (3 * hdp > 384) return 0;
-        p.col_proj = 0; p.col_r = 0; p.col_s = 384; p.col_o = hdp;     // O overlays the dead k accumulator
-    }
+    p.nreg = (!p.fuse_proj && 2 * p.rsz <= 512) ? 2 : 1;
+    p.col_o = p.fuse_proj ? p.cp + hdp + 128 : 0;
+    // a [3 hdp x 64] qkv slab is one ring slot and one issue step (every step costs ~400 cycles of wait / commit bookkeeping on
+    // top of its MMAs, so steps are kept as large as the MMA N limit of 256 allows); 3 hdp > 256: two N pieces
     const int n3 = 3 * hdp;
-    if (n3 <= 256) { p.qkv_pieces = 1; p.qp_rows[0] = n3; p.qp_rows[1] = 0; }
-    else { p.qkv_pieces = 2; p.qp_rows[0] = (n3 / 2 + 15) / 16 * 16; p.qp_rows[1] = n3 - p.qp_rows[0]; }
-    if (p.cp <= 256) { p.n_pp = 1; p.pp_rows[0] = p.cp; p.pp_rows[1] = 0; }
-    else { p.n_pp = 2; p.pp_rows[0] = (p.cp / 2 + 15) / 16 * 16; p.pp_rows[1] = p.cp - p.pp_rows[0]; }
-    p.w1_slot_bytes = (p.qp_rows[0] * 128 + 1023) / 1024 * 1024;       // qp_rows[0] >= qp_rows[1]
-    p.w2_slot_bytes = p.fuse_proj ? (p.cp * 128 + 1023) / 1024 * 1024 : 0;
-    p.w2_slots = p.fuse_proj ? 1 : 0;
-    const int avail = kSmemLimit - p.ks * kPanelBytes - 2 * p.pan * kPanelBytes - fixed_smem_bytes(nH, hdp, p.cp) - p.w2_slots * p.w2_slot_bytes;
-    p.w1_slots = avail / p.w1_slot_bytes;
-    if (p.w1_slots > kMaxSlots) p.w1_slots = kMaxSlots;
-    if (p.w1_slots < 2) return 0;
-    if (p.fuse_proj && avail - p.w1_slots * p.w1_slot_bytes >= p.w2_slot_bytes && p.w1_slots >= 4) p.w2_slots = 2;
+    p.qkv_pieces = n3 <= 256 ? 1 : 2;
+    p.qp_rows[0] = p.qkv_pieces == 1 ? n3 : round16(n3 / 2);
+    p.qp_rows[1] = n3 - p.qp_rows[0];
+    p.qp_rows[2] = p.qp_rows[3] = 0;
+    p.w_slot_bytes = (p.qp_rows[0] * 128 + 1023) / 1024 * 1024;        // qp_rows[0] >= qp_rows[1]
+    p.n_pp = 0;
+    p.p_slots = 0;
+    p.p_slot_bytes = 0;
+    for (int i = 0; i < 4; ++i) p.pp_rows[i] = 0;
+    if (p.fuse_proj) {                                                 // a head's proj slab [cp x 64]: one MMA N piece, or two when cp > 256
+        p.n_pp = p.cp <= 256 ? 1 : 2;
+        p.pp_rows[0] = p.n_pp == 1 ? p.cp : round16(p.cp / 2);
+        p.pp_rows[1] = p.cp - p.pp_rows[0];
+        p.p_slot_bytes = (p.pp_rows[0] * 128 + 1023) / 1024 * 1024;
+        p.p_slots = p.n_pp;                                            // the ring holds one head's proj weights: fetched a head ahead
+    }
+    const int avail = kSmemLimit - p.ks * kPanelBytes - 2 * p.pan * kPanelBytes - fixed_smem_bytes(nH, hdp, p.cp) - p.p_slots * p.p_slot_bytes;
+    p.w_slots = avail / p.w_slot_bytes;
+    if (p.w_slots > kMaxSlots) p.w_slots = kMaxSlots;
+    if (p.w_slots < 2) return 0;
     return p.fuse_proj ? 2 : 1;
 }
 
@@ -689,10 +818,14 @@ int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream) {
     if ((reinterpret_cast<uintptr_t>(p.x) & 15) || (reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldx % 8) || (p.ldo % 8) ||
         (reinterpret_cast<uintptr_t>(p.w1p) & 15) || (reinterpret_cast<uintptr_t>(p.w2p) & 15))
         return ADSR_ERR_BAD_ALIGN;
-    if (p.ldx < p.k16 * 16) return ADSR_ERR_BAD_SHAPE;                 // zero-filled chunk addresses stay inside the row pitch
+    if (p.ldx < (p.C + 7) / 8 * 8) return ADSR_ERR_BAD_SHAPE;
     if (p.fuse_proj ? p.ldo < (p.C + 7) / 8 * 8 : p.ldo < p.nH * p.hdp) return ADSR_ERR_BAD_SHAPE;
     p.n_tiles = p.B * nW / 2;
-    const int smem_bytes = p.ks * kPanelBytes + 2 * p.pan * kPanelBytes + p.w1_slots * p.w1_slot_bytes + p.w2_slots * p.w2_slot_bytes +
+    if (p.shift != 0 && p.shift != 4) return ADSR_ERR_BAD_SHAPE;      // square token boxes of side 8 / 4 cover these two
+    p.box_r = p.shift == 0 ? 8 : 4;
+    const int st = encode_tmap_nhwc_box_bf16(&p.tmap_x, p.x, p.B, p.H, p.W, p.C, p.ldx, p.box_r);
+    if (st != ADSR_OK) return st;
+    const int smem_bytes = p.ks * kPanelBytes + 2 * p.pan * kPanelBytes + p.w_slots * p.w_slot_bytes + p.p_slots * p.p_slot_bytes +
                            fixed_smem_bytes(p.nH, p.hdp, p.cp);
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;

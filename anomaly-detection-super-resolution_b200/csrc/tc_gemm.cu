@@ -566,6 +566,22 @@ int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, lo
     return encode_2d(map, base, rows, cols, ld_elems, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// token rows viewed as the NHWC image [B, H, W, C]: boxes of R x R tokens x 64 channels (the window pieces of swin_attn.cu);
+// a box lands as R*R rows of 128 bytes (x fastest) in the 128-byte-swizzle operand layout
+int encode_tmap_nhwc_box_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int R) {
+    EncodeFn encode = get_encode_fn();
+    if (encode == nullptr) return ADSR_ERR_CUDA;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld_elems) * 2, static_cast<cuuint64_t>(ld_elems) * 2 * W,
+                                   static_cast<cuuint64_t>(ld_elems) * 2 * W * H};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(R), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ADSR_OK : ADSR_ERR_CUDA;
+}
+
 // 32 x 32 bf16 boxes in the 64-byte-swizzle layout of the epilogue staging tiles (residual loads / output stores)
 int encode_tmap_epilogue_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld_elems) {
     return encode_2d(map, base, rows, cols, ld_elems, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);

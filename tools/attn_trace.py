@@ -28,14 +28,14 @@ setter(trace.data_ptr()); run(); torch.cuda.synchronize(); setter(None)
 t = trace.cpu().view(3, 4, 9, 8)
 t0 = int(t[t > 0].min())
 rel = lambda v: f"{(int(v) - t0):7d}" if int(v) > 0 else "      -"
-names = {0: ["wait qkv_ready", "S issued<-", "p_ready seen", "PV issued", "qkv(h+1) issued", "o_ready seen", "proj issued", ""],
+names = {0: ["top", "qkv(g+1) all issued", "S issue", "PV issue", "PV issued", "", "", ""],
          1: ["wait qkv_full", "qkv_full seen", "qkv epi done", "s_full seen", "softmax done", "o_full seen", "O epi done", ""]}
 print(f"C={C} heads={heads} hdp={hdp} shift={shift} mode={mode}   (SM cycles relative to the first event)")
 for it in range(3):
     print(f"--- tile {it}")
-    print("  producer: wait x_empty %s  got %s  issued %s  landed %s" % tuple(rel(v) for v in t[2, it, 8, :4]))
-    print("  mma: wait x_full %s  got %s  qkv(0) issued %s" % tuple(rel(v) for v in t[0, it, 8, :3]))
+    print("  x loader: wait x_empty %s  got %s  issued %s" % tuple(rel(v) for v in t[2, it, 8, :3]))
+    print("  mma tile end: proj start %s  proj issued %s  next qkv issued %s" % tuple(rel(v) for v in t[0, it, 8, :3]))
     for h in range(heads):
-        print(f"  head {h} mma: " + "  ".join(f"{names[0][k]} {rel(t[0, it, h, k])}" for k in range(7)))
+        print(f"  head {h} mma: " + "  ".join(f"{names[0][k]} {rel(t[0, it, h, k])}" for k in range(5)))
         print(f"  head {h} epi: " + "  ".join(f"{names[1][k]} {rel(t[1, it, h, k])}" for k in range(7)))
     print("  epi: wait proj_full %s  seen %s  proj epi done %s" % tuple(rel(v) for v in t[1, it, 8, :3]))
