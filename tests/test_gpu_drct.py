@@ -75,3 +75,18 @@ def test_drct_rectangular_input_and_gray():
         want = O.drct_forward(sd, x, cfg)
     got = m(x.to(DEV)).cpu()
     assert float((got - want).abs().max()) / 255.0 < TOL
+
+
+@pytest.mark.timeout(600)
+def test_drct_l_64px_lr_vs_oracle():
+    """BASELINE configs[3]: DRCT-L x4 at 64 px LR -> 256 px HR: 16 x 16 windows (N = 256), shift 8, 4096 tokens per image."""
+    cfg = O.DrctCfg(img_size=64, window_size=16)
+    sd = O.make_state_dict(cfg, seed=4, affine_jitter=0.05)
+    m = _model(cfg, sd)
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(11)) * 255.0
+    with torch.no_grad():
+        want = O.drct_forward(sd, x, cfg)
+    got = m(x.to(DEV)).cpu()
+    assert got.shape == (1, 3, 256, 256)
+    err = float((got - want).abs().max()) / 255.0
+    assert err < TOL, f"max|dSR|/rgb_range = {err}"
