@@ -373,6 +373,108 @@ __global__ void __launch_bounds__(128) conv_last_quant_kernel(const __nv_bfloat1
     }
 }
 
+// Tiled variant for Cin = 64 (the DRCT tail) and W % 4 == 0: a block owns an 8 x 64 pixel tile; its 10 x 66 x 64-channel
+// halo tile is fetched with coalesced 16-byte cp.async (zero fill outside the image) into shared memory with a pixel pitch
+// of 144 bytes (conflict-free 16-byte reads); a thread computes FOUR horizontally adjacent pixels, so every weight vector
+// read from shared memory feeds 16 multiply-adds (packed fma.f32x2).  Same fp32 arithmetic as the kernel above.
+constexpr int kClTileW = 64, kClTileH = 8, kClPitch = 144, kClCin = 64;
+constexpr int kClHaloW = kClTileW + 2, kClHaloH = kClTileH + 2;
+constexpr int kClSmemBytes = kClHaloH * kClHaloW * kClPitch + 9 * kClCin * 4 * 4;
+
+__global__ void __launch_bounds__(128) conv_last_quant_tiled_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, int B,
+                                                                     int H, int W, const float* __restrict__ weight,
+                                                                     const float* __restrict__ bias, int nc,
+                                                                     const float* __restrict__ mean, float inv_img_range,
+                                                                     float u8_scale, float* __restrict__ out,
+                                                                     uint8_t* __restrict__ out_u8) {
+    extern __shared__ __align__(16) uint8_t cl_smem[];
+    uint8_t* tile = cl_smem;                                                     // [10][66] pixels x 144 B
+    float* swl = reinterpret_cast<float*>(cl_smem + kClHaloH * kClHaloW * kClPitch);   // [9][64][4]
+    const int tiles_x = (W + kClTileW - 1) / kClTileW, tiles_y = (H + kClTileH - 1) / kClTileH;
+    int bid = blockIdx.x;
+    const int tx0 = (bid % tiles_x) * kClTileW;
+    bid /= tiles_x;
+    const int ty0 = (bid % tiles_y) * kClTileH;
+    const int b = bid / tiles_y;
+
+    // halo tile: 660 pixels x 8 chunks of 16 bytes; consecutive threads fetch consecutive chunks (a pixel row is contiguous)
+    const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+    for (int i = threadIdx.x; i < kClHaloH * kClHaloW * 8; i += 128) {
+        const int ch = i & 7, px = i >> 3;
+        const int hy = px / kClHaloW, hx = px - hy * kClHaloW;
+        const int iy = ty0 + hy - 1, ix = tx0 + hx - 1;
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const __nv_bfloat16* src = in + ((static_cast<long long>(b) * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * ld_in + ch * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + static_cast<uint32_t>(px * kClPitch + ch * 16)), "l"(src),
+                     "r"(ok ? 16 : 0)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = threadIdx.x; i < 9 * kClCin * 4; i += 128) {
+        const int o = i & 3, c = (i >> 2) % kClCin, t = (i >> 2) / kClCin;
+        swl[i] = o < nc ? weight[(o * kClCin + c) * 9 + t] : 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int lx = (threadIdx.x & 15) * 4, ly = threadIdx.x >> 4;               // my 4 pixels: tile row ly, columns lx .. lx + 3
+    float2 acc[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int ty = 0; ty < 3; ++ty) {
+        const uint8_t* row = tile + ((ly + ty) * kClHaloW + lx) * kClPitch;      // halo column lx = image column lx - 1
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+            uint4 v[6];                                                          // 8 channels of the 6 input pixels of this row
+#pragma unroll
+            for (int j = 0; j < 6; ++j) v[j] = *reinterpret_cast<const uint4*>(row + j * kClPitch + ch * 16);
+#pragma unroll
+            for (int tx = 0; tx < 3; ++tx) {
+                const float4* wt = reinterpret_cast<const float4*>(swl) + ((ty * 3 + tx) * kClCin + ch * 8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float4 w = wt[e];
+                    const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4& u = v[i + tx];
+                        const uint32_t word = e < 2 ? u.x : (e < 4 ? u.y : (e < 6 ? u.z : u.w));
+                        const float a = (e & 1) ? bf16_hi(word) : bf16_lo(word);
+                        const float2 a2 = make_float2(a, a);
+                        acc[i][0] = __ffma2_rn(a2, w01, acc[i][0]);
+                        acc[i][1] = __ffma2_rn(a2, w23, acc[i][1]);
+                    }
+                }
+            }
+        }
+    }
+    const int y = ty0 + ly, x = tx0 + lx;
+    if (y >= H || x >= W) return;                                               // W % 4 == 0: a thread's 4 pixels are all in or all out
+    float vout[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) vout[i][o] = o < nc ? (a[o] + __ldg(bias + o)) * inv_img_range + __ldg(mean + o) : 0.f;
+    }
+    if (out) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (o < nc)
+                *reinterpret_cast<float4*>(out + ((static_cast<long long>(b) * nc + o) * H + y) * W + x) =
+                    make_float4(vout[0][o], vout[1][o], vout[2][o], vout[3][o]);
+    }
+    if (out_u8) {
+        uint8_t* dst = out_u8 + ((static_cast<long long>(b) * H + y) * W + x) * nc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (o < nc) dst[i * nc + o] = static_cast<uint8_t>(fminf(fmaxf(vout[i][o] * u8_scale, 0.f), 255.f));   // truncation
+    }
+}
+
 __global__ void quantize_u8_kernel(const float* __restrict__ x, int B, int nc, int H, int W, float u8_scale,
                                    uint8_t* __restrict__ out) {
     const long long total = static_cast<long long>(B) * H * W;
@@ -471,6 +573,20 @@ extern "C" int adsr_conv_last_quant(const void* in, int64_t ld_in, int B, int H,
     if (B <= 0) return ADSR_OK;
     if (nc < 1 || nc > 4 || Cin <= 0 || (Cin % 8) || (ld_in % 8)) return ADSR_ERR_BAD_SHAPE;
     if (reinterpret_cast<uintptr_t>(in) & 15) return ADSR_ERR_BAD_ALIGN;
+    if (Cin == kClCin && (W % 4) == 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(conv_last_quant_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmemBytes) != cudaSuccess)
+                return ADSR_ERR_CUDA;
+            attr_set = true;
+        }
+        const long long blocks = static_cast<long long>(B) * ((H + kClTileH - 1) / kClTileH) * ((W + kClTileW - 1) / kClTileW);
+        if (blocks > 0x7fffffffLL) return ADSR_ERR_BAD_SHAPE;
+        conv_last_quant_tiled_kernel<<<static_cast<int>(blocks), 128, kClSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(in), ld_in, B, H, W, weight, bias, nc, mean, 1.0f / img_range,
+            static_cast<float>(255.0 / static_cast<double>(rgb_range)), out_nchw, out_u8_hwc);
+        return check_launch();
+    }
     const size_t smem = static_cast<size_t>(9) * Cin * 4 * sizeof(float);
     if (smem > 48 * 1024) return ADSR_ERR_BAD_SHAPE;
     const long long total = static_cast<long long>(B) * H * W;

@@ -112,6 +112,27 @@ def test_conv_last_quant(nc, rgb_range):
     assert np.array_equal(u8.cpu().numpy(), want_u8)
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 128, 128), (1, 40, 72), (3, 10, 18)])
+def test_conv_last_quant_sizes(B, H, W):
+    """Full 8 x 64 tiles (the DRCT-L HR size), ragged tiles, and a width that is not a multiple of 4 (generic kernel)."""
+    ops = mod("ops")
+    torch.manual_seed(H + W)
+    nc, Cin, rgb_range = 3, 64, 255.0
+    x = (torch.randn(B * H * W, Cin, device=DEV) * 2).to(torch.bfloat16)
+    w, bias = torch.randn(nc, Cin, 3, 3, device=DEV) * 0.05 * rgb_range, torch.randn(nc, device=DEV) * rgb_range * 0.3
+    mean = torch.tensor(O.RGB_MEAN, device=DEV)
+    out = torch.empty(B, nc, H, W, device=DEV)
+    u8 = torch.empty(B, H, W, nc, device=DEV, dtype=torch.uint8)
+    ops.conv_last_quant(x, B, H, W, Cin, w, bias, nc, mean, 1.0, rgb_range, out, u8)
+    xin = x.float().view(B, H, W, Cin).permute(0, 3, 1, 2)
+    want = F.conv2d(xin, w, bias, padding=1) + mean.view(1, nc, 1, 1)
+    assert (out - want).abs().max() < 1e-4 * float(want.abs().max())
+    assert np.array_equal(u8.cpu().numpy(), S.quantize_u8(out.cpu().numpy(), rgb_range))
+    u8_only = torch.empty_like(u8)
+    ops.conv_last_quant(x, B, H, W, Cin, w, bias, nc, mean, 1.0, rgb_range, None, u8_only)     # the evaluator's call: no fp32 image
+    assert torch.equal(u8_only, u8)
+
+
 def test_quantize_u8_matches_oracle():
     ops = mod("ops")
     torch.manual_seed(4)
