@@ -172,10 +172,54 @@ class BatchedEvaluator:
         self.window_sizes = list(window_sizes) if window_sizes is not None else None
         self.device = torch.device('cuda')
         self.last_sr_u8: Optional[torch.Tensor] = None
+        self._copy_stream = None
+        self._graphs = {}
+        self.use_graph = os.environ.get('ADSR_CUDA_GRAPH', '1') != '0'
+        self._bufs = [None, None]
+        self._next_buf = 0
 
     def step(self, lr: torch.Tensor, hr: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         lr_d = lr.to(self.device, non_blocking=True)
         hr_d = hr.to(self.device, non_blocking=True)
+        if lr.is_cuda and hr.is_cuda and out is None:         # device-resident inputs: the step can be replayed as a CUDA graph
+            return self._score_graphed(lr_d, hr_d)
+        return self._score(lr_d, hr_d, out)
+
+    # ---- the whole step (~1000 kernel launches through the C ABI) as ONE CUDA graph per static input buffer pair
+    def _score_graphed(self, lr_d: torch.Tensor, hr_d: torch.Tensor) -> torch.Tensor:
+        """First call for a buffer pair runs eagerly (workspaces, packed weights), the second one is captured, later ones
+        replay the graph.  The returned table (and last_sr_u8) are the graph's static outputs: valid until the next replay."""
+        if not self.use_graph or ops.PROFILE is not None:
+            return self._score(lr_d, hr_d)
+        key = (lr_d.data_ptr(), hr_d.data_ptr(), tuple(lr_d.shape), tuple(hr_d.shape), lr_d.dtype, hr_d.dtype,
+               tuple(self.window_sizes) if self.window_sizes is not None else None)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            self._graphs[key] = {"graph": None, "keep": (lr_d, hr_d)}
+            return self._score(lr_d, hr_d)
+        if ent["graph"] is None:
+            try:
+                torch.cuda.synchronize(self.device)
+                n0 = ops.LAUNCHES
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ent["out"] = self._score(lr_d, hr_d)
+                    ent["sr_u8"] = self.last_sr_u8
+                ent["launches"] = ops.LAUNCHES - n0
+                ops.LAUNCHES = n0
+                ent["graph"] = g
+            except Exception as e:                            # capture not possible: stay on the eager path (still no fallback
+                self.use_graph = False                        # away from the CUDA kernels)
+                print(f"[adsr] CUDA graph capture disabled: {e}", file=sys.stderr)
+                return self._score(lr_d, hr_d)
+        ent["graph"].replay()
+        ops.LAUNCHES += ent["launches"]
+        self.last_sr_u8 = ent["sr_u8"]
+        return ent["out"]
+
+    def _score(self, lr_d: torch.Tensor, hr_d: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if hr_d.dtype == torch.uint8:                         # already quantised NHWC
             hr_u8 = hr_d
         else:
@@ -189,6 +233,55 @@ class BatchedEvaluator:
             self.window_sizes = metrics.window_sizes_for(min(h, w))
         self.last_sr_u8 = sr_u8
         return metrics.score_batch(sr_u8, hr_u8, self.window_sizes, out)
+
+    # ---- double-buffered input path: the host -> device copies of batch i + 1 run on a copy stream while batch i is computed
+    def submit(self, lr: torch.Tensor, hr: torch.Tensor):
+        """Start the (pinned) host -> device copies of one batch on the copy stream; returns a handle for step_submitted().
+        Two persistent device buffer sets alternate (no allocation per batch): at most one submitted batch may be pending
+        while another one is being computed."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        k = self._next_buf
+        self._next_buf ^= 1
+        key = (tuple(lr.shape), lr.dtype, tuple(hr.shape), hr.dtype)
+        buf = self._bufs[k]
+        if buf is None or buf[0] != key:
+            buf = [key, torch.empty(lr.shape, dtype=lr.dtype, device=self.device), torch.empty(hr.shape, dtype=hr.dtype, device=self.device),
+                   None]                                       # [key, lr_d, hr_d, event: the compute that last read this set]
+            self._bufs[k] = buf
+        with torch.cuda.stream(self._copy_stream):
+            if buf[3] is not None:
+                self._copy_stream.wait_event(buf[3])           # the batch computed from this buffer set two submits ago is done
+            buf[1].copy_(lr, non_blocking=True)
+            buf[2].copy_(hr, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        return k, done
+
+    def step_submitted(self, handle, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        k, done = handle
+        buf = self._bufs[k]
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(done)
+        scores = self._score_graphed(buf[1], buf[2]) if out is None else self._score(buf[1], buf[2], out)
+        buf[3] = torch.cuda.Event()
+        buf[3].record(cur)
+        return scores
+
+    def run_pipelined(self, batches):
+        """Iterates (lr, hr) host batches with one batch of copy look-ahead; yields the device score table of each batch."""
+        it = iter(batches)
+        try:
+            nxt = self.submit(*next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = self.submit(*next(it))
+            except StopIteration:
+                nxt = None
+            yield self.step_submitted(cur)
 
 
 def _dist_info():
@@ -258,22 +351,28 @@ def evaluate_on_test(opt, checkpoint_model_path, output_dir: str, save_images: b
     bs = batch_size or getattr(opt, 'eval_batch_size', None) or 64
     mine = list(range(rank, len(entries), world))            # image index i -> rank i mod R
     rows, ids = [], []
-    with torch.no_grad():
+
+    def host_batches():
+        """(lr, hr) pinned host batches in evaluation order; `order` records the image ids of each batch."""
         for s in range(0, len(mine), bs):
             idx = mine[s:s + bs]
             pairs = [load_pair(entries[i][2], entries[i][3], scale, opt.n_colors, opt.rgb_range) for i in idx]
             shapes = {(tuple(p[0].shape), tuple(p[1].shape)) for p in pairs}
             groups = [list(range(len(idx)))] if len(shapes) == 1 else [[j] for j in range(len(idx))]
             for g in groups:                                  # mixed sizes fall back to one image per launch
-                lr = torch.stack([pairs[j][0] for j in g]).pin_memory()
-                hr = torch.stack([pairs[j][1] for j in g]).pin_memory()
-                rows.append(ev.step(lr, hr))
-                ids += [idx[j] for j in g]
-                if save_images:
-                    sr_np = ev.last_sr_u8.cpu().numpy()
-                    for k, j in enumerate(g):
-                        name = os.path.splitext(os.path.basename(entries[idx[j]][2]))[0]
-                        save_sr_image(sr_np[k], output_dir, name, entries[idx[j]][1], scale)
+                order.append([idx[j] for j in g])
+                yield (torch.stack([pairs[j][0] for j in g]).pin_memory(), torch.stack([pairs[j][1] for j in g]).pin_memory())
+
+    order: List[List[int]] = []
+    with torch.no_grad():
+        for k, scores in enumerate(ev.run_pipelined(host_batches())):   # PNG decode + H2D of batch k + 1 overlap batch k
+            rows.append(scores)
+            ids += order[k]
+            if save_images:
+                sr_np = ev.last_sr_u8.cpu().numpy()
+                for j, i in enumerate(order[k]):
+                    name = os.path.splitext(os.path.basename(entries[i][2]))[0]
+                    save_sr_image(sr_np[j], output_dir, name, entries[i][1], scale)
     n_cols = len(ev.window_sizes) + 2 if ev.window_sizes else 3
     local = torch.cat(rows) if rows else torch.empty(0, n_cols, dtype=torch.float64, device='cuda')
     table = gather_scores(local, torch.tensor(ids, dtype=torch.int64, device='cuda'), len(entries))
