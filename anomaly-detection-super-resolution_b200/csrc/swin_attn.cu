@@ -90,7 +90,7 @@ __device__ __forceinline__ void tr_ev(long long* trace, int role, int it, int h,
     }
 }
 
-template <bool TRACE>
+template <bool TRACE, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_constant__ SwinAttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int x_bytes = p.ks * kPanelBytes;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         s_bq[i] = p.bias_qkv[i];
         s_cq[i] = p.colsum_qkv[i];
     }
-    if (p.fuse_proj)
+    if (FUSE)
         for (int i = threadIdx.x; i < p.cp; i += kThreads) s_bp[i] = p.bias_p[i];
     for (int i = threadIdx.x; i < 225 * p.nH; i += kThreads) {
         const int h = i % p.nH, e = i / p.nH;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         }
     } else if (warp == kPLoaderWarp) {
         // ============================================================ proj weight slabs: (head, N piece) in order, every tile
-        if (p.fuse_proj) {
+        if (FUSE) {
             int slot = 0;
             uint32_t phase = 0;
             const size_t pslab_bytes = static_cast<size_t>(p.cp) * 128u;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
             tc_fence_after_sync();
         };
         auto region_of = [&](int g) -> uint32_t {                      // fuse_proj: one region behind the proj accumulator
-            return tmem + static_cast<uint32_t>(p.fuse_proj ? p.cp : (p.nreg == 2 ? (g & 1) : 0) * p.rsz);
+            return tmem + static_cast<uint32_t>(FUSE ? p.cp : (p.nreg == 2 ? (g & 1) : 0) * p.rsz);
         };
 
         // q|k|v of one head is issued in (K slab, N piece) steps so that the short S / P V MMAs of the current head can cut in
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         auto qkv_begin = [&](int g) {
             q_g = g; q_step = 0; q_s = 0; q_pc = 0;
             q_dst = region_of(g);
-            q_full_idx = (!p.fuse_proj && p.nreg == 2) ? static_cast<uint32_t>(g & 1) : 0u;
+            q_full_idx = (!FUSE && p.nreg == 2) ? static_cast<uint32_t>(g & 1) : 0u;
             q_last_head = (g % p.nH) == p.nH - 1;
         };
         auto qkv_finish = [&]() {
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 const bool more_tiles = it + 1 < my_tiles;
                 const uint32_t t_r = region_of(g);
                 const uint32_t t_s = t_r + static_cast<uint32_t>(p.hdp);
-                const uint32_t t_o = p.fuse_proj ? tmem + static_cast<uint32_t>(p.col_o) : t_r;
+                const uint32_t t_o = FUSE ? tmem + static_cast<uint32_t>(p.col_o) : t_r;
                 auto issue_s = [&]() {
                     // S = q k^T : q bf16 in TMEM (unit u at column 16 u of the region), k panel in shared memory
                     tc_fence_after_sync();
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     __syncwarp();
                 };
                 tr_ev<TRACE>(p.trace, 0, it, h, 0);
-                if (p.fuse_proj) {
+                if (FUSE) {
                     // one region: S / P overlay the k|v accumulators, so the next head's q|k|v follows P V in the pipe; it runs
                     // while the epilogue normalises O, whose bf16 copy then feeds  Y += O_h Wp_h^T  (persistent accumulator)
                     mbar_wait(&bars->qkv_ready, par);
@@ -501,13 +501,13 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
             for (int h = 0; h < p.nH; ++h) {
                 const int g = it * p.nH + h;
                 const uint32_t par = static_cast<uint32_t>(g) & 1;
-                const int reg = (!p.fuse_proj && p.nreg == 2) ? (g & 1) : 0;
-                const uint32_t t_r = t_base + static_cast<uint32_t>(p.fuse_proj ? p.cp : reg * p.rsz);
+                const int reg = (!FUSE && p.nreg == 2) ? (g & 1) : 0;
+                const uint32_t t_r = t_base + static_cast<uint32_t>(FUSE ? p.cp : reg * p.rsz);
                 const uint32_t t_s = t_r + static_cast<uint32_t>(p.hdp);
-                const uint32_t t_o = p.fuse_proj ? t_base + static_cast<uint32_t>(p.col_o) : t_r;
+                const uint32_t t_o = FUSE ? t_base + static_cast<uint32_t>(p.col_o) : t_r;
                 // ---- q | k | v of head h: folded LayerNorm + bias -> bf16; q in place (TMEM), k / v into the operand panels
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 0);
-                mbar_wait(&bars->qkv_full[reg], static_cast<uint32_t>((!p.fuse_proj && p.nreg == 2) ? (g >> 1) : g) & 1);
+                mbar_wait(&bars->qkv_full[reg], static_cast<uint32_t>((!FUSE && p.nreg == 2) ? (g >> 1) : g) & 1);
                 tc_fence_after_sync();
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 1);
                 for (int u = grp; u < 3 * uq; u += 4) {
@@ -622,23 +622,42 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                             const float2 v = __fmul2_rn(f2_(__uint_as_float(raw[2 * e]), __uint_as_float(raw[2 * e + 1])), inv2);
                             pk[e] = pack_bf16x2(v.x, v.y);
                         }
-                        if (p.fuse_proj) {
+                        if (FUSE) {
                             tmem_st8_(t_o + static_cast<uint32_t>(16 * u), pk);        // in place: A operand of the proj MMAs
                         } else {
-                            uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<long long>(tok) * p.ldo + h * p.hdp + 16 * u);
-                            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            // stage the row piece in the k panel (dead: S has completed; same swizzled row layout as k itself)
+                            const uint32_t rowa = k_row + static_cast<uint32_t>((u >> 2) * kPanelBytes);
+                            const int c0 = (2 * u) & 7;
+                            st_shared_v4(rowa + static_cast<uint32_t>(((c0 ^ rsw) << 4)), pk[0], pk[1], pk[2], pk[3]);
+                            st_shared_v4(rowa + static_cast<uint32_t>((((c0 + 1) ^ rsw) << 4)), pk[4], pk[5], pk[6], pk[7]);
                         }
                     }
                 }
                 tmem_st_wait();
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->o_ready);
+                if (lane == 0) mbar_arrive(&bars->o_ready);            // O has left TMEM: the region may be reused
+                if (!FUSE) {
+                    // attention rows -> out[token, h * hdp ...]: the quadrant's 32 staged rows are copied out by its four warps,
+                    // consecutive lanes along a row (coalesced 16-byte pieces instead of one 32-byte piece per lane and row)
+                    named_bar_sync(1 + quad, 128);                       // the quadrant's rows (and s_tok) are complete
+                    const int cpr = p.hdp >> 3;                          // 16-byte chunks per row
+                    const uint32_t kq = smem_u32(k_buf);
+                    for (int id = t128; id < 32 * cpr; id += 128) {
+                        const int rl = id / cpr, ch = id - rl * cpr;
+                        const int rq = quad * 32 + rl;
+                        uint4 val;
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                                     : "r"(kq + static_cast<uint32_t>((ch >> 3) * kPanelBytes + rq * 128 + (((ch & 7) ^ (rq & 7)) << 4))));
+                        *reinterpret_cast<uint4*>(p.out + static_cast<long long>(s_tok[mb * 128 + rq]) * p.ldo + h * p.hdp + ch * 8) = val;
+                    }
+                    named_bar_sync(1 + quad, 128);                       // copied out: the next head may overwrite the k panel
+                }
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 6);
             }
 
-            if (p.fuse_proj) {
+            if (FUSE) {
                 // ---- y = proj + bias + shortcut -> original token rows; (sum, sumsq) of the row for norm2.
                 // 64-column chunks are staged in the idle k / v panels so that every global access is a coalesced 128-byte
                 // row piece: the shortcut chunk is fetched into the panel by cp.async (two chunks ahead, L2 hits), the epilogue
@@ -834,7 +853,8 @@ int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream) {
         kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
         return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };
-    return p.trace != nullptr ? launch(swin_attn_kernel<true>) : launch(swin_attn_kernel<false>);
+    if (p.trace != nullptr) return p.fuse_proj ? launch(swin_attn_kernel<true, true>) : launch(swin_attn_kernel<true, false>);
+    return p.fuse_proj ? launch(swin_attn_kernel<false, true>) : launch(swin_attn_kernel<false, false>);
 }
 
 }  // namespace adsr
