@@ -14,6 +14,8 @@ struct TcGemmParams {
     CUtensorMap tmap_out;  // TMA epilogue: output  [M x (ocol0 + n_store)], box 32 x 32, 64-byte swizzle
     CUtensorMap tmap_res;  // TMA epilogue: residual [M x N], same box (columns >= N read as zero)
     int use_tma;           // 1 = A tiles arrive by TMA (GEMM), 0 = producer warps gather them (conv)
+    int conv_tma;          // conv, stride 1, 128-pixel tiles made of whole image rows: tmap_a is the NHWC image [B, H, W, C] and every
+                           // (tap, channel panel) stage is ONE 4-D TMA box shifted by the tap (zero fill outside the image)
     int epi_tma;           // set by launch_tc_gemm: 1 = TMA epilogue, 0 = manual epilogue
     // A operand: token rows (GEMM) or NHWC image (implicit-GEMM conv)
     const __nv_bfloat16* A;
@@ -123,6 +125,7 @@ struct SwinAttnParams {
     long long* trace;         // optional clock64 timeline of CTA 0 (tools/attn_trace.py), else nullptr
 };
 int encode_tmap_nhwc_box_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int R);
+int encode_tmap_nhwc_box2_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int box_w, int box_h);
 int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj);   // 0 = not covered, 1 = qkv + attention, 2 = + proj
 int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream);
 

@@ -569,12 +569,17 @@ int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, lo
 // token rows viewed as the NHWC image [B, H, W, C]: boxes of R x R tokens x 64 channels (the window pieces of swin_attn.cu);
 // a box lands as R*R rows of 128 bytes (x fastest) in the 128-byte-swizzle operand layout
 int encode_tmap_nhwc_box_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int R) {
+    return encode_tmap_nhwc_box2_bf16(map, base, B, H, W, C, ld_elems, R, R);
+}
+
+// general form: boxes of box_w x box_h tokens x 64 channels (box_w tokens of a row are contiguous in shared memory)
+int encode_tmap_nhwc_box2_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int box_w, int box_h) {
     EncodeFn encode = get_encode_fn();
     if (encode == nullptr) return ADSR_ERR_CUDA;
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld_elems) * 2, static_cast<cuuint64_t>(ld_elems) * 2 * W,
                                    static_cast<cuuint64_t>(ld_elems) * 2 * W * H};
-    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(R), static_cast<cuuint32_t>(R), 1};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -624,6 +629,17 @@ int launch_tc_gemm(TcGemmParams& p, int num_sms, cudaStream_t stream) {
 
     const int units = p.m_tiles * p.n_tiles;
     const int grid = units < num_sms ? units : num_sms;
+    // stride-1 convolutions whose 128-pixel tiles are whole image rows: the A stages come by 4-D TMA boxes (manual-epilogue kernel)
+    p.conv_tma = 0;
+    if (p.conv && p.stride == 1 && p.Hout == p.Hin && p.Wout == p.Win && p.Win <= 128 && (128 % p.Win) == 0 &&
+        ((p.Hin * p.Win) % 128) == 0 && !p.ln_fold && p.stats_out == nullptr && (reinterpret_cast<uintptr_t>(p.A) & 15) == 0) {
+        const int B = p.M / (p.Hin * p.Win);
+        if (encode_tmap_nhwc_box2_bf16(&p.tmap_a, p.A, B, p.Hin, p.Win, p.K8, p.lda, p.Win, 128 / p.Win) == ADSR_OK) {
+            p.conv_tma = 1;
+            p.epi_tma = 0;
+            return launch_tc_gemm_manual(p, grid, stream);
+        }
+    }
     auto launch = [&](auto kernel) -> int {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return ADSR_ERR_CUDA;
         kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(p);

@@ -29,7 +29,7 @@ constexpr int kAStageBytes = 128 * 128;       // 128 rows x 64 bf16
 constexpr int kBStageBytes = 256 * 128;       // up to 256 rows x 64 bf16
 constexpr int kNumThreadsConv = 512;          // 16 warps: loader, MMA, TMEM alloc, spare, 8 epilogue, 4 A producers
 constexpr int kNumThreadsGemm = 384;          // GEMM mode (A by TMA): no producer warps -> up to 168 registers per thread
-enum Mode { MODE_GEMM = 0, MODE_GEMM_LN = 1, MODE_GEMM_STATS = 2, MODE_CONV = 3 };
+enum Mode { MODE_GEMM = 0, MODE_GEMM_LN = 1, MODE_GEMM_STATS = 2, MODE_CONV = 3, MODE_CONV_TMA = 4 };
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kTmemCols = 512;                // 2 accumulator buffers x 256 fp32 columns
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(MODE == MODE_CONV ? kNumThreadsConv : kNumThre
 tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
     constexpr bool STATS = MODE == MODE_GEMM_STATS;
     constexpr bool LNF = MODE == MODE_GEMM_LN;
-    constexpr bool CONV = MODE == MODE_CONV;
+    constexpr bool CONV = MODE == MODE_CONV;            // A stages gathered by producer warps
+    constexpr bool CONVT = MODE == MODE_CONV_TMA;       // A stages = 4-D TMA boxes of the NHWC image, shifted by the tap
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kAStageBytes;
@@ -127,6 +128,7 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
             const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
             const uint32_t tx_bytes = b_bytes + (!CONV ? static_cast<uint32_t>(kAStageBytes) : 0u);
             if (!CONV && lane == 0) tma_prefetch_desc(&p.tmap_a);
+            const int hw = p.Hin * p.Win;
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -137,7 +139,15 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
-                        if (!CONV) tma_load_2d(smem_a + stage * kAStageBytes, &p.tmap_a, ks * 64, m0, &bars->full[stage]);
+                        if (CONVT) {
+                            // tile = 128 / W whole image rows starting at (b, y0); tap (dy, dx) reads the same box shifted by
+                            // (dx, dy): columns / rows outside the image (and channels >= Cin) are zero-filled by the TMA unit
+                            const int tap = ks / p.stages_per_tap, cpan = ks - tap * p.stages_per_tap;
+                            const int b = m0 / hw, y0 = (m0 - b * hw) / p.Win;
+                            tma_load_4d(smem_a + stage * kAStageBytes, &p.tmap_a, cpan * 64, tap % 3 - 1, y0 + tap / 3 - 1, b, &bars->full[stage]);
+                        } else if (!CONV) {
+                            tma_load_2d(smem_a + stage * kAStageBytes, &p.tmap_a, ks * 64, m0, &bars->full[stage]);
+                        }
                         bulk_g2s(smem_b + stage * kBStageBytes, src + static_cast<size_t>(ks) * b_bytes, b_bytes,
                                  &bars->full[stage]);
                     }
@@ -161,7 +171,7 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * 256);
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
                     int steps;
-                    if (CONV) {
+                    if (CONV || CONVT) {
                         steps = p.k16_per_tap - 4 * (ks % p.stages_per_tap);
                     } else {
                         steps = p.k16_total - 4 * ks;
@@ -445,11 +455,12 @@ int launch_tc_gemm_manual(const TcGemmParams& p, int grid, cudaStream_t stream) 
         kernel<<<grid, threads, kSmemBytes, stream>>>(p);
         return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };
-    const bool conv = !p.use_tma;
-    if (conv && (p.ln_fold || p.stats_out != nullptr)) return ADSR_ERR_BAD_SHAPE;
+    const bool conv = !p.use_tma && !p.conv_tma;
+    if ((conv || p.conv_tma) && (p.ln_fold || p.stats_out != nullptr)) return ADSR_ERR_BAD_SHAPE;
     if (p.ln_fold && p.stats_out != nullptr) return ADSR_ERR_BAD_SHAPE;
 #define ADSR_CASE(ACT_)                                                                                        \
     case ACT_:                                                                                                 \
+        if (p.conv_tma) return launch(tc_gemm_manual_kernel<ACT_, MODE_CONV_TMA>, kNumThreadsGemm);            \
         if (conv) return launch(tc_gemm_manual_kernel<ACT_, MODE_CONV>, kNumThreadsConv);                      \
         if (p.ln_fold) return launch(tc_gemm_manual_kernel<ACT_, MODE_GEMM_LN>, kNumThreadsGemm);              \
         if (p.stats_out != nullptr) return launch(tc_gemm_manual_kernel<ACT_, MODE_GEMM_STATS>, kNumThreadsGemm); \
