@@ -128,14 +128,10 @@ extern "C" int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int
 static long long* g_mlp_trace = nullptr;
 extern "C" void adsr_debug_set_mlp_trace(void* device_buffer) { g_mlp_trace = static_cast<long long*>(device_buffer); }
 
-extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, const void* w1_packed, const void* w2_packed,
-                                  const float* bias1, const float* colsum1, const float* bias2, const int32_t* plan, int plan_len,
-                                  float ln_eps, const float* ln_stats_in, int stats_in_slots, int stats_in_stride, void* z,
-                                  int64_t ldz, int num_sms, void* stream) {
-    if (M <= 0) return ADSR_OK;
-    if (plan == nullptr || plan_len < 22 || C <= 0 || ldy < C || ldz < C || ln_stats_in == nullptr || stats_in_slots <= 0)
-        return ADSR_ERR_BAD_SHAPE;
-    SwinMlpParams p{};
+static int swin_mlp_common(SwinMlpParams& p, const void* y, int64_t ldy, int M, int C, const void* w1_packed, const void* w2_packed,
+                           const float* bias1, const float* colsum1, const float* bias2, const int32_t* plan, int plan_len,
+                           float ln_eps, const float* ln_stats_in, int stats_in_slots, int stats_in_stride) {
+    if (plan == nullptr || plan_len < 22 || C <= 0 || ldy < C || ln_stats_in == nullptr || stats_in_slots <= 0) return ADSR_ERR_BAD_SHAPE;
     p.ks1 = plan[0]; p.k1steps = plan[1]; p.nc = plan[2]; p.hc = plan[3]; p.n2 = plan[4];
     p.acc1_col[0] = plan[5]; p.acc1_col[1] = plan[6];
     p.n_pieces = plan[7]; p.piece_rows[0] = plan[8]; p.piece_rows[1] = plan[9];
@@ -150,7 +146,46 @@ extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, cons
     p.stats_in_slots = stats_in_slots; p.stats_in_stride = stats_in_stride;
     p.ln_eps = ln_eps; p.C = C; p.M = M;
     p.trace = g_mlp_trace;
+    return ADSR_OK;
+}
+
+extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, const void* w1_packed, const void* w2_packed,
+                                  const float* bias1, const float* colsum1, const float* bias2, const int32_t* plan, int plan_len,
+                                  float ln_eps, const float* ln_stats_in, int stats_in_slots, int stats_in_stride, void* z,
+                                  int64_t ldz, int num_sms, void* stream) {
+    if (M <= 0) return ADSR_OK;
+    if (ldz < C) return ADSR_ERR_BAD_SHAPE;
+    SwinMlpParams p{};
+    const int st = swin_mlp_common(p, y, ldy, M, C, w1_packed, w2_packed, bias1, colsum1, bias2, plan, plan_len, ln_eps, ln_stats_in,
+                                   stats_in_slots, stats_in_stride);
+    if (st != ADSR_OK) return st;
     return launch_swin_mlp(p, y, ldy, z, ldz, num_sms, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int C, const void* w1_packed, const void* w2_packed,
+                                         const float* bias1, const float* colsum1, const float* bias2, const int32_t* plan,
+                                         int plan_len, float ln_eps, const float* ln_stats_in, int stats_in_slots,
+                                         int stats_in_stride, const void* wadj_packed, const float* bias_adj, float slope,
+                                         void* out, int64_t ldo, int ocol0, float* stats_out, int stats_out_slot0,
+                                         int stats_out_stride, int num_sms, void* stream) {
+    if (M <= 0) return ADSR_OK;
+    if (plan_len < 23 || wadj_packed == nullptr || bias_adj == nullptr || out == nullptr || ldo < ocol0 + 32) return ADSR_ERR_BAD_SHAPE;
+    SwinMlpParams p{};
+    const int st = swin_mlp_common(p, y, ldy, M, C, w1_packed, w2_packed, bias1, colsum1, bias2, plan, plan_len, ln_eps, ln_stats_in,
+                                   stats_in_slots, stats_in_stride);
+    if (st != ADSR_OK) return st;
+    p.fuse_adj = 1;
+    p.adj_tcol = plan[22];
+    p.wadj = static_cast<const uint8_t*>(wadj_packed);
+    p.bias_adj = bias_adj;
+    p.adj_out = static_cast<__nv_bfloat16*>(out);
+    p.ld_adj = ldo;
+    p.adj_col0 = ocol0;
+    p.adj_slope = slope;
+    p.adj_stats = reinterpret_cast<float2*>(stats_out);
+    p.adj_stats_slot0 = stats_out_slot0;
+    p.adj_stats_stride = stats_out_stride;
+    return launch_swin_mlp(p, y, ldy, nullptr, 0, num_sms, static_cast<cudaStream_t>(stream));
 }
 
 static long long* g_attn_trace = nullptr;

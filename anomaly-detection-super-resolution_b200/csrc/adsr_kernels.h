@@ -87,6 +87,18 @@ struct SwinMlpParams {
     int acc1_col[2];
     int w1_slots, w1_slot_bytes, w2_slots, w2_slot_bytes, a_buf_bytes;
     long long* trace;     // optional [4 roles][8 tiles][64][8] clock64 timeline of CTA 0 (tools/mlp_trace.py), else nullptr
+    // optional fused adjust 1x1 conv (src/drct.py:389-393): adj_out[:, adj_col0 + n] = LReLU(z W_adj^T + b)[n], n < 32; z itself is
+    // then NOT written (nothing else reads it)
+    int fuse_adj;
+    int adj_tcol;         // TMEM column of the [128 x 32] adjust accumulator
+    const uint8_t* wadj;  // ks1 slabs [32 rows x 64 bf16], 128-byte swizzle; resident in shared memory
+    const float* bias_adj;   // [32]
+    __nv_bfloat16* adj_out;
+    long long ld_adj;
+    int adj_col0;
+    float adj_slope;
+    float2* adj_stats;    // per-row (sum, sumsq) of the 32 new columns -> adj_stats[row * stride + slot0] (slot0 + 1 is zeroed)
+    int adj_stats_slot0, adj_stats_stride;
 };
 int swin_mlp_fixed_smem_bytes();
 int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, long long ldz, int num_sms, cudaStream_t stream);

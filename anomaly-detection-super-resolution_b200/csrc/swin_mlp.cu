@@ -31,10 +31,11 @@ constexpr int kW2LoaderWarp = 19;             // fc2 weight slabs
 constexpr int kTileWarp = 20;                 // TMEM alloc, y-tile loads, z-tile stores
 constexpr int kThreads = 21 * 32;
 constexpr int kPanelBytes = 128 * 128;        // 128 rows x 64 bf16
-constexpr int kMaxHidden = 512;               // padded hidden columns (sum of chunk strides)
+constexpr int kMaxHidden = 640;               // padded hidden columns (sum of chunk strides)
 constexpr int kMaxN2 = 320;
 constexpr int kConstBytes = (2 * kMaxHidden + kMaxN2) * 4;
 constexpr int kSmemLimit = 232448;            // 227 KB
+constexpr int kAdjSlabBytes = 32 * 128;       // fused adjust: 32 output rows x 64 bf16
 
 struct __align__(16) MlpBarriers {
     uint64_t w1_full[8], w1_empty[8];
@@ -46,6 +47,9 @@ struct __align__(16) MlpBarriers {
     uint64_t h_ready[2][2];                   // [accumulator buffer][64-column slab of the chunk]
     uint64_t acc2_full;
     uint64_t acc2_free;
+    uint64_t adj_w_full;                      // fused adjust: the resident weight slabs have landed
+    uint64_t adj_full;                        // adjust accumulator complete
+    uint64_t adj_done[2];                     // the adjust MMAs have finished reading the z tile in buffer b
     uint32_t tmem_base;
 };
 
@@ -84,10 +88,12 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     uint8_t* a_buf = smem;                                            // 2 x a_buf_bytes
     uint8_t* ring1 = smem + 2 * p.a_buf_bytes;                        // w1_slots x w1_slot_bytes
     uint8_t* ring2 = ring1 + p.w1_slots * p.w1_slot_bytes;            // w2_slots x w2_slot_bytes
-    float* s_bias1 = reinterpret_cast<float*>(ring2 + p.w2_slots * p.w2_slot_bytes);
+    uint8_t* wadj_s = ring2 + p.w2_slots * p.w2_slot_bytes;           // fused adjust: ks1 x [32 x 64] weight slabs (resident)
+    float* s_bias1 = reinterpret_cast<float*>(wadj_s + (p.fuse_adj ? p.ks1 * kAdjSlabBytes : 0));
     float* s_colsum1 = s_bias1 + kMaxHidden;
     float* s_bias2 = s_colsum1 + kMaxHidden;
-    MlpBarriers* bars = reinterpret_cast<MlpBarriers*>(s_bias2 + kMaxN2);
+    float2* s_adj_stat = reinterpret_cast<float2*>(s_bias2 + kMaxN2);   // [2][128] fused adjust: row partials of the two column halves
+    MlpBarriers* bars = reinterpret_cast<MlpBarriers*>(s_adj_stat + (p.fuse_adj ? 256 : 0));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -118,6 +124,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         }
         mbar_init(&bars->acc2_full, 1);
         mbar_init(&bars->acc2_free, kEpiWarps);
+        mbar_init(&bars->adj_w_full, 1);
+        mbar_init(&bars->adj_full, 1);
+        mbar_init(&bars->adj_done[0], 1);
+        mbar_init(&bars->adj_done[1], 1);
         fence_barrier_init();
     }
     if (warp == kTileWarp) tmem_alloc<512>(&bars->tmem_base);
@@ -216,6 +226,29 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         uint32_t phase = 0;
         const uint32_t slot_units = static_cast<uint32_t>(p.w2_slot_bytes >> 4);
         const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring2));
+        // fused adjust: D_adj[128 x 32] = z_tile W_adj^T, issued once the last epilogue has turned the y tile into z in place
+        // (i.e. right when the fc2 accumulator is free again); its completion releases the tile buffer for the next load
+        const uint64_t adj_a_desc0 = umma_desc_k_sw128(smem_u32(a_buf));
+        const uint64_t adj_b_desc = umma_desc_k_sw128(smem_u32(wadj_s));
+        const uint32_t adj_idesc = umma_idesc_bf16_m128(32u);
+        auto issue_adj = [&](int it) {
+            if (it == 0) mbar_wait(&bars->adj_w_full, 0);
+            mbar_wait(&bars->z_ready[it & 1], static_cast<uint32_t>(it >> 1) & 1);
+            tc_fence_after_sync();
+            if (elect_one_sync()) {
+                const uint64_t a_desc = adj_a_desc0 + static_cast<uint64_t>((it & 1) * static_cast<uint32_t>(p.a_buf_bytes >> 4));
+                const uint32_t d = tmem + static_cast<uint32_t>(p.adj_tcol);
+                for (int s = 0; s < p.ks1; ++s) {
+                    const int ksteps = min(4, p.k1steps - 4 * s);
+                    for (int j = 0; j < ksteps; ++j)
+                        umma_bf16(d, a_desc + static_cast<uint64_t>(s * (kPanelBytes >> 4)) + 2 * j,
+                                  adj_b_desc + static_cast<uint64_t>(s * (kAdjSlabBytes >> 4)) + 2 * j, adj_idesc, (s > 0 || j > 0) ? 1u : 0u);
+                }
+                umma_commit(&bars->adj_full);
+                umma_commit(&bars->adj_done[it & 1]);
+            }
+            __syncwarp();
+        };
         for (int it = 0; it < my_tiles; ++it) {
             for (int j = 0; j < p.nc; ++j) {
                 const int cg = it * p.nc + j;
@@ -226,7 +259,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                     const int ksteps = min(4, (p.hcw[j] >> 4) - 4 * s);
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 0);
                     mbar_wait(&bars->h_ready[b][s], static_cast<uint32_t>(cg >> 1) & 1);
-                    if (j == 0 && s == 0) mbar_wait(&bars->acc2_free, (static_cast<uint32_t>(it) & 1) ^ 1);
+                    if (j == 0 && s == 0) {
+                        mbar_wait(&bars->acc2_free, (static_cast<uint32_t>(it) & 1) ^ 1);
+                        if (p.fuse_adj && it > 0) issue_adj(it - 1);      // the previous tile's z is complete: adjust goes first
+                    }
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 1);
                     const uint32_t at = acc1 + static_cast<uint32_t>(64 * s);     // K=16 step u of the chunk lives at column 16 u
                     const uint32_t first_acc = (j == 0 && s == 0) ? 0u : 1u;
@@ -254,6 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                 }
             }
         }
+        if (p.fuse_adj && my_tiles > 0) issue_adj(my_tiles - 1);
     } else if (warp == kTileWarp) {
         // ============================================================ y-tile loads / z-tile stores (same buffers)
         auto load_a = [&](int it) {
@@ -267,19 +304,28 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             __syncwarp();
         };
         if (lane == 0) tma_prefetch_desc(&p.tmap_y);
+        if (p.fuse_adj && lane == 0) {
+            mbar_arrive_expect_tx(&bars->adj_w_full, static_cast<uint32_t>(p.ks1 * kAdjSlabBytes));
+            bulk_g2s(wadj_s, p.wadj, static_cast<uint32_t>(p.ks1 * kAdjSlabBytes), &bars->adj_w_full);
+        }
         if (my_tiles > 0) load_a(0);
         if (my_tiles > 1) load_a(1);
         for (int it = 0; it < my_tiles; ++it) {
             const int ab = it & 1;
             const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
-            mbar_wait(&bars->z_ready[ab], static_cast<uint32_t>(it >> 1) & 1);
-            if (lane == 0) {        // bulk-group bookkeeping is per thread: the same lane stores and waits
-                for (int pn = 0; pn < p.ks1; ++pn)
-                    tma_store_2d_box(&p.tmap_z, a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, pn * 64, m0);
-                bulk_commit_group();
-                bulk_wait_group_read0();
+            if (p.fuse_adj) {
+                // z only feeds the fused adjust conv: nothing is stored; the buffer is free once the adjust MMAs have read it
+                mbar_wait(&bars->adj_done[ab], static_cast<uint32_t>(it >> 1) & 1);
+            } else {
+                mbar_wait(&bars->z_ready[ab], static_cast<uint32_t>(it >> 1) & 1);
+                if (lane == 0) {        // bulk-group bookkeeping is per thread: the same lane stores and waits
+                    for (int pn = 0; pn < p.ks1; ++pn)
+                        tma_store_2d_box(&p.tmap_z, a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, pn * 64, m0);
+                    bulk_commit_group();
+                    bulk_wait_group_read0();
+                }
+                __syncwarp();
             }
-            __syncwarp();
             if (it + 2 < my_tiles) load_a(it + 2);                    // the buffer is free again: fetch the tile after next
         }
         if (lane == 0) bulk_wait_group0();
@@ -411,6 +457,46 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             if (tr) trace_ev<TRACE>(p.trace, 2, it, 16, 2);
         };
 
+        // ---- fused adjust: 32 new slab columns = LReLU(acc + bias), stored at the tile's token rows, + their row statistics
+        auto epi3 = [&](int it) {
+            const int row = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128 + r_in_tile;
+            mbar_wait(&bars->adj_full, static_cast<uint32_t>(it) & 1);
+            tc_fence_after_sync();
+            if (grp < 2) {
+                uint32_t raw[16];
+                tmem_ld16(tmem + lane_off + static_cast<uint32_t>(p.adj_tcol + 16 * grp), raw);
+                tmem_ld_wait();
+                float st = 0.f, sq = 0.f;
+                uint32_t pk[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float v0 = __uint_as_float(raw[2 * e]) + __ldg(p.bias_adj + 16 * grp + 2 * e);
+                    float v1 = __uint_as_float(raw[2 * e + 1]) + __ldg(p.bias_adj + 16 * grp + 2 * e + 1);
+                    v0 = v0 > 0.f ? v0 : v0 * p.adj_slope;
+                    v1 = v1 > 0.f ? v1 : v1 * p.adj_slope;
+                    st += v0 + v1;
+                    sq = fmaf(v0, v0, fmaf(v1, v1, sq));
+                    pk[e] = pack_bf16x2(v0, v1);
+                }
+                s_adj_stat[grp * 128 + r_in_tile] = f2(st, sq);
+                if (row < p.M) {
+                    // the slab slice starts at an 8-byte aligned column (C_k * 2 bytes): four 8-byte stores per 16 columns
+                    uint2* dst = reinterpret_cast<uint2*>(p.adj_out + static_cast<long long>(row) * p.ld_adj + p.adj_col0 + 16 * grp);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dst[e] = make_uint2(pk[2 * e], pk[2 * e + 1]);
+                }
+            }
+            tc_fence_before_sync();
+            named_bar_sync(1 + quad, 128);
+            if (grp == 0 && row < p.M && p.adj_stats != nullptr) {
+                const float2 a = s_adj_stat[r_in_tile], b = s_adj_stat[128 + r_in_tile];
+                float2* so = p.adj_stats + static_cast<long long>(row) * p.adj_stats_stride + p.adj_stats_slot0;
+                so[0] = f2(a.x + b.x, a.y + b.y);
+                so[1] = f2(0.f, 0.f);
+            }
+            named_bar_sync(1 + quad, 128);                            // s_adj_stat is reused by the next tile
+        };
+
         // task order mirrors the MMA streams: chunk 0 of tile it+1 is turned around BEFORE the last epilogue of tile it
         // (fc1 runs ahead of fc2, so that chunk is ready while the last fc2 MMAs of tile it are still in flight)
         float rstd = 1.f, nrm = 0.f;
@@ -420,12 +506,14 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         }
         for (int it = 0; it < my_tiles; ++it) {
             for (int j = 1; j < p.nc; ++j) epi1(it, j, rstd, nrm);
+            if (p.fuse_adj && it > 0) epi3(it - 1);                   // its MMAs were issued right after epi2(it - 1)
             if (it + 1 < my_tiles) {
                 row_stats(it + 1, rstd, nrm);
                 epi1(it + 1, 0, rstd, nrm);
             }
             epi2(it);
         }
+        if (p.fuse_adj && my_tiles > 0) epi3(my_tiles - 1);
     }
 
     tc_fence_before_sync();
@@ -459,16 +547,25 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
         if (p.hcw[j] <= 0 || p.hcw[j] > p.hc || p.hcw[j] > 128 || (p.hcw[j] % 16) != 0 || p.hcw[j] * 128 > p.w1_slot_bytes)
             return ADSR_ERR_BAD_SHAPE;
     p.a_buf_bytes = p.ks1 * kPanelBytes;
+    if (p.fuse_adj) {
+        if (p.wadj == nullptr || p.bias_adj == nullptr || p.adj_out == nullptr || (p.adj_col0 % 4) || (p.ld_adj % 4) || p.adj_tcol % 16 ||
+            p.adj_tcol < p.acc1_col[1] + p.hc || p.adj_tcol + 32 > 512 || (reinterpret_cast<uintptr_t>(p.wadj) & 15) ||
+            (reinterpret_cast<uintptr_t>(p.adj_out) & 7))
+            return ADSR_ERR_BAD_SHAPE;
+        if (p.adj_stats != nullptr && p.adj_stats_slot0 + 2 > p.adj_stats_stride) return ADSR_ERR_BAD_SHAPE;
+    }
     const int smem_bytes = 2 * p.a_buf_bytes + p.w1_slots * p.w1_slot_bytes + p.w2_slots * p.w2_slot_bytes + kConstBytes +
-                           static_cast<int>(sizeof(MlpBarriers));
+                           (p.fuse_adj ? p.ks1 * kAdjSlabBytes + 2 * 128 * 8 : 0) + static_cast<int>(sizeof(MlpBarriers));
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
-    if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(z) & 15) || (ldy % 8) || (ldz % 8) ||
+    if ((reinterpret_cast<uintptr_t>(y) & 15) || (!p.fuse_adj && ((reinterpret_cast<uintptr_t>(z) & 15) || (ldz % 8))) || (ldy % 8) ||
         (reinterpret_cast<uintptr_t>(p.w1p) & 15) || (reinterpret_cast<uintptr_t>(p.w2p) & 15))
         return ADSR_ERR_BAD_ALIGN;
     int st = encode_tmap_rows_bf16(&p.tmap_y, y, p.M, p.C, ldy);
     if (st != ADSR_OK) return st;
-    st = encode_tmap_rows_bf16(&p.tmap_z, z, p.M, p.C, ldz);
-    if (st != ADSR_OK) return st;
+    if (!p.fuse_adj) {
+        st = encode_tmap_rows_bf16(&p.tmap_z, z, p.M, p.C, ldz);
+        if (st != ADSR_OK) return st;
+    }
     p.m_tiles = (p.M + 127) / 128;
     const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
     auto launch = [&](auto kernel) -> int {

@@ -28,6 +28,7 @@ from . import ops, pack
 from .pack import PackedWeight, round_up
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # src/drct.py:774
+_FUSED_ADJUST = os.environ.get("ADSR_FUSED_ADJUST", "1") != "0"  # A/B switch: 0 = adjust convs as separate GEMMs
 _FUSED_ATTN = os.environ.get("ADSR_FUSED_ATTN", "1") != "0"    # A/B switch for profiling: 0 = separate qkv / attention / proj kernels
 
 
@@ -196,8 +197,18 @@ class DRCT(nn.Module):
                 b.attn_mode = ops.swin_attn_mode(b.dim, b.heads, b.hdp) if (b.ws == 8 and _FUSED_ATTN) else 0
                 b.attn = pack.pack_swin_attn(sw.attn.qkv.weight, sw.attn.qkv.bias, sw.norm1.weight, sw.norm1.bias, sw.norm1.eps,
                                              sw.attn.proj.weight, sw.attn.proj.bias, b.heads) if b.attn_mode else None
-                b.mlp = pack.pack_swin_mlp(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias, sw.norm2.eps,
-                                           sw.mlp.fc2.weight, sw.mlp.fc2.bias)
+                # the 32-channel adjust convs ride in the MLP kernel's last epilogue where its tiling leaves room (z is then never
+                # written); otherwise (and for adjust5) the adjust conv stays a GEMM of its own
+                b.mlp = None
+                if k < 4 and adj.out_channels == 32 and _FUSED_ADJUST:
+                    try:
+                        b.mlp = pack.pack_swin_mlp(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias, sw.norm2.eps,
+                                                   sw.mlp.fc2.weight, sw.mlp.fc2.bias, adj.weight, adj.bias)
+                    except ValueError:
+                        b.mlp = None
+                if b.mlp is None:
+                    b.mlp = pack.pack_swin_mlp(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias, sw.norm2.eps,
+                                               sw.mlp.fc2.weight, sw.mlp.fc2.bias)
                 b.adjust = pack.pack_gemm_weight(adj.weight, adj.bias, rows_kernel=(k == 4))
                 blocks.append(b)
             P["blocks"].append(blocks)
@@ -303,6 +314,10 @@ class DRCT(nn.Module):
                     ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0))
                 # ---- MLP half (src/drct.py:510, 185-189): norm2 + fc1 + GELU + fc2 + residual in ONE kernel, the hidden
                 #      activations never leave the SM
+                if b.mlp.wadj is not None:
+                    # ... and the adjust 1x1 conv (+LeakyReLU 0.2) into the slab slice (src/drct.py:389-393) in the same kernel
+                    ops.swin_mlp_adjust(y, C, b.mlp, slab, C, stats_in=(st_y, y_slots), stats_out=(st_slab, xs + 2 * k))
+                    continue
                 ops.swin_mlp(y, C, b.mlp, z, stats_in=(st_y, y_slots))
                 # ---- adjust 1x1 conv (+LeakyReLU 0.2) into the slab slice / 0.2*x5 + x  (src/drct.py:389-396)
                 if not b.last:

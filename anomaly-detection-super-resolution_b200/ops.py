@@ -82,6 +82,26 @@ def swin_mlp(y: torch.Tensor, c: int, pm, z: torch.Tensor, stats_in: tuple, m: O
     _count("swin_mlp", 4.0 * m * pm.C * pm.H, _t)
 
 
+def swin_mlp_adjust(y: torch.Tensor, c: int, pm, out: torch.Tensor, ocol0: int, stats_in: tuple, stats_out: Optional[tuple] = None,
+                    slope: float = 0.2, m: Optional[int] = None) -> None:
+    """out[:, ocol0:ocol0+32] = LReLU_slope(adjust(z)),  z = y + fc2(GELU(fc1(LayerNorm(y[:, :c]))))  -- the fused MLP kernel with
+    the RDG's adjust 1x1 conv in its last epilogue; z is never written.  `pm` from pack.pack_swin_mlp(..., adjust_w, adjust_b)."""
+    _cuda(y, "y")
+    _cuda(out, "out")
+    if pm.wadj is None:
+        raise ValueError("swin_mlp_adjust: weights were packed without the adjust conv")
+    m = y.shape[0] if m is None else m
+    si_t, si_n = stats_in
+    so_t, so_0 = stats_out if stats_out is not None else (None, 0)
+    _t = _begin()
+    check(lib().adsr_swin_mlp_adjust_bf16(ptr(y), y.stride(0), m, c, ptr(pm.w1), ptr(pm.w2), ptr(pm.bias1), ptr(pm.colsum1), ptr(pm.bias2),
+                                          pm.plan.data_ptr(), pm.plan.numel(), pm.ln_eps, ptr(si_t), si_n, si_t.shape[1],
+                                          ptr(pm.wadj), ptr(pm.bias_adj), slope, ptr(out), out.stride(0), ocol0, ptr(so_t), so_0,
+                                          so_t.shape[1] if so_t is not None else 0, _abi.num_sms(), stream_ptr()),
+          "adsr_swin_mlp_adjust_bf16")
+    _count("swin_mlp", 4.0 * m * pm.C * pm.H + 2.0 * m * pm.C * 32, _t)
+
+
 def swin_attn_mode(c: int, heads: int, hdp: int, allow_proj: bool = True) -> int:
     """What adsr_swin_attn_bf16 covers for this block shape: 2 = whole attention half, 1 = qkv + attention, 0 = nothing."""
     return int(lib().adsr_swin_attn_mode(c, heads, hdp, int(allow_proj)))

@@ -149,7 +149,7 @@ def pack_proj_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: 
 
 # ------------------------------------------------------------------------------------------------ fused Swin MLP
 _SMEM_LIMIT = 232448            # 227 KB of shared memory per CTA
-_MLP_FIXED_BYTES = (2 * 512 + 320) * 4 + 512   # bias1 / colsum1 / bias2 caches + barriers (swin_mlp.cu)
+_MLP_FIXED_BYTES = (2 * 640 + 320) * 4 + 512   # bias1 / colsum1 / bias2 caches + barriers (swin_mlp.cu)
 
 
 @dataclass
@@ -163,30 +163,38 @@ class PackedMlp:
     ln_eps: float
     C: int
     H: int
+    wadj: Optional[torch.Tensor] = None      # fused adjust conv: uint8 slabs [32 rows x 64 bf16] per K slab, 128-byte swizzle
+    bias_adj: Optional[torch.Tensor] = None  # fp32 [32]
 
 
-def swin_mlp_plan(c: int, h: int) -> dict:
+_ADJ_N = 32                     # output channels of the fusable adjust convs (gc of the RDG)
+
+
+def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
     """Static tiling of one fused MLP (swin_mlp.cu): hidden chunks of <= 128 columns (two fp32 chunk accumulators plus the
     fc2 accumulator must fit the 512 TMEM columns), the fc2 output issued in two pieces of >= 128 rows when it is wider
     than 255, and the shared memory left after the two y-tile buffers split between the fc1 and fc2 weight rings."""
     n2 = round_up(c, 16)
     k1steps = (c + 15) // 16
     ks1 = (c + 63) // 64
-    hc_max = min(128, ((512 - n2) // 2) // 16 * 16)
+    # TMEM: fc2 accumulator (n2) + two fc1 chunk accumulators (2 hc) [+ 32 columns of the fused adjust accumulator]
+    hc_max = min(128, ((512 - n2 - (_ADJ_N if fuse_adj else 0)) // 2) // 16 * 16)
     nc = (h + hc_max - 1) // hc_max
     hc = round_up((h + nc - 1) // nc, 16)
     widths = [hc] * (nc - 1) + [round_up(h - hc * (nc - 1), 16)]
-    if n2 >= 256:
+    s1 = round_up(hc * 128, 1024)
+    avail = _SMEM_LIMIT - 2 * ks1 * 16384 - _MLP_FIXED_BYTES - ((ks1 * _ADJ_N * 128 + 2048) if fuse_adj else 0)
+    # the fc2 N dimension goes out in one piece, or in two when it is wider than 255 -- or when one-piece ring slots would not
+    # leave room for two slots per ring (fused adjust takes shared memory for its resident weights)
+    if n2 >= 256 or avail < 2 * s1 + 2 * round_up(n2 * 128, 1024):
         p0 = round_up(n2 // 2, 16)
         pieces = [p0, n2 - p0]
     else:
         pieces = [n2]
-    s1 = round_up(hc * 128, 1024)
     s2 = round_up(max(pieces) * 128, 1024)
-    avail = _SMEM_LIMIT - 2 * ks1 * 16384 - _MLP_FIXED_BYTES
     # bytes per tile through each ring decide how the slots are shared out (at least 2 each)
     n1, n2s = 2, 2
-    if avail < n1 * s1 + n2s * s2 or nc > 8 or n2 > 320 or nc * hc > 512:
+    if avail < n1 * s1 + n2s * s2 or nc > 8 or n2 > 320 or nc * hc > 640:
         raise ValueError(f"fused MLP does not fit: C={c} H={h}")
     while True:
         grew = False
@@ -202,7 +210,7 @@ def swin_mlp_plan(c: int, h: int) -> dict:
         if not grew:
             break
     return dict(ks1=ks1, k1steps=k1steps, nc=nc, hc=hc, n2=n2, widths=widths, pieces=pieces, w1_slots=n1, w1_slot_bytes=s1,
-                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(n2, n2 + hc))
+                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(n2, n2 + hc), adj_tcol=n2 + 2 * hc)
 
 
 def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
@@ -215,14 +223,20 @@ def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
     return torch.gather(t, 1, src).contiguous().view(torch.uint8).reshape(-1)
 
 
-def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b) -> PackedMlp:
+def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, adjust_w=None, adjust_b=None) -> PackedMlp:
     """norm2 + fc1 + GELU + fc2 of one Swin block (src/drct.py:438-441, 173-190) for adsr_swin_mlp_bf16: gamma folded into
-    fc1 (pack_ln_gemm_weight's algebra), the 0.5 of GELU folded into fc2 (exact in bf16)."""
+    fc1 (pack_ln_gemm_weight's algebra), the 0.5 of GELU folded into fc2 (exact in bf16).  With adjust_w [32, C(,1,1)] the
+    RDG's adjust 1x1 conv is packed along for adsr_swin_mlp_adjust_bf16 (raises ValueError if the tiling does not fit)."""
     w1 = fc1_w.detach().float()
     w2 = fc2_w.detach().float() * 0.5
     h, c = w1.shape
     dev = w1.device
-    pl = swin_mlp_plan(c, h)
+    fuse_adj = adjust_w is not None
+    if fuse_adj and adjust_w.shape[0] != _ADJ_N:
+        raise ValueError("only 32-channel adjust convs can be fused")
+    pl = swin_mlp_plan(c, h, fuse_adj)
+    if fuse_adj and pl["adj_tcol"] + _ADJ_N > 512:
+        raise ValueError(f"fused adjust does not fit the tensor memory: C={c} H={h}")
     hc, nc, n2, ks1 = pl["hc"], pl["nc"], pl["n2"], pl["ks1"]
     w1g = torch.zeros(nc * hc, ks1 * 64, device=dev)
     w1g[:h, :c] = w1 * gamma.detach().float()[None, :]
@@ -250,9 +264,15 @@ def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b) -> PackedMlp:
                 dcol += rows
     pieces = pl["pieces"] + [0] * (2 - len(pl["pieces"]))
     plan = [ks1, pl["k1steps"], nc, hc, n2, pl["acc1_col"][0], pl["acc1_col"][1], len(pl["pieces"]), pieces[0], pieces[1],
-            pl["w1_slots"], pl["w1_slot_bytes"], pl["w2_slots"], pl["w2_slot_bytes"]] + pl["widths"] + [0] * (8 - nc)
+            pl["w1_slots"], pl["w1_slot_bytes"], pl["w2_slots"], pl["w2_slot_bytes"]] + pl["widths"] + [0] * (8 - nc) + [pl["adj_tcol"]]
+    wadj = bias_adj = None
+    if fuse_adj:
+        wa = torch.zeros(_ADJ_N, ks1 * 64, device=dev)
+        wa[:, :c] = adjust_w.detach().float().reshape(_ADJ_N, -1)
+        wadj = torch.cat([_swizzle_slab(wa[:, 64 * s:64 * s + 64].contiguous()) for s in range(ks1)]).contiguous()
+        bias_adj = (adjust_b.detach().float() if adjust_b is not None else torch.zeros(_ADJ_N, device=dev)).contiguous()
     return PackedMlp(torch.cat(slabs1).contiguous(), torch.cat(slabs2).contiguous(), bias1, colsum1, bias2,
-                     torch.tensor(plan, dtype=torch.int32), float(eps), c, h)
+                     torch.tensor(plan, dtype=torch.int32), float(eps), c, h, wadj, bias_adj)
 
 
 # ------------------------------------------------------------------------------------------------ fused attention half

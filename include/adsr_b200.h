@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 6
+#define ADSR_ABI_VERSION 7
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -77,6 +77,20 @@ int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C,
                        const int32_t* plan, int plan_len, float ln_eps,
                        const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
                        void* z, int64_t ldz, int num_sms, void* stream);
+
+/* Same kernel with the adjust 1x1 conv of the RDG fused in (src/drct.py:389-393: x_k = LReLU_0.2(adjust_k(swin_k(...))) appended to
+ * the dense feature slab): out[:, ocol0 + n] = LReLU(z W_adj^T + b_adj)[n] for the 32 new channels, where z is the MLP result above.
+ * z itself is NOT written (nothing else reads it).  wadj_packed / bias_adj and the extended plan (..., adj_tmem_col) come from
+ * pack.pack_swin_mlp(..., adjust_w, adjust_b); stats_out receives the per-row (sum, sumsq) of the 32 new columns in slot
+ * stats_out_slot0 (slot0 + 1 is zeroed), for the LayerNorm folds of the following blocks. */
+int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int C,
+                              const void* w1_packed, const void* w2_packed,
+                              const float* bias1, const float* colsum1, const float* bias2,
+                              const int32_t* plan, int plan_len, float ln_eps,
+                              const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
+                              const void* wadj_packed, const float* bias_adj, float slope,
+                              void* out, int64_t ldo, int ocol0,
+                              float* stats_out, int stats_out_slot0, int stats_out_stride, int num_sms, void* stream);
 
 /* ---- fused attention half of a Swin block for 8 x 8 windows ------------------------------------------------------
  *   y = x + proj( WindowAttention( LayerNorm(x) ) )

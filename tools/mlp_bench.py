@@ -30,3 +30,18 @@ for (C, H) in shapes:
     best, avg = timeit(lambda: ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2)))
     fl = 4.0 * M * C * H
     print(f"swin_mlp C={C} H={H}: {best*1e3:8.1f} us (avg {avg*1e3:8.1f})  {fl/best/1e9:7.1f} TFLOP/s  {4.0*M*C/best/1e6:7.1f} GB/s(y+z)")
+    # the same with the RDG's adjust 1x1 conv fused in (z never written) next to MLP + separate adjust GEMM
+    wa, ba = torch.randn(32, C, device=dev) * 0.05, torch.randn(32, device=dev)
+    try:
+        pma = pack.pack_swin_mlp(torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
+                                 torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev), wa, ba)
+    except ValueError:
+        continue
+    padj = pack.pack_gemm_weight(wa, ba)
+    slab = torch.zeros(M, 320, device=dev, dtype=torch.bfloat16); st_s = torch.zeros(M, 12, 2, device=dev)
+    bf, af = timeit(lambda: ops.swin_mlp_adjust(y, C, pma, slab, C, stats_in=(stats, 2), stats_out=(st_s, 2)))
+    def sep():
+        ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2))
+        ops.tc_gemm(z, C, padj, slab, act=ops.ACT_LRELU, slope=0.2, ocol0=C, n_store=32, stats_out=(st_s, 2))
+    bs, _ = timeit(sep)
+    print(f"   + adjust: fused {bf*1e3:8.1f} us (avg {af*1e3:8.1f})   separate MLP + adjust GEMM {bs*1e3:8.1f} us   plan {pma.plan.tolist()[:14]}")
