@@ -39,6 +39,7 @@ constexpr int kThreads = 20 * 32;
 constexpr int kPanelBytes = 128 * 128;
 constexpr int kMaxSlots = 10;
 constexpr int kSmemLimit = 232448;
+constexpr int kIdentBytes = 16 * 128;         // fuse_proj: identity operand slab (16 rows x 64 bf16, 128-byte swizzle)
 
 struct __align__(8) AttnBlockBarriers {
     uint64_t w_full[kMaxSlots], w_empty[kMaxSlots];
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
     uint8_t* v_buf = k_buf + op_bytes;                                 // [pan panels] v of the current head (MN-major B operand of P V)
     uint8_t* ring = v_buf + op_bytes;                                  // qkv slabs: w_slots x w_slot_bytes
     uint8_t* pring = ring + p.w_slots * p.w_slot_bytes;                // proj slabs: p_slots x p_slot_bytes
-    float* s_bq = reinterpret_cast<float*>(pring + p.p_slots * p.p_slot_bytes);     // [nqkv] folded qkv bias, per-head q|k|v order
+    uint8_t* ident_s = pring + p.p_slots * p.p_slot_bytes;             // FUSE: [16 x 64] bf16 operand slab holding the 16 x 16 identity
+    float* s_bq = reinterpret_cast<float*>(ident_s + (FUSE ? kIdentBytes : 0));     // [nqkv] folded qkv bias, per-head q|k|v order
     float* s_cq = s_bq + nqkv;                                         // [nqkv] column sums of the gamma-folded weights
     float* s_bp = s_cq + nqkv;                                         // [cp] proj bias
     float* s_bias = s_bp + p.cp;                                       // [nH][232] rel-pos table * log2(e)
@@ -125,6 +127,16 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
     for (int i = threadIdx.x; i < 225 * p.nH; i += kThreads) {
         const int h = i % p.nH, e = i / p.nH;
         s_bias[h * 232 + e] = __ldg(p.table + i) * 1.4426950408889634f;
+    }
+    if (FUSE) {
+        // B operand of the shortcut MMAs: row n of the K-major slab is the unit vector e_n (n < 16), i.e. out[:, n] = A[:, n]
+        for (int i = threadIdx.x; i < kIdentBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(ident_s)[i] = 0u;
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            const int n = threadIdx.x;
+            *reinterpret_cast<uint16_t*>(ident_s + n * 128 + (((n >> 3) ^ (n & 7)) << 4) + (n & 7) * 2) = 0x3F80;   // bf16 1.0
+        }
+        fence_proxy_async_smem();
     }
     if (warp == kMmaWarp && lane == 0) {
         for (int s = 0; s < kMaxSlots; ++s) {
@@ -364,8 +376,18 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     tr_ev<TRACE>(p.trace, 0, it, h, 1);
                     ensure_o(g);
                     if (h == 0) {
+                        // the accumulator starts as the shortcut: Y[:, 16 g .. 16 g + 15] = x[:, same columns] * I (x tile still
+                        // resident; bf16 values enter the fp32 accumulator exactly), the proj MMAs of every head accumulate on top
                         mbar_wait(&bars->proj_free, (static_cast<uint32_t>(it) & 1) ^ 1);
                         tc_fence_after_sync();
+                        if (elect_one_sync()) {
+                            const uint64_t idesc_b = umma_desc_k_sw128(smem_u32(ident_s));
+                            const uint32_t idesc16 = idesc_m128(16u, 0);
+                            for (int gcol = 0; gcol < p.cp / 16; ++gcol)
+                                umma_bf16(tmem + static_cast<uint32_t>(16 * gcol),
+                                          x_desc + static_cast<uint64_t>((gcol >> 2) * (kPanelBytes >> 4) + (gcol & 3) * 2), idesc_b, idesc16, 0u);
+                        }
+                        __syncwarp();
                     }
                     uint32_t dcol = 0;
                     for (int pc = 0; pc < p.n_pp; ++pc) {
@@ -375,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                             const uint64_t bdesc = pring_desc + static_cast<uint64_t>(static_cast<uint32_t>(pslot) * pslot_units);
                             const uint32_t idesc = idesc_m128(static_cast<uint32_t>(p.pp_rows[pc]), 0);
                             for (int u = 0; u < uq; ++u)
-                                umma_bf16_ts(tmem + dcol, t_o + static_cast<uint32_t>(16 * u), bdesc + 2 * u, idesc, (h > 0 || u > 0) ? 1u : 0u);
+                                umma_bf16_ts(tmem + dcol, t_o + static_cast<uint32_t>(16 * u), bdesc + 2 * u, idesc, 1u);
                             umma_commit(&bars->p_empty[pslot]);
                             if (h == p.nH - 1 && pc == p.n_pp - 1) umma_commit(&bars->proj_full);
                         }
@@ -658,89 +680,64 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
             }
 
             if (FUSE) {
-                // ---- y = proj + bias + shortcut -> original token rows; (sum, sumsq) of the row for norm2.
-                // 64-column chunks are staged in the idle k / v panels so that every global access is a coalesced 128-byte
-                // row piece: the shortcut chunk is fetched into the panel by cp.async (two chunks ahead, L2 hits), the epilogue
-                // adds bias + accumulator in place, then the same four warps copy the panel rows out.  A quadrant (4 warps,
-                // 32 tile rows) only touches its own panel rows, so quadrant-wide named barriers are all the sync needed.
+                // ---- y = accumulator (shortcut + proj) + bias -> original token rows; (sum, sumsq) of the row for norm2.
+                // 64-column chunks are staged in the idle k / v panels so that every global access is a coalesced 128-byte row
+                // piece: the epilogue writes its 16 columns, then the quadrant's four warps copy the 32 panel rows out.  A quadrant
+                // only touches its own panel rows, so quadrant-wide named barriers are all the sync needed.
                 const int nch = (p.cp + 63) >> 6;
                 const uint32_t panel0 = smem_u32(k_buf), panel1 = smem_u32(v_buf);
-                named_bar_sync(1 + quad, 128);                           // s_tok of the quadrant's rows is visible
-                auto issue_res = [&](int c) {
-                    const uint32_t pbase = (c & 1) ? panel1 : panel0;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int id = t128 + 128 * i;
-                        const int rq = quad * 32 + (id >> 3), j = id & 7;
-                        const int col = 64 * c + 8 * j;
-                        int valid = (p.C - col) * 2;
-                        valid = valid < 0 ? 0 : (valid > 16 ? 16 : valid);
-                        const __nv_bfloat16* src = p.x + static_cast<long long>(s_tok[mb * 128 + rq]) * p.ldx + (valid > 0 ? col : 0);
-                        cp_async16_zfill(pbase + static_cast<uint32_t>(rq * 128) + static_cast<uint32_t>(((j ^ (rq & 7)) << 4)), src, valid);
-                    }
-                    cp_async_commit_();
-                };
-                issue_res(0);
-                if (nch > 1) issue_res(1);
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, 8, 0);
                 mbar_wait(&bars->proj_full, static_cast<uint32_t>(it) & 1);
                 tc_fence_after_sync();
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, 8, 1);
                 float2 st = f2_(0.f, 0.f), sq = f2_(0.f, 0.f);
-                for (int c = 0; c < nch; ++c) {
-                    const uint32_t pbase = (c & 1) ? panel1 : panel0;
-                    const int col0 = 64 * c + 16 * grp;
-                    const bool active = col0 < p.cp;
-                    uint32_t raw[16];
-                    if (active) tmem_ld16(t_base + static_cast<uint32_t>(col0), raw);
-                    if (c + 1 < nch) asm volatile("cp.async.wait_group 1;" ::: "memory");
-                    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    named_bar_sync(1 + quad, 128);                       // the quadrant's shortcut chunk has landed
-                    if (active) {
-                        tmem_ld_wait();
-                        const uint32_t rowa = pbase + static_cast<uint32_t>(r * 128);
+                for (int c2 = 0; c2 < nch; c2 += 2) {                   // two 64-column chunks (= both panels) per barrier round
 #pragma unroll
-                        for (int o = 0; o < 2; ++o) {
-                            const uint32_t sa = rowa + static_cast<uint32_t>((((2 * grp + o) ^ rsw) << 4));
-                            uint32_t rw[4];
-                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(sa));
-                            const float4 b0 = *reinterpret_cast<const float4*>(s_bp + col0 + 8 * o);
-                            const float4 b1 = *reinterpret_cast<const float4*>(s_bp + col0 + 8 * o + 4);
-                            const uint32_t* a8 = &raw[8 * o];
-                            const float2 v0 = __fadd2_rn(__fadd2_rn(f2_(__uint_as_float(a8[0]), __uint_as_float(a8[1])), f2_(b0.x, b0.y)),
-                                                         f2_(bf16_lo(rw[0]), bf16_hi(rw[0])));
-                            const float2 v1 = __fadd2_rn(__fadd2_rn(f2_(__uint_as_float(a8[2]), __uint_as_float(a8[3])), f2_(b0.z, b0.w)),
-                                                         f2_(bf16_lo(rw[1]), bf16_hi(rw[1])));
-                            const float2 v2 = __fadd2_rn(__fadd2_rn(f2_(__uint_as_float(a8[4]), __uint_as_float(a8[5])), f2_(b1.x, b1.y)),
-                                                         f2_(bf16_lo(rw[2]), bf16_hi(rw[2])));
-                            const float2 v3 = __fadd2_rn(__fadd2_rn(f2_(__uint_as_float(a8[6]), __uint_as_float(a8[7])), f2_(b1.z, b1.w)),
-                                                         f2_(bf16_lo(rw[3]), bf16_hi(rw[3])));
-                            // columns >= C: zero weight rows, zero bias, zero-filled shortcut -> exact zeros, no effect on the sums
-                            st = __fadd2_rn(st, __fadd2_rn(__fadd2_rn(v0, v1), __fadd2_rn(v2, v3)));
-                            sq = __ffma2_rn(v0, v0, sq);
-                            sq = __ffma2_rn(v1, v1, sq);
-                            sq = __ffma2_rn(v2, v2, sq);
-                            sq = __ffma2_rn(v3, v3, sq);
-                            st_shared_v4(sa, pack_bf16x2(v0.x, v0.y), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v2.x, v2.y), pack_bf16x2(v3.x, v3.y));
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int col0 = 64 * (c2 + pp) + 16 * grp;
+                        if (col0 < p.cp) {
+                            uint32_t raw[16];
+                            tmem_ld16(t_base + static_cast<uint32_t>(col0), raw);
+                            tmem_ld_wait();
+                            const uint32_t rowa = (pp ? panel1 : panel0) + static_cast<uint32_t>(r * 128);
+#pragma unroll
+                            for (int o = 0; o < 2; ++o) {
+                                const float4 b0 = *reinterpret_cast<const float4*>(s_bp + col0 + 8 * o);
+                                const float4 b1 = *reinterpret_cast<const float4*>(s_bp + col0 + 8 * o + 4);
+                                const uint32_t* a8 = &raw[8 * o];
+                                const float2 v0 = __fadd2_rn(f2_(__uint_as_float(a8[0]), __uint_as_float(a8[1])), f2_(b0.x, b0.y));
+                                const float2 v1 = __fadd2_rn(f2_(__uint_as_float(a8[2]), __uint_as_float(a8[3])), f2_(b0.z, b0.w));
+                                const float2 v2 = __fadd2_rn(f2_(__uint_as_float(a8[4]), __uint_as_float(a8[5])), f2_(b1.x, b1.y));
+                                const float2 v3 = __fadd2_rn(f2_(__uint_as_float(a8[6]), __uint_as_float(a8[7])), f2_(b1.z, b1.w));
+                                // columns >= C: zero weight rows, zero bias, zero-filled x -> exact zeros, no effect on the sums
+                                st = __fadd2_rn(st, __fadd2_rn(__fadd2_rn(v0, v1), __fadd2_rn(v2, v3)));
+                                sq = __ffma2_rn(v0, v0, sq);
+                                sq = __ffma2_rn(v1, v1, sq);
+                                sq = __ffma2_rn(v2, v2, sq);
+                                sq = __ffma2_rn(v3, v3, sq);
+                                st_shared_v4(rowa + static_cast<uint32_t>((((2 * grp + o) ^ rsw) << 4)), pack_bf16x2(v0.x, v0.y),
+                                             pack_bf16x2(v1.x, v1.y), pack_bf16x2(v2.x, v2.y), pack_bf16x2(v3.x, v3.y));
+                            }
                         }
                     }
-                    if (c == nch - 1) {                                  // the accumulator has been read: the regions may take q|k|v again
+                    if (c2 + 2 >= nch) {                                 // the accumulator has been read: the next tile may start it over
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars->proj_free);
                     }
-                    named_bar_sync(1 + quad, 128);                       // the quadrant's y chunk is complete
+                    named_bar_sync(1 + quad, 128);                       // the quadrant's y chunks (and s_tok) are complete
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int id = t128 + 128 * i;
+                    for (int i = 0; i < 4; ++i) {
+                        const int pp = i >> 1;
+                        const int id = t128 + 128 * (i & 1);
                         const int rq = quad * 32 + (id >> 3), j = id & 7;
-                        const int col = 64 * c + 8 * j;
+                        const int col = 64 * (c2 + pp) + 8 * j;
                         const int nvalid = p.C - col;
                         if (nvalid > 0) {
                             uint4 val;
                             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                                          : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                                         : "r"(pbase + static_cast<uint32_t>(rq * 128) + static_cast<uint32_t>(((j ^ (rq & 7)) << 4))));
+                                         : "r"((pp ? panel1 : panel0) + static_cast<uint32_t>(rq * 128) + static_cast<uint32_t>(((j ^ (rq & 7)) << 4))));
                             __nv_bfloat16* dst = p.out + static_cast<long long>(s_tok[mb * 128 + rq]) * p.ldo + col;
                             if (nvalid >= 8) {
                                 *reinterpret_cast<uint4*>(dst) = val;
@@ -752,10 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                             }
                         }
                     }
-                    if (c + 2 < nch) {
-                        named_bar_sync(1 + quad, 128);                   // the panel has been copied out: refill it
-                        issue_res(c + 2);
-                    }
+                    if (c2 + 2 < nch) named_bar_sync(1 + quad, 128);     // copied out: the next round may overwrite the panels
                 }
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, 8, 2);
                 if (p.stats_out != nullptr) {
@@ -780,8 +774,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
     }
 }
 
-int fixed_smem_bytes(int nH, int hdp, int cp) {
-    return (2 * nH * 3 * hdp + cp + nH * 232) * 4 + 256 * 4 + 2 * 512 * 4 + static_cast<int>(sizeof(AttnBlockBarriers)) + 64;
+int fixed_smem_bytes(int nH, int hdp, int cp) {       // kIdentBytes is only used with fuse_proj; reserving it always keeps this simple
+    return kIdentBytes + (2 * nH * 3 * hdp + cp + nH * 232) * 4 + 256 * 4 + 2 * 512 * 4 + static_cast<int>(sizeof(AttnBlockBarriers)) + 64;
 }
 
 int round16(int v) { return (v + 15) / 16 * 16; }
