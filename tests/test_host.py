@@ -63,6 +63,63 @@ def test_pack_qkv_head_padding():
     assert pw.bias[(heads + 1) * 64 + 53] == 0
 
 
+def test_pack_swin_attn_layout():
+    """Fused attention half: qkv slabs per (head, K slab) with rows q_h | k_h | v_h (gamma folded, pad rows zero), the folded
+    bias / column sums in the same row order, proj slabs per head with K = the head's channels."""
+    pack = importlib.import_module(PKG + ".pack")
+    torch.manual_seed(1)
+    c, heads = 212, 4                                    # head_dim 53 -> 64, 4 K slabs
+    hd, hdp, ks, cp = 53, 64, 4, 224
+    qkv_w, qkv_b = torch.randn(3 * c, c), torch.randn(3 * c)
+    gamma, beta = torch.rand(c) + 0.5, torch.randn(c)
+    proj_w, proj_b = torch.randn(c, c), torch.randn(c)
+    pa = pack.pack_swin_attn(qkv_w, qkv_b, gamma, beta, 1e-5, proj_w, proj_b, heads)
+    assert (pa.C, pa.heads, pa.hd, pa.hdp) == (c, heads, hd, hdp)
+    img = pa.w1.view(torch.bfloat16).view(heads, ks, 3 * hdp, 8, 8)          # [head, K slab, row, chunk position, element]
+    wg = (qkv_w * gamma[None, :]).to(torch.bfloat16)
+    for (h, which, d, k) in [(0, 0, 0, 0), (1, 1, 52, 200), (3, 2, 17, 64), (2, 0, 30, 211)]:
+        row = which * hdp + d
+        s_, kk = divmod(k, 64)
+        chunk, e = divmod(kk, 8)
+        assert img[h, s_, row, chunk ^ (row % 8), e] == wg[which * c + h * hd + d, k]
+    assert img[:, :, hd:hdp].abs().sum() == 0 and img[:, :, hdp + hd:2 * hdp].abs().sum() == 0      # head padding rows
+    t = qkv_w @ beta + qkv_b
+    assert torch.allclose(pa.bias_qkv.view(heads, 3, hdp)[1, 2, 5], t[2 * c + 1 * hd + 5])
+    assert pa.bias_qkv.view(heads, 3, hdp)[:, :, hd:].abs().sum() == 0
+    cs = wg.float().sum(1)
+    assert torch.allclose(pa.colsum_qkv.view(heads, 3, hdp)[3, 0, 7], cs[3 * hd + 7], rtol=1e-5)
+    pimg = pa.w2.view(torch.bfloat16).view(heads, cp, 8, 8)
+    pw = proj_w.to(torch.bfloat16)
+    for (h, n, d) in [(0, 0, 0), (2, 211, 52), (3, 100, 9)]:
+        chunk, e = divmod(d, 8)
+        assert pimg[h, n, chunk ^ (n % 8), e] == pw[n, h * hd + d]
+    assert pimg[:, c:].abs().sum() == 0 and torch.equal(pa.bias_p[:c], proj_b) and pa.bias_p[c:].abs().sum() == 0
+
+
+def test_swin_mlp_plans_fit_the_sm():
+    """Static tilings of the fused MLP (with and without the fused adjust conv) for the DRCT-L widths: TMEM columns, shared
+    memory and chunk widths stay inside the limits the kernel checks."""
+    pack = importlib.import_module(PKG + ".pack")
+    for c, h, fuse_ok in [(180, 360, True), (212, 424, True), (244, 488, True), (276, 276, False), (308, 308, False)]:
+        for fuse in (False, True):
+            try:
+                pl = pack.swin_mlp_plan(c, h, fuse)
+            except ValueError:
+                assert fuse and not fuse_ok, (c, h, fuse)
+                continue
+            assert not fuse or fuse_ok
+            n2, hc, nc = pl["n2"], pl["hc"], pl["nc"]
+            assert n2 == (c + 15) // 16 * 16 and sum(pl["widths"]) >= h and all(w % 16 == 0 and w <= hc for w in pl["widths"])
+            assert n2 + 2 * hc + (32 if fuse else 0) <= 512 and pl["adj_tcol"] == n2 + 2 * hc
+            assert sum(pl["pieces"]) == n2 and all(16 <= r <= 256 and r % 16 == 0 for r in pl["pieces"])
+            smem = 2 * pl["ks1"] * 16384 + pl["w1_slots"] * pl["w1_slot_bytes"] + pl["w2_slots"] * pl["w2_slot_bytes"] + \
+                pack._MLP_FIXED_BYTES + ((pl["ks1"] * 4096 + 2048) if fuse else 0)
+            assert smem <= 232448 and pl["w1_slots"] >= 2 and pl["w2_slots"] >= 2 and nc * hc <= 640
+    pm = pack.pack_swin_mlp(torch.randn(360, 180), torch.randn(360), torch.ones(180), torch.zeros(180), 1e-5, torch.randn(180, 360),
+                            torch.randn(180), torch.randn(32, 180, 1, 1), torch.randn(32))
+    assert pm.wadj.numel() == 3 * 32 * 128 and pm.bias_adj.numel() == 32 and pm.plan.numel() == 23
+
+
 def test_state_dict_matches_reference_layout(pkg):
     from oracle import drct_oracle as O
     drct = importlib.import_module(PKG + ".drct")
