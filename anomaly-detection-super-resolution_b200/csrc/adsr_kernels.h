@@ -132,6 +132,7 @@ struct SwinAttnParams {
     int qkv_pieces, qp_rows[4];  // a qkv slab is issued in N pieces of <= 128 rows (one ring slot each)
     int rsz, nreg;            // TMEM: columns per head region, number of regions (2 = next head's q|k|v runs one head ahead)
     int col_o;                // TMEM column of O (fuse_proj: behind the region; else O overlays the region's q columns)
+    int col_acc;              // fuse_proj with spare TMEM: separate q|k|v accumulator columns, else -1 (accumulators = the region)
     int w_slots, w_slot_bytes;   // qkv weight ring
     int p_slots, p_slot_bytes;   // proj weight ring (fuse_proj)
     long long* trace;         // optional clock64 timeline of CTA 0 (tools/attn_trace.py), else nullptr

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         };
         auto qkv_begin = [&](int g) {
             q_g = g; q_step = 0; q_s = 0; q_pc = 0;
-            q_dst = region_of(g);
+            q_dst = (FUSE && p.col_acc >= 0) ? tmem + static_cast<uint32_t>(p.col_acc) : region_of(g);
             q_full_idx = (!FUSE && p.nreg == 2) ? static_cast<uint32_t>(g & 1) : 0u;
             q_last_head = (g % p.nH) == p.nH - 1;
         };
@@ -365,11 +365,16 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     mbar_wait(&bars->qkv_ready, par);
                     tr_ev<TRACE>(p.trace, 0, it, h, 2);
                     issue_s();
+                    const bool acc_sep = p.col_acc >= 0;               // q|k|v has its own accumulator columns (spare TMEM): the next
+                    if (acc_sep && next_in_tile) {                     // head's q|k|v need not wait for P V, it runs under the softmax
+                        qkv_begin(g + 1);
+                        qkv_finish();
+                    }
                     mbar_wait(&bars->p_ready, par);
                     tr_ev<TRACE>(p.trace, 0, it, h, 3);
                     issue_pv();
                     tr_ev<TRACE>(p.trace, 0, it, h, 4);
-                    if (next_in_tile) {
+                    if (!acc_sep && next_in_tile) {
                         qkv_begin(g + 1);
                         qkv_finish();
                     }
@@ -527,6 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 const uint32_t t_r = t_base + static_cast<uint32_t>(FUSE ? p.cp : reg * p.rsz);
                 const uint32_t t_s = t_r + static_cast<uint32_t>(p.hdp);
                 const uint32_t t_o = FUSE ? t_base + static_cast<uint32_t>(p.col_o) : t_r;
+                const uint32_t t_acc = (FUSE && p.col_acc >= 0) ? t_base + static_cast<uint32_t>(p.col_acc) : t_r;   // q|k|v accumulators
                 // ---- q | k | v of head h: folded LayerNorm + bias -> bf16; q in place (TMEM), k / v into the operand panels
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 0);
                 mbar_wait(&bars->qkv_full[reg], static_cast<uint32_t>((!FUSE && p.nreg == 2) ? (g >> 1) : g) & 1);
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 1);
                 for (int u = grp; u < 3 * uq; u += 4) {
                     uint32_t raw[16];
-                    tmem_ld16(t_r + static_cast<uint32_t>(16 * u), raw);
+                    tmem_ld16(t_acc + static_cast<uint32_t>(16 * u), raw);
                     tmem_ld_wait();
                     const float* bp = s_bq + h * 3 * p.hdp + 16 * u;
                     const float* cp = s_cq + h * 3 * p.hdp + 16 * u;
@@ -799,6 +805,9 @@ int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj) {
     p.fuse_proj = (allow_proj && hdp <= 64 && p.cp + 2 * hdp + 128 <= 512) ? 1 : 0;
     p.nreg = (!p.fuse_proj && 2 * p.rsz <= 512) ? 2 : 1;
     p.col_o = p.fuse_proj ? p.cp + hdp + 128 : 0;
+    // spare TMEM (the narrowest block): q|k|v gets accumulator columns of its own behind O, so that the next head's q|k|v MMAs can
+    // be issued as soon as S is (they no longer overwrite P) instead of after P V
+    p.col_acc = (p.fuse_proj && p.cp + 2 * hdp + 128 + 3 * hdp <= 512) ? p.cp + 2 * hdp + 128 : -1;
     // a [3 hdp x 64] qkv slab is one ring slot and one issue step (every step costs ~400 cycles of wait / commit bookkeeping on
     // top of its MMAs, so steps are kept as large as the MMA N limit of 256 allows); 3 hdp > 256: two N pieces
     const int n3 = 3 * hdp;
