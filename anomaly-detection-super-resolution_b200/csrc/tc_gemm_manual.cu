@@ -122,8 +122,9 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
     tc_fence_after_sync();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == 0) {
-        // ================================ B loader: one bulk copy per ring stage =================
+    if (warp == 0 || (CONVT && warp == 3)) {
+        // ================================ loader(s): one bulk copy (+ one TMA box) per ring stage.  The TMA-fed conv walks 18 - 27
+        // stages per tile and is bound by the per-stage overhead of this loop: two warps share it (even / odd ring stages)
         {   // converged warp, one elected lane issues (keeps descriptors in uniform registers)
             const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * 128u;
             const uint32_t tx_bytes = b_bytes + (!CONV ? static_cast<uint32_t>(kAStageBytes) : 0u);
@@ -135,16 +136,19 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
                 const int n_tile = tile % p.n_tiles;
                 const int m0 = (tile / p.n_tiles) * 128;
                 const uint8_t* src = p.Bp + static_cast<size_t>(n_tile) * p.num_k_stages * b_bytes;
+                // conv, TMA-fed: tile = 128 / W whole image rows starting at (b, y0).  The stage loop is bound by its own
+                // per-pass overhead (18 - 27 stages per tile), so nothing in it divides: tap and panel are counters
+                const int cb = CONVT ? m0 / hw : 0, cy0 = CONVT ? (m0 - cb * hw) / p.Win : 0;
+                int tap_y = -1, tap_x = -1, cpan = 0;                  // tap (dy, dx) and channel panel of stage ks
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
-                    mbar_wait(&bars->empty[stage], phase ^ 1);
-                    if (elect_one_sync()) {
+                    const bool mine = !CONVT || ((stage & 1) == (warp == 0 ? 0 : 1));   // kStages is even: parity of the ring stage
+                    if (mine) mbar_wait(&bars->empty[stage], phase ^ 1);
+                    if (mine && elect_one_sync()) {
                         mbar_arrive_expect_tx(&bars->full[stage], tx_bytes);
                         if (CONVT) {
-                            // tile = 128 / W whole image rows starting at (b, y0); tap (dy, dx) reads the same box shifted by
-                            // (dx, dy): columns / rows outside the image (and channels >= Cin) are zero-filled by the TMA unit
-                            const int tap = ks / p.stages_per_tap, cpan = ks - tap * p.stages_per_tap;
-                            const int b = m0 / hw, y0 = (m0 - b * hw) / p.Win;
-                            tma_load_4d(smem_a + stage * kAStageBytes, &p.tmap_a, cpan * 64, tap % 3 - 1, y0 + tap / 3 - 1, b, &bars->full[stage]);
+                            // tap (dy, dx) reads the tile's box shifted by (dx, dy): columns / rows outside the image (and channels
+                            // >= Cin) are zero-filled by the TMA unit
+                            tma_load_4d(smem_a + stage * kAStageBytes, &p.tmap_a, cpan * 64, tap_x, cy0 + tap_y, cb, &bars->full[stage]);
                         } else if (!CONV) {
                             tma_load_2d(smem_a + stage * kAStageBytes, &p.tmap_a, ks * 64, m0, &bars->full[stage]);
                         }
@@ -152,6 +156,10 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
                                  &bars->full[stage]);
                     }
                     __syncwarp();
+                    if (CONVT && ++cpan == p.stages_per_tap) {
+                        cpan = 0;
+                        if (++tap_x == 2) { tap_x = -1; ++tap_y; }
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -169,10 +177,12 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
                 mbar_wait(&bars->tmem_empty[buf], (use & 1) ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * 256);
+                int cpan = 0;                                          // channel panel of stage ks inside its tap (conv)
                 for (int ks = 0; ks < p.num_k_stages; ++ks) {
                     int steps;
                     if (CONV || CONVT) {
-                        steps = p.k16_per_tap - 4 * (ks % p.stages_per_tap);
+                        steps = p.k16_per_tap - 4 * cpan;
+                        if (++cpan == p.stages_per_tap) cpan = 0;
                     } else {
                         steps = p.k16_total - 4 * ks;
                     }
