@@ -305,11 +305,11 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
             if (++q_pc == p.qkv_pieces) { q_pc = 0; ++q_s; }
             if (++slot == p.w_slots) { slot = 0; wph ^= 1; }
         };
-        auto qkv_begin = [&](int g) {
+        auto qkv_begin = [&](int g, int head) {               // head = g % nH, known to every caller (no division on this path)
             q_g = g; q_step = 0; q_s = 0; q_pc = 0;
             q_dst = (FUSE && p.col_acc >= 0) ? tmem + static_cast<uint32_t>(p.col_acc) : region_of(g);
             q_full_idx = (!FUSE && p.nreg == 2) ? static_cast<uint32_t>(g & 1) : 0u;
-            q_last_head = (g % p.nH) == p.nH - 1;
+            q_last_head = head == p.nH - 1;
         };
         auto qkv_finish = [&]() {
             while (q_step < q_steps) {
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
 
         if (my_tiles > 0) {
             mbar_wait(&bars->x_full, 0);
-            qkv_begin(0);
+            qkv_begin(0, 0);
             qkv_finish();
         }
         for (int it = 0; it < my_tiles; ++it) {
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     issue_s();
                     const bool acc_sep = p.col_acc >= 0;               // q|k|v has its own accumulator columns (spare TMEM): the next
                     if (acc_sep && next_in_tile) {                     // head's q|k|v need not wait for P V, it runs under the softmax
-                        qkv_begin(g + 1);
+                        qkv_begin(g + 1, next_in_tile ? h + 1 : 0);
                         qkv_finish();
                     }
                     mbar_wait(&bars->p_ready, par);
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     issue_pv();
                     tr_ev<TRACE>(p.trace, 0, it, h, 4);
                     if (!acc_sep && next_in_tile) {
-                        qkv_begin(g + 1);
+                        qkv_begin(g + 1, next_in_tile ? h + 1 : 0);
                         qkv_finish();
                     }
                     tr_ev<TRACE>(p.trace, 0, it, h, 1);
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     tr_ev<TRACE>(p.trace, 0, it, h, 5);
                     if (!next_in_tile && more_tiles) {
                         mbar_wait(&bars->x_full, static_cast<uint32_t>(it + 1) & 1);
-                        qkv_begin(g + 1);                              // next tile's first head: overlaps the last epilogue of this tile
+                        qkv_begin(g + 1, next_in_tile ? h + 1 : 0);                              // next tile's first head: overlaps the last epilogue of this tile
                         qkv_finish();
                     }
                 } else if (p.nreg == 2) {
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     if (g >= 1) ensure_o(g - 1);
                     const bool look = next_in_tile || more_tiles;
                     bool began = false;
-                    if (next_in_tile) { qkv_begin(g + 1); began = true; }
+                    if (next_in_tile) { qkv_begin(g + 1, next_in_tile ? h + 1 : 0); began = true; }
                     bool s_done = false, pv_done = false;
                     while (!pv_done) {
                         if (!s_done) {
@@ -433,14 +433,14 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                             pv_done = true;
                             continue;
                         }
-                        if (look && !began && ready(&bars->x_full, static_cast<uint32_t>(it + 1) & 1)) { qkv_begin(g + 1); began = true; }
+                        if (look && !began && ready(&bars->x_full, static_cast<uint32_t>(it + 1) & 1)) { qkv_begin(g + 1, next_in_tile ? h + 1 : 0); began = true; }
                         if (began && q_step < q_steps && ready(&bars->w_full[slot], wph)) qkv_step();
                     }
                     tr_ev<TRACE>(p.trace, 0, it, h, 4);
                     if (look) {
                         if (!began) {
                             mbar_wait(&bars->x_full, static_cast<uint32_t>(it + 1) & 1);
-                            qkv_begin(g + 1);
+                            qkv_begin(g + 1, next_in_tile ? h + 1 : 0);
                         }
                         qkv_finish();
                     }
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     ensure_o(g);                                       // single region: strictly one head after the other
                     if (next_in_tile || more_tiles) {
                         if (!next_in_tile) mbar_wait(&bars->x_full, static_cast<uint32_t>(it + 1) & 1);
-                        qkv_begin(g + 1);
+                        qkv_begin(g + 1, next_in_tile ? h + 1 : 0);
                         qkv_finish();
                     }
                 }
@@ -482,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         const float2 sc2 = f2_(p.scale_log2e, p.scale_log2e);
         const uint32_t t_base = tmem + lane_off;
         const int t128 = grp * 32 + lane;
+        const uint32_t cpr_magic = (65536u + static_cast<uint32_t>(p.hdp >> 3) - 1u) / static_cast<uint32_t>(p.hdp >> 3);   // id / (hdp / 8), id < 512
 
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
@@ -672,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     const int cpr = p.hdp >> 3;                          // 16-byte chunks per row
                     const uint32_t kq = smem_u32(k_buf);
                     for (int id = t128; id < 32 * cpr; id += 128) {
-                        const int rl = id / cpr, ch = id - rl * cpr;
+                        const int rl = static_cast<int>((static_cast<uint32_t>(id) * cpr_magic) >> 16), ch = id - rl * cpr;
                         const int rq = quad * 32 + rl;
                         uint4 val;
                         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"

@@ -148,9 +148,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_rows_kernel(const __grid_
         // ============================================================ A tiles (whole K extent), n_abuf deep
         if (lane == 0) tma_prefetch_desc(&p.tmap_a);
         for (int it = 0; it < my_tiles; ++it) {
-            const int ab = it % rp.n_abuf;
+            const int ab = rp.n_abuf == 2 ? (it & 1) : 0;
             const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
-            mbar_wait(&bars->a_empty[ab], (static_cast<uint32_t>(it / rp.n_abuf) & 1) ^ 1);
+            mbar_wait(&bars->a_empty[ab], (static_cast<uint32_t>(rp.n_abuf == 2 ? (it >> 1) : it) & 1) ^ 1);
             if (lane == 0) {
                 mbar_arrive_expect_tx(&bars->a_full[ab], static_cast<uint32_t>(a_bytes));
                 for (int pn = 0; pn < rp.ks1; ++pn)
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_rows_kernel(const __grid_
         const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(a_buf));
         int c = 0;                                                     // running N-tile counter: accumulator = c % 4
         for (int it = 0; it < my_tiles; ++it) {
-            const int ab = it % rp.n_abuf;
-            mbar_wait(&bars->a_full[ab], static_cast<uint32_t>(it / rp.n_abuf) & 1);
+            const int ab = rp.n_abuf == 2 ? (it & 1) : 0;
+            mbar_wait(&bars->a_full[ab], static_cast<uint32_t>(rp.n_abuf == 2 ? (it >> 1) : it) & 1);
             const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(ab) * static_cast<uint32_t>(a_bytes >> 4));
             for (int nt = 0; nt < p.n_tiles; ++nt, ++c) {
                 if ((c & 1) != me) continue;
