@@ -129,7 +129,7 @@ struct SwinAttnParams {
     int fuse_proj;
     int cp;                   // proj accumulator columns (C rounded up to 16)
     int n_pp, pp_rows[4];     // a head's proj slab is issued in n_pp N pieces (each fits a ring slot)
-    int qkv_pieces, qp_rows[4];  // a qkv slab is issued in N pieces of <= 128 rows (one ring slot each)
+    int qkv_pieces, qp_rows[4];  // a qkv slab is one ring slot / issue step; two N pieces when 3 hdp > 256
     int rsz, nreg;            // TMEM: columns per head region, number of regions (2 = next head's q|k|v runs one head ahead)
     int col_o;                // TMEM column of O (fuse_proj: behind the region; else O overlays the region's q columns)
     int col_acc;              // fuse_proj with spare TMEM: separate q|k|v accumulator columns, else -1 (accumulators = the region)

@@ -9,20 +9,24 @@
 //     window; R = 4 when the cyclic shift makes windows wrap; closed-form index map of src/drct.py:483, 193-204) into
 //     K-major 128-byte-swizzled panels (A operand of qkv); channels >= C are zero-filled by the tensor map;
 //   * per head h the MMA warp computes  [q_h | k_h | v_h] = x W_h^T  (tcgen05.mma SS, N = 3 hdp) into a TMEM region (two
-//     alternating regions when proj is not fused: the next head's q|k|v then runs one head ahead); the weights of the whole
-//     half (qkv and proj slabs) stream from L2 through ONE ring in the fixed order of use;
+//     alternating regions when proj is not fused: the next head's q|k|v then runs one head ahead); the weights stream
+//     from L2 through a ring of whole [3 hdp x 64] qkv slabs and a one-head-deep proj ring, each fed by its own loader warp;
 //   * 16 epilogue warps apply the folded LayerNorm + bias and write q back IN PLACE into TMEM as bf16 (A operand of S), k and
 //     v as bf16 into shared-memory operand panels;
 //   * S = q k^T (tcgen05.mma TS, M = N = 128; the off-diagonal 64 x 64 blocks belong to the other window and are never
 //     used) lands on the dead k|v accumulator columns of the region; softmax: four threads per query row, relative-position
 //     bias from a shared-memory table, -100 mask from closed-form region ids (src/drct.py:449-470); unnormalised bf16
 //     probabilities go back in place into TMEM;  O = P v  (TS, v as MN-major B operand) lands on the dead q columns;
-//   * fuse_proj: the normalised O_h is written back in place as bf16 and  Y += O_h Wp_h^T  (TS) accumulates the proj Linear
-//     over the heads in a persistent TMEM accumulator; the last epilogue adds bias and the shortcut
-//     (fetched as coalesced 128-byte row pieces into the idle k / v panels), stores y at the ORIGINAL token rows
-//     (window_reverse + un-shift are the inverse permutation) and leaves the per-row (sum, sumsq) for the norm2 fold of
-//     the MLP kernel.  Otherwise (heads of 80 / 128 padded channels: TMEM cannot hold everything) the normalised O rows are
-//     stored to `out` [M, nH * hdp] and the row-tile GEMM applies proj.
+//   * fuse_proj (padded heads <= 64): a persistent TMEM accumulator Y is initialised with the SHORTCUT by identity MMAs
+//     (Y = x I, N = 16, straight from the resident x tile: bf16 values enter fp32 exactly); the normalised O_h is written back
+//     in place as bf16 and  Y += O_h Wp_h^T  (TS) accumulates the proj Linear over the heads; the last epilogue adds the bias,
+//     stages y through the idle k / v panels (coalesced 128-byte row pieces) to the ORIGINAL token rows (window_reverse +
+//     un-shift are the inverse permutation) and leaves the per-row (sum, sumsq) for the norm2 fold of the MLP kernel.  Where
+//     TMEM has room (the narrowest block) q|k|v has accumulator columns of its own and the next head's q|k|v is issued right
+//     after S.  Otherwise (heads of 80 / 128 padded channels: TMEM cannot hold everything) two TMEM regions alternate so that
+//     the next head's q|k|v runs one head ahead, the normalised O rows go through the k panel to `out` [M, nH * hdp] and the
+//     row-tile GEMM applies proj.
+// Single-warp issue loops are latency chains: nothing on them divides by a run-time value (one modulo per head cost 3 %).
 #include "adsr_kernels.h"
 #include "ptx.cuh"
 
