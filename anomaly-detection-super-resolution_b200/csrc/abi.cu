@@ -82,6 +82,30 @@ extern "C" int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K, const
     return launch_tc_gemm(p, num_sms, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int adsr_conv3x3_halo_bf16(const void* in, int64_t ld_in, int B, int H, int W, int Cin, const void* w_compact,
+                                      const float* bias_padded, int N, int BN, int act, float slope, void* out, int64_t ldo,
+                                      int ocol0, int n_store, int num_sms, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (in == nullptr || w_compact == nullptr || bias_padded == nullptr || out == nullptr) return ADSR_ERR_BAD_SHAPE;
+    if (ld_in < ((Cin + 7) & ~7)) return ADSR_ERR_BAD_SHAPE;
+    ConvHaloParams p{};
+    p.wp = static_cast<const uint8_t*>(w_compact);
+    p.bias = bias_padded;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo;
+    p.ocol0 = ocol0;
+    p.n_store = n_store;
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.Cin = Cin;
+    p.N = N;
+    p.BN = BN;
+    p.act = act;
+    p.slope = slope;
+    return launch_conv_halo(p, in, ld_in, num_sms, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int Hin, int Win, int Cin, int stride,
                                        const void* w_packed, const float* bias_padded, int N, int BN, int n_tiles, int act,
                                        float slope, float alpha, const void* res, int64_t ldres, void* out, int64_t ldo,

@@ -139,7 +139,27 @@ struct SwinAttnParams {
 };
 int encode_tmap_nhwc_box_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int R);
 int encode_tmap_nhwc_box2_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int box_w, int box_h);
+int encode_tmap_nhwc_box3_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int box_c, int box_w,
+                               int box_h);
 int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj);   // 0 = not covered, 1 = qkv + attention, 2 = + proj
 int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream);
+
+// ---- halo-tile 3x3 conv with resident weights (conv_halo.cu)
+struct ConvHaloParams {
+    CUtensorMap tmap_in;      // input as [B, H, W, C] bf16, box 64 channels x (W + 2) x box_rows, 128-byte swizzle
+    CUtensorMap tmap_tail;    // same image, box 16 channels, 32-byte swizzle: the last K = 16 step when Cin = 64 + (<= 16) channels
+    const uint8_t* wp;        // slabs [BN rows x 64 bf16], K index = tap * 16 k16_per_tap + channel (compact), 128-byte swizzle
+    const float* bias;        // [BN]
+    __nv_bfloat16* out;
+    long long ldo;
+    int ocol0, n_store;
+    int B, H, W, Cin, N, BN;
+    int act;
+    float slope;
+    // set by launch_conv_halo
+    int k16_per_tap, full_panels, tail, slabs, Wh, box_rows, box_bytes, panel_bytes, tail_box_bytes, tail_bytes, n_abuf, tiles_per_img,
+        n_tiles;
+};
+int launch_conv_halo(ConvHaloParams& p, const void* in, long long ld_in, int num_sms, cudaStream_t stream);
 
 }  // namespace adsr

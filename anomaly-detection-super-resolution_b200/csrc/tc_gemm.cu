@@ -574,16 +574,23 @@ int encode_tmap_nhwc_box_bf16(CUtensorMap* map, const void* base, int B, int H, 
 
 // general form: boxes of box_w x box_h tokens x 64 channels (box_w tokens of a row are contiguous in shared memory)
 int encode_tmap_nhwc_box2_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int box_w, int box_h) {
+    return encode_tmap_nhwc_box3_bf16(map, base, B, H, W, C, ld_elems, 64, box_w, box_h);
+}
+
+// box_c channels per token: 64 (128-byte swizzle), 32 (64-byte swizzle) or 16 (32-byte swizzle) -- the swizzle span equals the row
+int encode_tmap_nhwc_box3_bf16(CUtensorMap* map, const void* base, int B, int H, int W, int C, long long ld_elems, int box_c, int box_w,
+                               int box_h) {
     EncodeFn encode = get_encode_fn();
     if (encode == nullptr) return ADSR_ERR_CUDA;
+    const CUtensorMapSwizzle sw = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    if (box_c != 64 && box_c != 32 && box_c != 16) return ADSR_ERR_BAD_SHAPE;
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld_elems) * 2, static_cast<cuuint64_t>(ld_elems) * 2 * W,
                                    static_cast<cuuint64_t>(ld_elems) * 2 * W * H};
-    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? ADSR_OK : ADSR_ERR_CUDA;
 }
 

@@ -7,6 +7,7 @@ module (bench.py reports it as `gpu_launches`).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -16,6 +17,7 @@ from ._abi import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, OUT_PIXEL_SHUFFLE2, O
 from .pack import PackedWeight
 
 LAUNCHES = 0
+_HALO_CONV = os.environ.get("ADSR_HALO_CONV", "1") != "0"   # narrow 3x3 convs through csrc/conv_halo.cu (0 = streaming implicit GEMM)
 PROFILE = None      # set to a list to collect (kind, algorithmic_flops, start_event, end_event) per launch (bench.py)
 
 
@@ -134,6 +136,16 @@ def conv3x3(x: torch.Tensor, b: int, h: int, wd: int, cin: int, w: PackedWeight,
     _cuda(x, "x")
     n_store = (w.N + 15) // 16 * 16 if n_store is None else n_store
     _t = _begin()
+    wc = w.compact
+    if (wc is not None and _HALO_CONV and stride == 1 and res is None and out_mode == OUT_ROWS and alpha == 1.0 and 8 <= wd <= 126
+            and n_store <= wc.BN and n_store % 8 == 0 and ocol0 % 8 == 0 and act in (ACT_NONE, ACT_RELU, ACT_LRELU)):
+        # narrow layer: halo tile + resident weights (csrc/conv_halo.cu); BAD_SHAPE = does not fit the SM, fall through
+        st = lib().adsr_conv3x3_halo_bf16(ptr(x), x.stride(0), b, h, wd, cin, ptr(wc.data), ptr(wc.bias), wc.N, wc.BN, act, slope,
+                                          ptr(out), out.stride(0), ocol0, n_store, _abi.num_sms(), stream_ptr())
+        if st != 1:                       # ADSR_ERR_BAD_SHAPE
+            check(st, "adsr_conv3x3_halo_bf16")
+            _count("conv3x3_halo", 2.0 * b * h * wd * 9 * cin * w.N, _t)
+            return
     check(lib().adsr_conv3x3_igemm_bf16(ptr(x), x.stride(0), b, h, wd, cin, stride, ptr(w.data), ptr(w.bias), w.N, w.BN,
                                         w.n_tiles, act, slope, alpha, ptr(res), res.stride(0) if res is not None else 0,
                                         ptr(out), out.stride(0), ocol0, out_mode, n_store, _abi.num_sms(), stream_ptr()),

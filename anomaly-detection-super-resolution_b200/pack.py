@@ -49,6 +49,7 @@ class PackedWeight:
     BN: int = 0
     n_tiles: int = 0
     k_stages: int = 0
+    compact: Optional["PackedWeight"] = None   # 3x3 convs whose weights fit in shared memory: K-concatenated twin (conv_halo.cu)
 
 
 def _swizzle_tiles(w2d: torch.Tensor, bn: int, n_tiles: int) -> tuple[torch.Tensor, int]:
@@ -111,7 +112,17 @@ def pack_conv3x3_weight(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> P
     w2 = torch.zeros(cout, 9, spt * 64, dtype=torch.float32, device=w.device)
     w2[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
     data, ks = _swizzle_tiles(w2.reshape(cout, 9 * spt * 64), bn, n_tiles)
-    return PackedWeight(data, _pad_bias(bias, cout, bn * n_tiles, w.device), N=cout, K=cin, BN=bn, n_tiles=n_tiles, k_stages=ks)
+    pw = PackedWeight(data, _pad_bias(bias, cout, bn * n_tiles, w.device), N=cout, K=cin, BN=bn, n_tiles=n_tiles, k_stages=ks)
+    # halo-tile kernel (csrc/conv_halo.cu): one N tile of round16(cout) rows, K index = tap * round16(cin) + channel, resident in
+    # shared memory next to a two-panel halo tile (<= ~125 KB of weights)
+    bnc, kt = round_up(cout, 16), round_up(cin, 16)
+    slabs = (9 * kt + 63) // 64
+    if cout <= 128 and cin <= 128 and slabs * bnc * 128 <= 126 * 1024:
+        wc = torch.zeros(cout, slabs * 64, dtype=torch.float32, device=w.device)
+        wc[:, :9 * kt].view(cout, 9, kt)[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+        cdata, cks = _swizzle_tiles(wc, bnc, 1)
+        pw.compact = PackedWeight(cdata, _pad_bias(bias, cout, bnc, w.device), N=cout, K=cin, BN=bnc, n_tiles=1, k_stages=cks)
+    return pw
 
 
 def head_pad(hd: int) -> int:

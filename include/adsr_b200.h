@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 7
+#define ADSR_ABI_VERSION 8
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -125,6 +125,15 @@ int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int Hin, int W
                             const void* res, int64_t ldres,
                             void* out, int64_t ldo, int ocol0, int out_mode, int n_store,
                             int num_sms, void* stream);
+
+/* ---- halo-tile 3x3 convolution (pad 1, stride 1) with weights resident in shared memory ----------------
+ * replaces the two default_conv of every RCAB (src/drn.py:143-158; 80 -> 80 channels in DRN-L): Cin <= 128, Cout <= 128,
+ * 8 <= W <= 126, plain-row output with bias and optional ReLU / LeakyReLU.  `w_compact` is the K-concatenated image of
+ * pack.pack_conv3x3_weight(...).compact.  ADSR_ERR_BAD_SHAPE = shape not covered (use adsr_conv3x3_igemm_bf16). */
+int adsr_conv3x3_halo_bf16(const void* in, int64_t ld_in, int B, int H, int W, int Cin,
+                           const void* w_compact, const float* bias_padded, int N, int BN,
+                           int act, float slope, void* out, int64_t ldo, int ocol0, int n_store,
+                           int num_sms, void* stream);
 
 /* ---- LayerNorm over the first C columns of each row (eps, affine); writes round16(C) columns ---------
  * replaces nn.LayerNorm norm1 / norm2 / final norm (src/drct.py:432, 438, 833, 881). */

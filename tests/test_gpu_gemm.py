@@ -146,6 +146,49 @@ def test_conv_stride2_and_odd_sizes():
     _conv_case(3, 20, 12, 16, 32, seed=6)        # M not a multiple of 128, tiles straddle images
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,act", [(3, 32, 32, 80, 80, "relu"), (2, 64, 64, 80, 80, "none"), (5, 17, 24, 40, 48, "lrelu"),
+                                                (1, 9, 126, 128, 16, "none"), (150, 16, 16, 64, 64, "relu"), (2, 8, 8, 20, 20, "none")])
+def test_conv_halo_tile_kernel(B, H, W, Cin, Cout, act):
+    """Halo-tile conv with resident weights (csrc/conv_halo.cu), called directly: every tap offset / tile phase / image border,
+    poison in the untouched output columns, and equality with the streaming implicit GEMM on the same inputs."""
+    ops, pack, abi = mod("ops"), mod("pack"), mod("_abi")
+    torch.manual_seed(B * 131 + W)
+    ld = (Cin + 15) // 16 * 16 + 16
+    x = torch.full((B * H * W, ld), 7.0, device=DEV, dtype=torch.bfloat16)      # columns >= Cin must not matter beyond round8
+    x[:, :Cin] = torch.randn(B * H * W, Cin, device=DEV).to(torch.bfloat16)
+    x[:, Cin:(Cin + 7) // 8 * 8] = 0
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV) * 0.05
+    bias = torch.randn(Cout, device=DEV)
+    pw = pack.pack_conv3x3_weight(w, bias)
+    assert pw.compact is not None
+    wc = pw.compact
+    code = {"none": ops.ACT_NONE, "lrelu": ops.ACT_LRELU, "relu": ops.ACT_RELU}[act]
+    n_store = (Cout + 15) // 16 * 16
+    out = torch.full((B * H * W, n_store + 24), -3.0, device=DEV, dtype=torch.bfloat16)
+    st = abi.lib().adsr_conv3x3_halo_bf16(abi.ptr(x), x.stride(0), B, H, W, Cin, abi.ptr(wc.data), abi.ptr(wc.bias), wc.N, wc.BN, code,
+                                          0.1, abi.ptr(out), out.stride(0), 8, n_store, abi.num_sms(), abi.stream_ptr())
+    assert st == 0, f"status {st}"
+    torch.cuda.synchronize()
+    xin = x[:, :Cin].float().view(B, H, W, Cin).permute(0, 3, 1, 2)
+    want = F.conv2d(xin, bf16_round(w), bias, padding=1)
+    want = {"none": lambda t: t, "lrelu": lambda t: F.leaky_relu(t, 0.1), "relu": F.relu}[act](want)
+    got = out[:, 8:8 + Cout].float().view(B, H, W, Cout).permute(0, 3, 1, 2)
+    err = rel_err(got, want)
+    assert err < 0.012, f"halo conv rel err {err}"
+    assert bool((out[:, :8] == -3.0).all()) and bool((out[:, 8 + n_store:] == -3.0).all())
+    assert bool((out[:, 8 + Cout:8 + n_store] == 0).all())                      # padded output channels: zero weights, zero bias
+    # the streaming kernel computes the same sums in a different K order: equal to bf16 rounding
+    ref = torch.zeros(B * H * W, n_store, device=DEV, dtype=torch.bfloat16)
+    old = ops._HALO_CONV
+    ops._HALO_CONV = False
+    try:
+        ops.conv3x3(x, B, H, W, Cin, pw, ref, act=code, slope=0.1)
+    finally:
+        ops._HALO_CONV = old
+    torch.cuda.synchronize()
+    assert rel_err(out[:, 8:8 + Cout].float(), ref[:, :Cout].float()) < 0.006
+
+
 def _row_stats(t: torch.Tensor, slots: int) -> torch.Tensor:
     """(sum, sumsq) of each row in slot 0, zeros elsewhere: what a producing epilogue leaves behind."""
     st = torch.zeros(t.shape[0], slots, 2, device=t.device)
