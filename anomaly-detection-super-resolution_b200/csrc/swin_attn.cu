@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         const uint32_t idesc_pv = idesc_m128(static_cast<uint32_t>(p.hdp), 1);
         const uint64_t x_desc = umma_desc_k_sw128(smem_u32(x_buf));
         const uint32_t k_addr = smem_u32(k_buf), v_addr = smem_u32(v_buf);
+        const uint64_t k_desc = umma_desc_k_sw128(k_addr);
         const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring));
         const uint32_t slot_units = static_cast<uint32_t>(p.w_slot_bytes >> 4);
         const uint64_t pring_desc = umma_desc_k_sw128(smem_u32(pring));
@@ -341,9 +342,11 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     // S = q k^T : q bf16 in TMEM (unit u at column 16 u of the region), k panel in shared memory
                     tc_fence_after_sync();
                     if (elect_one_sync()) {
-                        for (int u = 0; u < uq; ++u) {
-                            const uint32_t off = static_cast<uint32_t>((u >> 2) * kPanelBytes + (u & 3) * 32);
-                            umma_bf16_ts(t_s, t_r + static_cast<uint32_t>(16 * u), umma_desc_k_sw128(k_addr + off), idesc_s, u == 0 ? 0u : 1u);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {                  // straight-line issue: a rolled loop costs ~100 cycles per MMA
+                            if (u < uq)
+                                umma_bf16_ts(t_s, t_r + static_cast<uint32_t>(16 * u),
+                                             k_desc + static_cast<uint64_t>(((u >> 2) * kPanelBytes + (u & 3) * 32) >> 4), idesc_s, u == 0 ? 0u : 1u);
                         }
                         umma_commit(&bars->s_full);
                     }
@@ -392,9 +395,12 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                         if (elect_one_sync()) {
                             const uint64_t idesc_b = umma_desc_k_sw128(smem_u32(ident_s));
                             const uint32_t idesc16 = idesc_m128(16u, 0);
-                            for (int gcol = 0; gcol < p.cp / 16; ++gcol)
-                                umma_bf16(tmem + static_cast<uint32_t>(16 * gcol),
-                                          x_desc + static_cast<uint64_t>((gcol >> 2) * (kPanelBytes >> 4) + (gcol & 3) * 2), idesc_b, idesc16, 0u);
+                            const int n16 = p.cp >> 4;
+#pragma unroll
+                            for (int gcol = 0; gcol < 20; ++gcol)             // cp <= 320
+                                if (gcol < n16)
+                                    umma_bf16(tmem + static_cast<uint32_t>(16 * gcol),
+                                              x_desc + static_cast<uint64_t>((gcol >> 2) * (kPanelBytes >> 4) + (gcol & 3) * 2), idesc_b, idesc16, 0u);
                         }
                         __syncwarp();
                     }
@@ -405,8 +411,9 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                         if (elect_one_sync()) {
                             const uint64_t bdesc = pring_desc + static_cast<uint64_t>(static_cast<uint32_t>(pslot) * pslot_units);
                             const uint32_t idesc = idesc_m128(static_cast<uint32_t>(p.pp_rows[pc]), 0);
-                            for (int u = 0; u < uq; ++u)
-                                umma_bf16_ts(tmem + dcol, t_o + static_cast<uint32_t>(16 * u), bdesc + 2 * u, idesc, 1u);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)                // fuse_proj: hdp <= 64
+                                if (u < uq) umma_bf16_ts(tmem + dcol, t_o + static_cast<uint32_t>(16 * u), bdesc + 2 * u, idesc, 1u);
                             umma_commit(&bars->p_empty[pslot]);
                             if (h == p.nH - 1 && pc == p.n_pp - 1) umma_commit(&bars->proj_full);
                         }
