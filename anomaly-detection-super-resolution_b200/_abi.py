@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadsr_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 ACT_NONE, ACT_LRELU, ACT_GELU, ACT_RELU = 0, 1, 2, 3
 OUT_ROWS, OUT_PIXEL_SHUFFLE2 = 0, 1
@@ -37,7 +37,9 @@ _SIGNATURES = {
                                         c_int, c_int, c_int, c_float, c_float, c_void_p, c_int64, c_void_p, c_int64,
                                         c_int, c_int, c_int, c_int, c_void_p]),
     "adsr_conv3x3_halo_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
-                                       c_float, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+                                       c_float, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "adsr_channel_mean_parts": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int, c_void_p]),
     "adsr_layernorm_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_float,
                                     c_void_p]),
     "adsr_window_attention": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -84,7 +84,7 @@ extern "C" int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K, const
 
 extern "C" int adsr_conv3x3_halo_bf16(const void* in, int64_t ld_in, int B, int H, int W, int Cin, const void* w_compact,
                                       const float* bias_padded, int N, int BN, int act, float slope, void* out, int64_t ldo,
-                                      int ocol0, int n_store, int num_sms, void* stream) {
+                                      int ocol0, int n_store, float* chan_part, int num_sms, void* stream) {
     if (B <= 0) return ADSR_OK;
     if (in == nullptr || w_compact == nullptr || bias_padded == nullptr || out == nullptr) return ADSR_ERR_BAD_SHAPE;
     if (ld_in < ((Cin + 7) & ~7)) return ADSR_ERR_BAD_SHAPE;
@@ -95,6 +95,7 @@ extern "C" int adsr_conv3x3_halo_bf16(const void* in, int64_t ld_in, int B, int 
     p.ldo = ldo;
     p.ocol0 = ocol0;
     p.n_store = n_store;
+    p.chan_part = chan_part;
     p.B = B;
     p.H = H;
     p.W = W;

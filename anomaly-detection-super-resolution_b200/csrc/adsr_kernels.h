@@ -153,6 +153,7 @@ struct ConvHaloParams {
     __nv_bfloat16* out;
     long long ldo;
     int ocol0, n_store;
+    float* chan_part;         // optional [n_tiles * 4, BN] per-(tile, row quadrant) column sums of the outputs (fp32, before bf16 rounding)
     int B, H, W, Cin, N, BN;
     int act;
     float slope;

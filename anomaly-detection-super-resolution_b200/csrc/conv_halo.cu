@@ -206,14 +206,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 uint32_t raw[16];
                 tmem_ld16(taddr + static_cast<uint32_t>(16 * u), raw);
                 tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float v = __uint_as_float(raw[e]) + s_bias[16 * u + e];
+                    if (p.act == ADSR_ACT_RELU) v = fmaxf(v, 0.f);
+                    else if (p.act == ADSR_ACT_LRELU) v = v > 0.f ? v : v * p.slope;
+                    f[e] = v;
+                }
                 uint32_t pk[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float v0 = __uint_as_float(raw[2 * e]) + s_bias[16 * u + 2 * e];
-                    float v1 = __uint_as_float(raw[2 * e + 1]) + s_bias[16 * u + 2 * e + 1];
-                    if (p.act == ADSR_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                    else if (p.act == ADSR_ACT_LRELU) { v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope; }
-                    pk[e] = pack_bf16x2(v0, v1);
+                for (int e = 0; e < 8; ++e) pk[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+                if (p.chan_part != nullptr) {
+                    // column sums over the 32 rows of this warp (pad / out-of-image positions count as 0): butterfly that halves the
+                    // values per lane at every step (16 shuffles per unit); lane l ends with column 16 u + (l >> 1)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) f[e] = valid ? f[e] : 0.f;
+#pragma unroll
+                    for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+                        const bool up = (lane & bit) != 0;
+#pragma unroll
+                        for (int j = 0; j < w; ++j) {
+                            const float send = up ? f[j] : f[j + w];
+                            const float keep = up ? f[j + w] : f[j];
+                            f[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                        }
+                    }
+                    f[0] += __shfl_xor_sync(0xffffffffu, f[0], 1);
+                    if ((lane & 1) == 0) p.chan_part[(static_cast<long long>(tile) * 4 + quad) * p.BN + 16 * u + (lane >> 1)] = f[0];
                 }
                 if (valid && 16 * u < p.n_store) {
                     uint4* d4 = reinterpret_cast<uint4*>(dst + 16 * u);
@@ -237,6 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
 
 }  // namespace
 
+// chan_part (optional): [n_tiles * 4, BN] fp32 per-(tile, row quadrant) column sums of the outputs -- a tile never straddles images,
+// n_tiles = B * ceil(H (W + 2) / 128): the AdaptiveAvgPool2d(1) of CALayer (src/drn.py:126, 137) without re-reading the output.
 // ADSR_ERR_BAD_SHAPE = shape not covered: the caller uses the streaming implicit GEMM (launch_tc_gemm) with the ordinary packing.
 int launch_conv_halo(ConvHaloParams& p, const void* in, long long ld_in, int num_sms, cudaStream_t stream) {
     if (p.B <= 0) return ADSR_OK;

@@ -173,6 +173,55 @@ __global__ void __launch_bounds__(256) channel_mean8_kernel(const __nv_bfloat16*
     }
 }
 
+// mean[b, c] from the per-(tile, row quadrant) column sums the halo conv's epilogue leaves behind (conv_halo.cu): fixed summation order
+// With w1 != nullptr the block goes on to CALayer's squeeze-excite MLP and writes scale[b, c] = sigmoid(W2 relu(W1 mean + b1) + b2)
+// instead of the mean: once per image, not once per block of the scaling pass.
+__global__ void __launch_bounds__(1024) channel_mean_parts_kernel(const float* __restrict__ part, int parts, int ld, int C, float inv_hw,
+                                                                   float* __restrict__ mean, const float* __restrict__ w1,
+                                                                   const float* __restrict__ b1, const float* __restrict__ w2,
+                                                                   const float* __restrict__ b2, int Cr) {
+    __shared__ float red[8][128];
+    __shared__ float hid[16];
+    const int b = blockIdx.x, c = threadIdx.x & 127, g = threadIdx.x >> 7;      // 8 groups take every 8th partial row
+    float acc = 0.f;
+    if (c < C) {
+        const float* p = part + static_cast<long long>(b) * parts * ld + c;
+        int i = g;
+        for (; i + 24 < parts; i += 32) {                                       // four independent loads in flight per thread
+            const float v0 = p[static_cast<long long>(i) * ld], v1 = p[static_cast<long long>(i + 8) * ld];
+            const float v2 = p[static_cast<long long>(i + 16) * ld], v3 = p[static_cast<long long>(i + 24) * ld];
+            acc += (v0 + v1) + (v2 + v3);
+        }
+        for (; i < parts; i += 8) acc += p[static_cast<long long>(i) * ld];
+    }
+    red[g][c] = acc;
+    __syncthreads();
+    if (g == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += red[j][c];
+        t *= inv_hw;
+        if (w1 == nullptr) mean[static_cast<long long>(b) * C + c] = t;
+        red[0][c] = t;
+    }
+    if (w1 == nullptr) return;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < Cr) {                                                            // one warp per hidden unit
+        float a = 0.f;
+        for (int k = lane; k < C; k += 32) a = fmaf(w1[warp * C + k], red[0][k], a);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) hid[warp] = fmaxf(a + b1[warp], 0.f);
+    }
+    __syncthreads();
+    if (g == 0 && c < C) {
+        float a = b2[c];
+        for (int j = 0; j < Cr; ++j) a = fmaf(w2[c * Cr + j], hid[j], a);
+        mean[static_cast<long long>(b) * C + c] = 1.f / (1.f + __expf(-a));
+    }
+}
+
 // out = res * sigmoid(W2 relu(W1 mean_b + b1) + b2) + x       (CALayer + RCAB residual, src/drn.py:123-158)
 __global__ void __launch_bounds__(256) rcab_ca_scale_kernel(const __nv_bfloat16* __restrict__ res, long long ldr,
                                                              const __nv_bfloat16* __restrict__ x, long long ldx,
@@ -183,33 +232,52 @@ __global__ void __launch_bounds__(256) rcab_ca_scale_kernel(const __nv_bfloat16*
     __shared__ float hid[16];
     __shared__ float sc[128];
     const int b = blockIdx.y;
-    if (threadIdx.x < Cr) {
+    if (Cr == 0) {                                          // `mean` already holds the scales (channel_mean_parts with the MLP)
+        if (threadIdx.x < C) sc[threadIdx.x] = mean[static_cast<long long>(b) * C + threadIdx.x];
+    } else if (threadIdx.x < Cr) {
         float a = b1[threadIdx.x];
         for (int c = 0; c < C; ++c) a = fmaf(w1[threadIdx.x * C + c], mean[static_cast<long long>(b) * C + c], a);
         hid[threadIdx.x] = fmaxf(a, 0.f);
     }
     __syncthreads();
-    if (threadIdx.x < C) {
+    if (Cr > 0 && threadIdx.x < C) {
         float a = b2[threadIdx.x];
         for (int j = 0; j < Cr; ++j) a = fmaf(w2[threadIdx.x * Cr + j], hid[j], a);
         sc[threadIdx.x] = 1.f / (1.f + __expf(-a));
     }
     __syncthreads();
-    const int vec = C / 8;                                  // 16-byte vectors per pixel
-    const long long n = static_cast<long long>(HW) * vec;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long p = static_cast<long long>(b) * HW + i / vec;
-        const int c0 = static_cast<int>(i % vec) * 8;
-        const uint4 r = __ldg(reinterpret_cast<const uint4*>(res + p * ldr + c0));
-        const uint4 xv = *reinterpret_cast<const uint4*>(x + p * ldx + c0);
-        const uint32_t rr[4] = {r.x, r.y, r.z, r.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
-        uint32_t o[4];
+    const uint32_t vec = static_cast<uint32_t>(C) / 8u;               // 16-byte vectors per pixel
+    const uint32_t n = static_cast<uint32_t>(HW) * vec;                 // per image: < 2^31 (checked by the wrapper)
+    const uint32_t step = gridDim.x * blockDim.x;
+    const __nv_bfloat16* rb = res + static_cast<long long>(b) * HW * ldr;
+    const __nv_bfloat16* xb = x + static_cast<long long>(b) * HW * ldx;
+    __nv_bfloat16* ob = out + static_cast<long long>(b) * HW * ldo;
+    // two vectors in flight per thread; 32-bit index arithmetic (a 64-bit division per vector used to dominate the issue slots)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * step) {
+        const uint32_t i1 = i + step;
+        const bool two = i1 < n;
+        const uint32_t p0 = i / vec, c0 = (i - p0 * vec) * 8u;
+        const uint32_t p1 = two ? i1 / vec : p0, c1 = two ? (i1 - p1 * vec) * 8u : c0;
+        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rb + static_cast<long long>(p0) * ldr + c0));
+        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rb + static_cast<long long>(p1) * ldr + c1));
+        const uint4 x0 = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(p0) * ldx + c0);
+        const uint4 x1 = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(p1) * ldx + c1);
+        {
+            const uint32_t rr[4] = {r0.x, r0.y, r0.z, r0.w}, xx[4] = {x0.x, x0.y, x0.z, x0.w};
+            uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            o[j] = pack_bf16x2(fmaf(bf16_lo(rr[j]), sc[c0 + 2 * j], bf16_lo(xx[j])),
-                               fmaf(bf16_hi(rr[j]), sc[c0 + 2 * j + 1], bf16_hi(xx[j])));
-        *reinterpret_cast<uint4*>(out + p * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+            for (int j = 0; j < 4; ++j)
+                o[j] = pack_bf16x2(fmaf(bf16_lo(rr[j]), sc[c0 + 2 * j], bf16_lo(xx[j])), fmaf(bf16_hi(rr[j]), sc[c0 + 2 * j + 1], bf16_hi(xx[j])));
+            *reinterpret_cast<uint4*>(ob + static_cast<long long>(p0) * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (two) {
+            const uint32_t rr[4] = {r1.x, r1.y, r1.z, r1.w}, xx[4] = {x1.x, x1.y, x1.z, x1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                o[j] = pack_bf16x2(fmaf(bf16_lo(rr[j]), sc[c1 + 2 * j], bf16_lo(xx[j])), fmaf(bf16_hi(rr[j]), sc[c1 + 2 * j + 1], bf16_hi(xx[j])));
+            *reinterpret_cast<uint4*>(ob + static_cast<long long>(p1) * ldo + c1) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
@@ -257,11 +325,22 @@ extern "C" int adsr_channel_mean(const void* x, int64_t ld, int B, int HW, int C
     return check_launch();
 }
 
+extern "C" int adsr_channel_mean_parts(const float* chan_part, int B, int parts, int ld_part, int C, int HW, float* mean, const float* w1,
+                                       const float* b1, const float* w2, const float* b2, int Cr, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (C < 1 || C > 128 || parts < 1 || ld_part < C || HW < 1) return ADSR_ERR_BAD_SHAPE;
+    if (w1 != nullptr && (Cr < 1 || Cr > 16 || b1 == nullptr || w2 == nullptr || b2 == nullptr)) return ADSR_ERR_BAD_SHAPE;
+    channel_mean_parts_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(chan_part, parts, ld_part, C, 1.f / static_cast<float>(HW), mean,
+                                                                                 w1, b1, w2, b2, Cr);
+    return check_launch();
+}
+
 extern "C" int adsr_rcab_ca_scale(const void* res, int64_t ldr, const void* x, int64_t ldx, void* out, int64_t ldo,
                                   const float* mean, const float* w1, const float* b1, const float* w2, const float* b2,
                                   int B, int HW, int C, int Cr, void* stream) {
     if (B <= 0) return ADSR_OK;
-    if (C < 8 || C > 128 || (C % 8) || Cr < 1 || Cr > 16 || (ldr % 8) || (ldx % 8) || (ldo % 8)) return ADSR_ERR_BAD_SHAPE;
+    if (C < 8 || C > 128 || (C % 8) || Cr < 0 || Cr > 16 || (ldr % 8) || (ldx % 8) || (ldo % 8)) return ADSR_ERR_BAD_SHAPE;
+    if (static_cast<long long>(HW) * (C / 8) >= (1ll << 31)) return ADSR_ERR_BAD_SHAPE;
     const int slices = std::max(1, std::min(64, HW * (C / 8) / 1024));
     rcab_ca_scale_kernel<<<dim3(slices, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(res), ldr, static_cast<const __nv_bfloat16*>(x), ldx,

@@ -204,9 +204,15 @@ class DRN(nn.Module):
             t1 = torch.empty(rows[p], round_up(c, 16), **bf)
             t2 = torch.empty(rows[p], round_up(c, 16), **bf)
             gap = torch.empty(B, c, dtype=torch.float32, device=dev)
+            n_parts = ops.halo_parts(res[p][0], res[p][1])
+            parts = torch.empty(B * n_parts, round_up(c, 16), dtype=torch.float32, device=dev)
             for r in lvl["rcabs"]:
                 ops.conv3x3(xbuf, B, res[p][0], res[p][1], c, r["c1"], t1, act=ops.ACT_RELU)
-                ops.conv3x3(t1, B, res[p][0], res[p][1], c, r["c2"], t2)
+                # CALayer's pooled mean leaves the second conv's epilogue as per-tile partial sums when the halo kernel covers it
+                if ops.conv3x3(t1, B, res[p][0], res[p][1], c, r["c2"], t2, chan_part=parts):
+                    ops.channel_mean_parts(parts, B, n_parts, c, hw, gap, r["w1"], r["b1"], r["w2"], r["b2"], r["cr"])
+                    ops.rcab_ca_scale(t2, xbuf, xbuf, gap, r["w1"], r["b1"], r["w2"], r["b2"], B, hw, c, 0)     # gap = the scales
+                    continue
                 ops.channel_mean(t2, B, hw, c, gap)
                 ops.rcab_ca_scale(t2, xbuf, xbuf, gap, r["w1"], r["b1"], r["w2"], r["b2"], B, hw, c, r["cr"])
             shuf = torch.empty(rows[p - 1], round_up(c, 16), **bf)

@@ -131,8 +131,10 @@ def swin_attn(x: torch.Tensor, pa, table: torch.Tensor, out: torch.Tensor, b: in
 
 def conv3x3(x: torch.Tensor, b: int, h: int, wd: int, cin: int, w: PackedWeight, out: torch.Tensor, *, stride: int = 1,
             act: int = ACT_NONE, slope: float = 0.0, alpha: float = 1.0, res: Optional[torch.Tensor] = None,
-            out_mode: int = OUT_ROWS, n_store: Optional[int] = None, ocol0: int = 0) -> None:
-    """x: [b*h*wd, ld] NHWC bf16 -> out rows (b*ho*wo) [at column ocol0] or pixel-shuffled [b, 2h, 2w, N/4]."""
+            out_mode: int = OUT_ROWS, n_store: Optional[int] = None, ocol0: int = 0, chan_part: Optional[torch.Tensor] = None) -> bool:
+    """x: [b*h*wd, ld] NHWC bf16 -> out rows (b*ho*wo) [at column ocol0] or pixel-shuffled [b, 2h, 2w, N/4].
+    chan_part: optional fp32 [b * halo_parts(h, wd), round16(N)] scratch; returns True when the halo-tile kernel ran and filled it
+    with per-image partial column sums (channel_mean_parts turns them into CALayer's pooled means)."""
     _cuda(x, "x")
     n_store = (w.N + 15) // 16 * 16 if n_store is None else n_store
     _t = _begin()
@@ -141,16 +143,32 @@ def conv3x3(x: torch.Tensor, b: int, h: int, wd: int, cin: int, w: PackedWeight,
             and n_store <= wc.BN and n_store % 8 == 0 and ocol0 % 8 == 0 and act in (ACT_NONE, ACT_RELU, ACT_LRELU)):
         # narrow layer: halo tile + resident weights (csrc/conv_halo.cu); BAD_SHAPE = does not fit the SM, fall through
         st = lib().adsr_conv3x3_halo_bf16(ptr(x), x.stride(0), b, h, wd, cin, ptr(wc.data), ptr(wc.bias), wc.N, wc.BN, act, slope,
-                                          ptr(out), out.stride(0), ocol0, n_store, _abi.num_sms(), stream_ptr())
+                                          ptr(out), out.stride(0), ocol0, n_store, ptr(chan_part), _abi.num_sms(), stream_ptr())
         if st != 1:                       # ADSR_ERR_BAD_SHAPE
             check(st, "adsr_conv3x3_halo_bf16")
             _count("conv3x3_halo", 2.0 * b * h * wd * 9 * cin * w.N, _t)
-            return
+            return chan_part is not None
     check(lib().adsr_conv3x3_igemm_bf16(ptr(x), x.stride(0), b, h, wd, cin, stride, ptr(w.data), ptr(w.bias), w.N, w.BN,
                                         w.n_tiles, act, slope, alpha, ptr(res), res.stride(0) if res is not None else 0,
                                         ptr(out), out.stride(0), ocol0, out_mode, n_store, _abi.num_sms(), stream_ptr()),
           "adsr_conv3x3_igemm_bf16")
     _count("conv3x3", 2.0 * b * (-(-h // stride)) * (-(-wd // stride)) * 9 * cin * w.N, _t)
+    return False
+
+
+def halo_parts(h: int, wd: int) -> int:
+    """Partial-sum rows per image written by the halo conv: 4 row quadrants per 128-position tile of the padded raster."""
+    return 4 * ((h * (wd + 2) + 127) // 128)
+
+
+def channel_mean_parts(part: torch.Tensor, b: int, parts: int, c: int, hw: int, mean: torch.Tensor, w1=None, b1=None, w2=None, b2=None,
+                       cr: int = 0) -> None:
+    """mean [b, c] <- pooled means from the halo conv's partial sums; with the CALayer weights given: the sigmoid scales instead
+    (pass them to rcab_ca_scale with cr=0)."""
+    _t = _begin()
+    check(lib().adsr_channel_mean_parts(ptr(part), b, parts, part.stride(0), c, hw, ptr(mean), ptr(w1), ptr(b1), ptr(w2), ptr(b2), cr,
+                                        stream_ptr()), "adsr_channel_mean_parts")
+    _count("channel_mean_parts", 0.0, _t)
 
 
 def layernorm_rows(x: torch.Tensor, out: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, c: int, eps: float = 1e-5,

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 8
+#define ADSR_ABI_VERSION 9
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -129,11 +129,19 @@ int adsr_conv3x3_igemm_bf16(const void* in, int64_t ld_in, int B, int Hin, int W
 /* ---- halo-tile 3x3 convolution (pad 1, stride 1) with weights resident in shared memory ----------------
  * replaces the two default_conv of every RCAB (src/drn.py:143-158; 80 -> 80 channels in DRN-L): Cin <= 128, Cout <= 128,
  * 8 <= W <= 126, plain-row output with bias and optional ReLU / LeakyReLU.  `w_compact` is the K-concatenated image of
- * pack.pack_conv3x3_weight(...).compact.  ADSR_ERR_BAD_SHAPE = shape not covered (use adsr_conv3x3_igemm_bf16). */
+ * pack.pack_conv3x3_weight(...).compact.  ADSR_ERR_BAD_SHAPE = shape not covered (use adsr_conv3x3_igemm_bf16).
+ * chan_part (nullable): fp32 [B * parts, BN], parts = 4 * ceil(H * (W + 2) / 128): per-image partial column sums of the outputs
+ * (fp32, before the bf16 rounding), the input of adsr_channel_mean_parts -- CALayer's AdaptiveAvgPool2d(1) (src/drn.py:126, 137)
+ * without a second pass over the conv output. */
 int adsr_conv3x3_halo_bf16(const void* in, int64_t ld_in, int B, int H, int W, int Cin,
                            const void* w_compact, const float* bias_padded, int N, int BN,
                            int act, float slope, void* out, int64_t ldo, int ocol0, int n_store,
-                           int num_sms, void* stream);
+                           float* chan_part, int num_sms, void* stream);
+/* mean[b, c] = (sum over the `parts` partial rows of image b) / HW, summed in a fixed order (deterministic).  With w1 != NULL the
+ * kernel continues with CALayer's conv_du (src/drn.py:128-133) and writes sigmoid(W2 relu(W1 mean + b1) + b2) into `mean` instead:
+ * adsr_rcab_ca_scale then takes that buffer with Cr = 0 (scales given, no per-block MLP). */
+int adsr_channel_mean_parts(const float* chan_part, int B, int parts, int ld_part, int C, int HW, float* mean,
+                            const float* w1, const float* b1, const float* w2, const float* b2, int Cr, void* stream);
 
 /* ---- LayerNorm over the first C columns of each row (eps, affine); writes round16(C) columns ---------
  * replaces nn.LayerNorm norm1 / norm2 / final norm (src/drct.py:432, 438, 833, 881). */

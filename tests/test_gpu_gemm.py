@@ -165,9 +165,13 @@ def test_conv_halo_tile_kernel(B, H, W, Cin, Cout, act):
     code = {"none": ops.ACT_NONE, "lrelu": ops.ACT_LRELU, "relu": ops.ACT_RELU}[act]
     n_store = (Cout + 15) // 16 * 16
     out = torch.full((B * H * W, n_store + 24), -3.0, device=DEV, dtype=torch.bfloat16)
+    n_parts = ops.halo_parts(H, W)
+    parts = torch.full((B * n_parts, wc.BN), float("nan"), device=DEV)           # every entry must be written
     st = abi.lib().adsr_conv3x3_halo_bf16(abi.ptr(x), x.stride(0), B, H, W, Cin, abi.ptr(wc.data), abi.ptr(wc.bias), wc.N, wc.BN, code,
-                                          0.1, abi.ptr(out), out.stride(0), 8, n_store, abi.num_sms(), abi.stream_ptr())
+                                          0.1, abi.ptr(out), out.stride(0), 8, n_store, abi.ptr(parts), abi.num_sms(), abi.stream_ptr())
     assert st == 0, f"status {st}"
+    mean = torch.zeros(B, Cout, device=DEV)
+    ops.channel_mean_parts(parts, B, n_parts, Cout, H * W, mean)
     torch.cuda.synchronize()
     xin = x[:, :Cin].float().view(B, H, W, Cin).permute(0, 3, 1, 2)
     want = F.conv2d(xin, bf16_round(w), bias, padding=1)
@@ -175,6 +179,19 @@ def test_conv_halo_tile_kernel(B, H, W, Cin, Cout, act):
     got = out[:, 8:8 + Cout].float().view(B, H, W, Cout).permute(0, 3, 1, 2)
     err = rel_err(got, want)
     assert err < 0.012, f"halo conv rel err {err}"
+    # pooled means from the epilogue's partial sums (fp32 values before the bf16 rounding): AdaptiveAvgPool2d(1) of the output
+    want_mean = want.mean(dim=(2, 3))
+    assert float((mean - want_mean).abs().max()) < 2e-3 * max(1.0, float(want_mean.abs().max())), "pooled mean"
+    assert bool(torch.isfinite(parts).all())
+    # the same kernel continuing with CALayer's squeeze-excite MLP: sigmoid(W2 relu(W1 mean + b1) + b2)   (src/drn.py:128-139)
+    cr = max(1, Cout // 16)
+    w1, b1 = torch.randn(cr, Cout, device=DEV) * 0.3, torch.randn(cr, device=DEV) * 0.1
+    w2, b2 = torch.randn(Cout, cr, device=DEV) * 0.3, torch.randn(Cout, device=DEV) * 0.1
+    scale = torch.zeros(B, Cout, device=DEV)
+    ops.channel_mean_parts(parts, B, n_parts, Cout, H * W, scale, w1, b1, w2, b2, cr)
+    torch.cuda.synchronize()
+    want_scale = torch.sigmoid(F.relu(mean @ w1.t() + b1) @ w2.t() + b2)
+    assert float((scale - want_scale).abs().max()) < 1e-5
     assert bool((out[:, :8] == -3.0).all()) and bool((out[:, 8 + n_store:] == -3.0).all())
     assert bool((out[:, 8 + Cout:8 + n_store] == 0).all())                      # padded output channels: zero weights, zero bias
     # the streaming kernel computes the same sums in a different K order: equal to bf16 rounding

@@ -15,7 +15,7 @@ for tap in [4, 0, 5, 7]:
     pw = pack.pack_conv3x3_weight(w, None).compact
     out = torch.full((B * H * W, C), -1.0, device="cuda", dtype=torch.bfloat16)
     st = abi.lib().adsr_conv3x3_halo_bf16(abi.ptr(x), C, B, H, W, C, abi.ptr(pw.data), abi.ptr(pw.bias), C, C, 0, 0.0, abi.ptr(out), C, 0, C,
-                                          abi.num_sms(), abi.stream_ptr())
+                                          0, abi.num_sms(), abi.stream_ptr())
     torch.cuda.synchronize()
     dy, dx = tap // 3 - 1, tap % 3 - 1
     got = out[:, 0].float().view(H, W)
