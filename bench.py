@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 PKG = "anomaly-detection-super-resolution_b200"
 METRIC = "DRCT-L x4 128px HR images/sec (inference+scoring)"
 DOMINANT_KERNEL_NAMES = {"swin_attn": "swin_attn_kernel", "swin_mlp": "swin_mlp_kernel", "tc_gemm": "tc_gemm_rows_kernel",
-                         "window_attention": "window_attn_tc_kernel", "conv3x3": "tc_gemm_manual_kernel"}
+                         "window_attention": "window_attn_tc_kernel", "conv3x3": "tc_gemm_manual_kernel", "conv3x3_halo": "conv_halo_kernel"}
 HR, SCALE, NC = 128, 4, 3
 
 
@@ -328,7 +328,7 @@ def main():
 
     # ---- roofline of the dominant (tcgen05) kernels: per-launch CUDA events in one extra, untimed step
     roofline = None
-    TENSOR_KINDS = ("tc_gemm", "conv3x3", "swin_mlp", "swin_attn")
+    TENSOR_KINDS = ("tc_gemm", "conv3x3", "conv3x3_halo", "swin_mlp", "swin_attn")
     if rank == 0:
         ops.PROFILE = []
         barrier() if world == 1 else torch.cuda.synchronize()
