@@ -183,16 +183,31 @@ __global__ void __launch_bounds__(1024) channel_mean_parts_kernel(const float* _
     __shared__ float red[8][128];
     __shared__ float hid[16];
     const int b = blockIdx.x, c = threadIdx.x & 127, g = threadIdx.x >> 7;      // 8 groups take every 8th partial row
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the MLP weights do not depend on the sums: fetch them first so that the kernel is two L2 round trips, not seven
+    float w1v[4] = {0.f, 0.f, 0.f, 0.f}, w2v[16], b1v = 0.f, b2v = 0.f;
+    const bool mlp = w1 != nullptr;
+    if (mlp && warp < Cr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (lane + 32 * k < C) w1v[k] = w1[warp * C + lane + 32 * k];
+        b1v = b1[warp];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w2v[j] = (mlp && g == 0 && c < C && j < Cr) ? w2[c * Cr + j] : 0.f;
+    if (mlp && g == 0 && c < C) b2v = b2[c];
     float acc = 0.f;
     if (c < C) {
         const float* p = part + static_cast<long long>(b) * parts * ld + c;
-        int i = g;
-        for (; i + 24 < parts; i += 32) {                                       // four independent loads in flight per thread
-            const float v0 = p[static_cast<long long>(i) * ld], v1 = p[static_cast<long long>(i + 8) * ld];
-            const float v2 = p[static_cast<long long>(i + 16) * ld], v3 = p[static_cast<long long>(i + 24) * ld];
-            acc += (v0 + v1) + (v2 + v3);
+        float v[24];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) {                                          // up to 192 partial rows with every load in flight at once
+            const int i = g + 8 * k;
+            v[k] = i < parts ? p[static_cast<long long>(i) * ld] : 0.f;
         }
-        for (; i < parts; i += 8) acc += p[static_cast<long long>(i) * ld];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) acc += v[k];
+        for (int i = g + 192; i < parts; i += 8) acc += p[static_cast<long long>(i) * ld];
     }
     red[g][c] = acc;
     __syncthreads();
@@ -201,23 +216,26 @@ __global__ void __launch_bounds__(1024) channel_mean_parts_kernel(const float* _
 #pragma unroll
         for (int j = 0; j < 8; ++j) t += red[j][c];
         t *= inv_hw;
-        if (w1 == nullptr) mean[static_cast<long long>(b) * C + c] = t;
+        if (!mlp) mean[static_cast<long long>(b) * C + c] = t;
         red[0][c] = t;
     }
-    if (w1 == nullptr) return;
+    if (!mlp) return;
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp < Cr) {                                                            // one warp per hidden unit
         float a = 0.f;
-        for (int k = lane; k < C; k += 32) a = fmaf(w1[warp * C + k], red[0][k], a);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (lane + 32 * k < C) a = fmaf(w1v[k], red[0][lane + 32 * k], a);
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) hid[warp] = fmaxf(a + b1[warp], 0.f);
+        if (lane == 0) hid[warp] = fmaxf(a + b1v, 0.f);
     }
     __syncthreads();
     if (g == 0 && c < C) {
-        float a = b2[c];
-        for (int j = 0; j < Cr; ++j) a = fmaf(w2[c * Cr + j], hid[j], a);
+        float a = b2v;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < Cr) a = fmaf(w2v[j], hid[j], a);
         mean[static_cast<long long>(b) * C + c] = 1.f / (1.f + __expf(-a));
     }
 }
