@@ -499,12 +499,23 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
 
         // task order mirrors the MMA streams: chunk 0 of tile it+1 is turned around BEFORE the last epilogue of tile it
         // (fc1 runs ahead of fc2, so that chunk is ready while the last fc2 MMAs of tile it are still in flight)
+        // the (sum, sumsq) slots of a row were written by the previous kernel: fetched cold they cost ~2k cycles of exposed latency per
+        // tile (clock64 timeline), so the lines of tile it + 1 are pulled into L1 while the chunks of tile it are converted
+        auto prefetch_stats = [&](int it) {
+            const int row = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128 + r_in_tile;
+            if (grp == 0 && row < p.M) {
+                const char* sp = reinterpret_cast<const char*>(p.stats_in + static_cast<long long>(row) * p.stats_in_stride);
+                for (int o = 0; o < p.stats_in_slots * 8; o += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + o));
+            }
+        };
         float rstd = 1.f, nrm = 0.f;
         if (my_tiles > 0) {
+            if (my_tiles > 1) prefetch_stats(1);
             row_stats(0, rstd, nrm);
             epi1(0, 0, rstd, nrm);
         }
         for (int it = 0; it < my_tiles; ++it) {
+            if (it > 0 && it + 1 < my_tiles) prefetch_stats(it + 1);
             for (int j = 1; j < p.nc; ++j) epi1(it, j, rstd, nrm);
             if (p.fuse_adj && it > 0) epi3(it - 1);                   // its MMAs were issued right after epi2(it - 1)
             if (it + 1 < my_tiles) {
