@@ -521,6 +521,16 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 }
             }
             if (grp == 0) s_tok[mb * 128 + r] = tok;
+            if (grp == 1 && it + 1 < my_tiles) {
+                // the (sum, sumsq) slots of my row in the NEXT tile: fetched cold at the tile start they cost ~2k cycles of exposed
+                // latency, so their line is pulled into L1 a whole tile ahead (same closed-form token map)
+                const int win = (tile + static_cast<int>(gridDim.x)) * 2 + (r >> 6);
+                const int b = win / nW, w = win - b * nW;
+                int y = (w / nwx) * 8 + ny + p.shift; if (y >= p.H) y -= p.H;
+                int x = (w % nwx) * 8 + nx + p.shift; if (x >= p.W) x -= p.W;
+                const char* np_ = reinterpret_cast<const char*>(p.stats_in + static_cast<long long>((b * p.H + y) * p.W + x) * p.stats_in_stride);
+                for (int o = 0; o < p.stats_in_slots * 8; o += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(np_ + o));
+            }
             float rstd, nrm;
             {
                 const float2* sp = p.stats_in + static_cast<long long>(tok) * p.stats_in_stride;
