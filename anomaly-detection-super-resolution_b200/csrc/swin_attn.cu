@@ -372,22 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     mbar_wait(&bars->qkv_ready, par);
                     tr_ev<TRACE>(p.trace, 0, it, h, 2);
                     issue_s();
-                    const bool acc_sep = p.col_acc >= 0;               // q|k|v has its own accumulator columns (spare TMEM): the next
-                    if (acc_sep && next_in_tile) {                     // head's q|k|v need not wait for P V, it runs under the softmax
-                        qkv_begin(g + 1, next_in_tile ? h + 1 : 0);
-                        qkv_finish();
-                    }
-                    mbar_wait(&bars->p_ready, par);
-                    tr_ev<TRACE>(p.trace, 0, it, h, 3);
-                    issue_pv();
-                    tr_ev<TRACE>(p.trace, 0, it, h, 4);
-                    if (!acc_sep && next_in_tile) {
-                        qkv_begin(g + 1, next_in_tile ? h + 1 : 0);
-                        qkv_finish();
-                    }
-                    tr_ev<TRACE>(p.trace, 0, it, h, 1);
-                    ensure_o(g);
-                    if (h == 0) {
+                    if (h == 0) {   // issued under the softmax of head 0: the MMA warp and the tensor pipe are idle then (it used to delay S of head 1)
                         // the accumulator starts as the shortcut: Y[:, 16 g .. 16 g + 15] = x[:, same columns] * I (x tile still
                         // resident; bf16 values enter the fp32 accumulator exactly), the proj MMAs of every head accumulate on top
                         mbar_wait(&bars->proj_free, (static_cast<uint32_t>(it) & 1) ^ 1);
@@ -404,6 +389,21 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                         }
                         __syncwarp();
                     }
+                    const bool acc_sep = p.col_acc >= 0;               // q|k|v has its own accumulator columns (spare TMEM): the next
+                    if (acc_sep && next_in_tile) {                     // head's q|k|v need not wait for P V, it runs under the softmax
+                        qkv_begin(g + 1, next_in_tile ? h + 1 : 0);
+                        qkv_finish();
+                    }
+                    mbar_wait(&bars->p_ready, par);
+                    tr_ev<TRACE>(p.trace, 0, it, h, 3);
+                    issue_pv();
+                    tr_ev<TRACE>(p.trace, 0, it, h, 4);
+                    if (!acc_sep && next_in_tile) {
+                        qkv_begin(g + 1, next_in_tile ? h + 1 : 0);
+                        qkv_finish();
+                    }
+                    tr_ev<TRACE>(p.trace, 0, it, h, 1);
+                    ensure_o(g);
                     uint32_t dcol = 0;
                     for (int pc = 0; pc < p.n_pp; ++pc) {
                         mbar_wait(&bars->p_full[pslot], pph);
