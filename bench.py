@@ -144,17 +144,21 @@ def load_peaks() -> dict:
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_step(O, S, sd, cfg, lr_f: torch.Tensor, hr_u8: np.ndarray, wss):
     with torch.no_grad():
-        sr = O.drct_forward(sd, lr_f, cfg)
+        sr = O.drct_forward(sd, lr_f, cfg) if hasattr(O, "drct_forward") else O.drn_forward(sd, lr_f, cfg)[-1]
     sr_u8 = S.quantize_u8(sr.numpy(), 255.0)
     return S.score_images(list(sr_u8), list(hr_u8), wss)
 
 
-def cpu_setup(n: int):
-    from oracle import drct_oracle as O
+def cpu_setup(n: int, workload: str = "drct-l"):
     from oracle import scoring_oracle as S
+    if workload == "drct-l":
+        from oracle import drct_oracle as O
+        cfg = O.DrctCfg()
+    else:
+        from oracle import drn_oracle as O
+        cfg = O.DrnCfg()
 
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = O.DrctCfg()
     sd = O.make_state_dict(cfg, seed=1)
     hr, lr, _ = synthetic_pairs(n)
     return O, S, sd, cfg, to_float_nchw(lr), hr, S.window_sizes_for(HR)
@@ -164,7 +168,9 @@ def run_reference_arm(args, rank: int, emit):
     if rank != 0:
         return
     n = args.cpu_sample
-    O, S, sd, cfg, lr_f, hr, wss = cpu_setup(n)
+    O, S, sd, cfg, lr_f, hr, wss = cpu_setup(n, args.workload)
+    drct_wl = args.workload == "drct-l"
+    name = "DRCT-L" if drct_wl else "DRN-L"
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_step(O, S, sd, cfg, lr_f, hr, wss)
     t0 = time.perf_counter()
@@ -174,12 +180,13 @@ def run_reference_arm(args, rank: int, emit):
     value = n * args.steps / dt
     cores = torch.get_num_threads()
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC if drct_wl else "DRN-L x4 128px HR images/sec (inference+scoring)", "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "configs[2]: DRCT-L x4 RGB 32->128 px, inference + scoring", "images_per_step": n},
+        "config": {"workload": ("configs[2]: DRCT-L" if drct_wl else "configs[1]: DRN-L") + " x4 RGB 32->128 px, inference + scoring",
+                   "images_per_step": n},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} images/step x {args.steps} steps: oracle DRCT-L fp32 forward (torch CPU, {cores} threads) "
+                         "sample": f"{n} images/step x {args.steps} steps: oracle {name} fp32 forward (torch CPU, {cores} threads) "
                                    "+ vectorised box-SSIM sweep/MSE/PSNR (numpy); the reference's own ssim_numpy is a Python "
                                    "loop ~100x slower than this port"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -369,9 +376,9 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only): oracle port on a bounded sample
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "drct-l":
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = args.cpu_sample
-        O, S, sd, cfg, lr_f, hr_np, wss_c = cpu_setup(n)
+        O, S, sd, cfg, lr_f, hr_np, wss_c = cpu_setup(n, args.workload)
         cpu_step(O, S, sd, cfg, lr_f, hr_np, wss_c)
         t0 = time.perf_counter()
         reps_c = 3
@@ -380,7 +387,8 @@ def main():
         dtc = time.perf_counter() - t0
         cores = torch.get_num_threads()
         cpu_baseline = {"value": n * reps_c / dtc, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"{n} images x {reps_c} passes: oracle DRCT-L fp32 forward (torch CPU, {cores} threads) + "
+                        "sample": f"{n} images x {reps_c} passes: oracle {'DRCT-L' if args.workload == 'drct-l' else 'DRN-L'} fp32 forward "
+                                  f"(torch CPU, {cores} threads) + "
                                   "vectorised SSIM sweep/MSE/PSNR (numpy)"}
 
     if rank == 0:
