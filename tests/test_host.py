@@ -51,6 +51,41 @@ def test_pack_gemm_layout_roundtrip():
     assert img[0, :, 40:].abs().sum() == 0 and pw.bias[39] == 39 and pw.bias[40:].abs().sum() == 0
 
 
+def test_pack_conv3x3_compact_twin_layout():
+    """K-concatenated weight image of the halo-tile conv (csrc/conv_halo.cu): K index = tap * round16(Cin) + channel, one N tile of
+    round16(Cout) rows in 64-column slabs with the 128-byte swizzle; absent when the weights cannot stay resident in shared memory."""
+    pack = importlib.import_module(PKG + ".pack")
+    ops = importlib.import_module(PKG + ".ops")
+    assert ops.halo_parts(64, 64) == 4 * 33 and ops.halo_parts(32, 32) == 4 * 9      # 4 row quadrants per 128-position tile
+    torch.manual_seed(3)
+    w, b = torch.randn(80, 80, 3, 3), torch.randn(80)
+    pw = pack.pack_conv3x3_weight(w, b)
+    c = pw.compact
+    assert c is not None and c.BN == 80 and c.n_tiles == 1 and c.k_stages == 12 and c.N == 80 and c.K == 80
+    assert torch.equal(c.bias[:80], b) and c.data.numel() == 12 * 80 * 128
+    img = c.data.view(torch.bfloat16).view(1, c.k_stages, c.BN, 8, 8)
+    wb = w.to(torch.bfloat16)
+    for (n, ci, ky, kx) in [(0, 0, 0, 0), (79, 79, 2, 2), (17, 64, 1, 0), (5, 3, 0, 2), (42, 31, 2, 1)]:
+        k = (ky * 3 + kx) * 80 + ci
+        s, kk = divmod(k, 64)
+        chunk, e = divmod(kk, 8)
+        assert img[0, s, n, chunk ^ (n % 8), e] == wb[n, ci, ky, kx]
+    # K tail of the last slab (720 .. 767) is zero
+    flat = torch.zeros(80, 768)
+    for s in range(12):
+        for chunk in range(8):
+            rows = torch.arange(80)
+            flat[rows, s * 64 + chunk * 8:s * 64 + chunk * 8 + 8] = img[0, s, rows, chunk ^ (rows % 8)].float()
+    assert flat[:, 720:].abs().sum() == 0
+    assert torch.equal(flat[:, :720].view(80, 9, 80), wb.permute(0, 2, 3, 1).reshape(80, 9, 80).float())
+    # channel padding to 16 per tap
+    c2 = pack.pack_conv3x3_weight(torch.randn(48, 40, 3, 3), None).compact
+    assert c2 is not None and c2.BN == 48 and c2.k_stages == (9 * 48 + 63) // 64
+    # too wide to stay resident / too many channels: no twin, the streaming kernel is used
+    assert pack.pack_conv3x3_weight(torch.randn(256, 64, 3, 3), None).compact is None
+    assert pack.pack_conv3x3_weight(torch.randn(64, 180, 3, 3), None).compact is None
+
+
 def test_pack_qkv_head_padding():
     pack = importlib.import_module(PKG + ".pack")
     c, heads = 212, 4            # head_dim 53 -> padded to 64
