@@ -33,7 +33,7 @@ constexpr int kGuardBytes = 1024;             // the most negative tap shift of 
 constexpr int kSmemLimit = 232448;
 
 struct __align__(8) HaloBarriers {
-    uint64_t w_full[3], a_full[2], a_empty[2];   // weights arrive in three slab groups: the first tile starts on the first third
+    uint64_t w_full, a_full[2], a_empty[2];
     uint64_t acc_full[2], acc_free[2];
     uint32_t tmem_base;
 };
@@ -55,8 +55,7 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw32(uint32_t smem_addr) {
 // TAIL: the last K = 16 step of every tap reads the 32-byte-swizzled tail panel (descriptor t0, rows 2 units apart).
 template <int K16, bool TAIL>
 __device__ __forceinline__ void issue_tile(uint64_t a0, uint64_t t0, int wh, uint32_t pan_u, uint64_t b0, uint32_t slab_u, uint32_t d,
-                                           uint32_t idesc, uint64_t* w_full, bool first) {
-    constexpr int kSlabs = (9 * K16 + 3) / 4, kGroup = (kSlabs + 2) / 3;      // slabs per weight group (see the loader)
+                                           uint32_t idesc) {
     const uint32_t a_hi = static_cast<uint32_t>(a0 >> 32), a_lo = static_cast<uint32_t>(a0);
     const uint32_t t_hi = static_cast<uint32_t>(t0 >> 32), t_lo = static_cast<uint32_t>(t0);
     const uint32_t b_hi = static_cast<uint32_t>(b0 >> 32), b_lo = static_cast<uint32_t>(b0);
@@ -67,7 +66,6 @@ __device__ __forceinline__ void issue_tile(uint64_t a0, uint64_t t0, int wh, uin
 #pragma unroll
         for (int c = 0; c < K16; ++c) {
             const int idx = tap * K16 + c;
-            if ((idx & 3) == 0 && (idx >> 2) % kGroup == 0 && first) mbar_wait(&w_full[(idx >> 2) / kGroup], 0);   // first tile only
             const uint32_t bl = b_lo + static_cast<uint32_t>(idx >> 2) * slab_u + static_cast<uint32_t>((idx & 3) * 2);
             const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | bl;
             if (TAIL && c == K16 - 1) {
@@ -97,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     for (int i = threadIdx.x; i < 128; i += kThreads) s_bias[i] = i < p.BN ? p.bias[i] : 0.f;
     if (warp == 1 && lane == 0) {
-        for (int b = 0; b < 3; ++b) mbar_init(&bars->w_full[b], 1);
+        mbar_init(&bars->w_full, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->a_full[b], 1);
             mbar_init(&bars->a_empty[b], 1);
@@ -120,13 +118,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         }
         if (elect_one_sync()) {
             const uint32_t slab_bytes = static_cast<uint32_t>(p.BN) * 128u;
-            const int group = (p.slabs + 2) / 3;
-            for (int g = 0; g < 3; ++g) {
-                const int s0 = g * group, s1 = min(p.slabs, s0 + group);
-                mbar_arrive_expect_tx(&bars->w_full[g], static_cast<uint32_t>(max(s1 - s0, 0)) * slab_bytes);
-                for (int i = s0; i < s1; ++i)
-                    bulk_g2s(w_s + static_cast<size_t>(i) * slab_bytes, p.wp + static_cast<size_t>(i) * slab_bytes, slab_bytes, &bars->w_full[g]);
-            }
+            mbar_arrive_expect_tx(&bars->w_full, static_cast<uint32_t>(p.slabs) * slab_bytes);
+            for (int i = 0; i < p.slabs; ++i) bulk_g2s(w_s + static_cast<size_t>(i) * slab_bytes, p.wp + static_cast<size_t>(i) * slab_bytes, slab_bytes, &bars->w_full);
         }
         __syncwarp();
         const uint32_t tx_bytes = static_cast<uint32_t>(p.full_panels * p.box_bytes + p.tail * p.tail_box_bytes);
@@ -152,6 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         const uint32_t a_base = smem_u32(a_s), t_base = smem_u32(t_s);
         const uint64_t b0 = umma_desc_k_sw128(smem_u32(w_s));
         const uint32_t slab_u = static_cast<uint32_t>(p.BN) * 8u, pan_u = static_cast<uint32_t>(p.panel_bytes) >> 4;   // 16-byte units
+        mbar_wait(&bars->w_full, 0);
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
             const int b = tile / p.tiles_per_img, t = tile - b * p.tiles_per_img;
@@ -170,17 +164,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 const uint64_t a0 = umma_desc_k_sw128(a_base + static_cast<uint32_t>(s * full_bytes + row0 * 128));
                 const uint64_t t0 = umma_desc_k_sw32(t_base + static_cast<uint32_t>(s * p.tail_bytes + row0 * 32));
                 if (p.tail) {
-                    issue_tile<5, true>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc, bars->w_full, it == 0);
+                    issue_tile<5, true>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc);
                 } else {
                     switch (p.k16_per_tap) {
-                        case 1: issue_tile<1, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc, bars->w_full, it == 0); break;
-                        case 2: issue_tile<2, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc, bars->w_full, it == 0); break;
-                        case 3: issue_tile<3, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc, bars->w_full, it == 0); break;
-                        case 4: issue_tile<4, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc, bars->w_full, it == 0); break;
-                        case 5: issue_tile<5, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc, bars->w_full, it == 0); break;
-                        case 6: issue_tile<6, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc, bars->w_full, it == 0); break;
-                        case 7: issue_tile<7, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc, bars->w_full, it == 0); break;
-                        default: issue_tile<8, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc, bars->w_full, it == 0); break;
+                        case 1: issue_tile<1, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc); break;
+                        case 2: issue_tile<2, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc); break;
+                        case 3: issue_tile<3, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc); break;
+                        case 4: issue_tile<4, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc); break;
+                        case 5: issue_tile<5, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc); break;
+                        case 6: issue_tile<6, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc); break;
+                        case 7: issue_tile<7, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc); break;
+                        default: issue_tile<8, false>(a0, t0, p.Wh, pan_u, b0, slab_u, d, idesc); break;
                     }
                 }
                 umma_commit(&bars->a_empty[s]);
