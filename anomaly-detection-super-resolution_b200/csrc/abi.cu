@@ -1,9 +1,20 @@
+#include <cstdlib>
 // extern "C" entry points that only marshal arguments (the kernels live in the other .cu files).
 #include "adsr_kernels.h"
 
 using namespace adsr;
 
 extern "C" int adsr_abi_version(void) { return ADSR_ABI_VERSION; }
+
+namespace adsr {
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("ADSR_PDL");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    return on;
+}
+}  // namespace adsr
 
 extern "C" const char* adsr_status_string(int status) {
     switch (status) {

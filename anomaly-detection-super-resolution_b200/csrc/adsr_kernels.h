@@ -9,6 +9,30 @@
 
 namespace adsr {
 
+// Programmatic dependent launch (PDL): the kernel may become resident while the previous kernel of the stream is still draining; it
+// must execute pdl_wait() before touching anything the previous kernel wrote (or still reads).  Used by the three kernels of DRN's
+// RCAB chain (320 of the 333 launches of a DRN-L step), whose prologues (barrier init, TMEM allocation, resident weights) then
+// overlap the tail of their predecessor.  ADSR_PDL=0 in the environment falls back to plain stream order.
+bool pdl_enabled();
+template <typename Kernel, typename... Args>
+inline cudaError_t launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 struct TcGemmParams {
     CUtensorMap tmap_a;    // GEMM mode: [M rows x K cols] bf16, box 128 x 64, 128-byte swizzle (first: 64 B aligned)
     CUtensorMap tmap_out;  // TMA epilogue: output  [M x (ocol0 + n_store)], box 32 x 32, 64-byte swizzle

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = bars->tmem_base;
+    pdl_launch_dependents();                                            // the next kernel's prologue may overlap my tail
 
     if (warp == 0) {
         // ============================================================ loader: weights once, then one halo tile per tile
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             for (int i = 0; i < p.slabs; ++i) bulk_g2s(w_s + static_cast<size_t>(i) * slab_bytes, p.wp + static_cast<size_t>(i) * slab_bytes, slab_bytes, &bars->w_full);
         }
         __syncwarp();
+        pdl_wait();                                                     // the input image is the previous kernel's output
         const uint32_t tx_bytes = static_cast<uint32_t>(p.full_panels * p.box_bytes + p.tail * p.tail_box_bytes);
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
@@ -296,8 +298,9 @@ int launch_conv_halo(ConvHaloParams& p, const void* in, long long ld_in, int num
     if (p.tail && encode_tmap_nhwc_box3_bf16(&p.tmap_tail, in, p.B, p.H, p.W, k8, ld_in, 16, p.Wh, p.box_rows) != ADSR_OK) return ADSR_ERR_CUDA;
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     if (cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
-    conv_halo_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
-    return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
+    // every global access that depends on (or could disturb) the previous kernel sits behind the loader's pdl_wait(): the A tiles,
+    // hence the MMAs, hence the epilogue's stores
+    return launch_pdl(conv_halo_kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem_bytes), stream, p) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
 }
 
 #if HALO_TRACE

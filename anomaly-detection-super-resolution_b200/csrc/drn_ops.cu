@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(1024) channel_mean_parts_kernel(const float* _
 #pragma unroll
     for (int j = 0; j < 16; ++j) w2v[j] = (mlp && g == 0 && c < C && j < Cr) ? w2[c * Cr + j] : 0.f;
     if (mlp && g == 0 && c < C) b2v = b2[c];
+    pdl_launch_dependents();
+    pdl_wait();                                                                 // the partial sums are the previous kernel's output
     float acc = 0.f;
     if (c < C) {
         const float* p = part + static_cast<long long>(b) * parts * ld + c;
@@ -250,6 +252,8 @@ __global__ void __launch_bounds__(256) rcab_ca_scale_kernel(const __nv_bfloat16*
     __shared__ float hid[16];
     __shared__ float sc[128];
     const int b = blockIdx.y;
+    pdl_launch_dependents();
+    pdl_wait();                                             // mean / res / x come from the previous kernels
     if (Cr == 0) {                                          // `mean` already holds the scales (channel_mean_parts with the MLP)
         if (threadIdx.x < C) sc[threadIdx.x] = mean[static_cast<long long>(b) * C + threadIdx.x];
     } else if (threadIdx.x < Cr) {
@@ -348,9 +352,8 @@ extern "C" int adsr_channel_mean_parts(const float* chan_part, int B, int parts,
     if (B <= 0) return ADSR_OK;
     if (C < 1 || C > 128 || parts < 1 || ld_part < C || HW < 1) return ADSR_ERR_BAD_SHAPE;
     if (w1 != nullptr && (Cr < 1 || Cr > 16 || b1 == nullptr || w2 == nullptr || b2 == nullptr)) return ADSR_ERR_BAD_SHAPE;
-    channel_mean_parts_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(chan_part, parts, ld_part, C, 1.f / static_cast<float>(HW), mean,
-                                                                                 w1, b1, w2, b2, Cr);
-    return check_launch();
+    return launch_pdl(channel_mean_parts_kernel, dim3(B), dim3(1024), 0, static_cast<cudaStream_t>(stream), chan_part, parts, ld_part, C,
+                      1.f / static_cast<float>(HW), mean, w1, b1, w2, b2, Cr) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
 }
 
 extern "C" int adsr_rcab_ca_scale(const void* res, int64_t ldr, const void* x, int64_t ldx, void* out, int64_t ldo,
@@ -360,8 +363,8 @@ extern "C" int adsr_rcab_ca_scale(const void* res, int64_t ldr, const void* x, i
     if (C < 8 || C > 128 || (C % 8) || Cr < 0 || Cr > 16 || (ldr % 8) || (ldx % 8) || (ldo % 8)) return ADSR_ERR_BAD_SHAPE;
     if (static_cast<long long>(HW) * (C / 8) >= (1ll << 31)) return ADSR_ERR_BAD_SHAPE;
     const int slices = std::max(1, std::min(64, HW * (C / 8) / 1024));
-    rcab_ca_scale_kernel<<<dim3(slices, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(res), ldr, static_cast<const __nv_bfloat16*>(x), ldx,
-        static_cast<__nv_bfloat16*>(out), ldo, mean, w1, b1, w2, b2, HW, C, Cr);
-    return check_launch();
+    return launch_pdl(rcab_ca_scale_kernel, dim3(slices, B), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                      static_cast<const __nv_bfloat16*>(res), static_cast<long long>(ldr), static_cast<const __nv_bfloat16*>(x),
+                      static_cast<long long>(ldx), static_cast<__nv_bfloat16*>(out), static_cast<long long>(ldo), mean, w1, b1, w2, b2, HW, C,
+                      Cr) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
 }
