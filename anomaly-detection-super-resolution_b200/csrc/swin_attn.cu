@@ -169,6 +169,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = bars->tmem_base;
+    // programmatic dependent launch: the set-up above and the weight loaders run under the predecessor's tail; every warp that reads
+    // or writes activations / row statistics (x loader, epilogue warps) first waits for the predecessor to complete
+    pdl_launch_dependents();
+    if (warp < kEpiWarps || warp == kXLoaderWarp) pdl_wait();
     const int uq = p.hdp >> 4;                                         // 16-column units (= K16 steps) per head operand
     const int nwx = p.W >> 3, nW = (p.H >> 3) * nwx;
 
@@ -875,8 +879,7 @@ int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream) {
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     auto launch = [&](auto kernel) -> int {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
-        kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
-        return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
+        return launch_pdl(kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem_bytes), stream, p) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };
     if (p.trace != nullptr) return p.fuse_proj ? launch(swin_attn_kernel<true, true>) : launch(swin_attn_kernel<true, false>);
     return p.fuse_proj ? launch(swin_attn_kernel<false, true>) : launch(swin_attn_kernel<false, false>);

@@ -135,6 +135,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = bars->tmem_base;
+    // programmatic dependent launch: set-up and weight loaders overlap the predecessor's tail; the warps that touch activations or
+    // row statistics (tile loads / stores, epilogues) wait for it to complete
+    pdl_launch_dependents();
+    if (warp < kEpiWarps || warp == kTileWarp) pdl_wait();
 
     // The control warps below stay CONVERGED (uniform control flow, one elected lane issues): descriptors then live in
     // uniform registers and no tcgen05 / bulk-copy instruction gets wrapped in a lane-serialising loop.
@@ -581,8 +585,7 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
     const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
     auto launch = [&](auto kernel) -> int {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
-        kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
-        return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
+        return launch_pdl(kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem_bytes), stream, p) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };
     return p.trace != nullptr ? launch(swin_mlp_kernel<true>) : launch(swin_mlp_kernel<false>);
 }

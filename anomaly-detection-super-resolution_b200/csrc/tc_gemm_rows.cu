@@ -120,6 +120,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_rows_kernel(const __grid_
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = bars->tmem_base;
+    // programmatic dependent launch: only the weight loaders and the MMA issuers may run ahead of the predecessor's completion
+    pdl_launch_dependents();
+    if (warp < kEpiWarps || warp == kALoaderWarp || warp == kStoreWarp) pdl_wait();
     const int n_last = ((p.N - (p.n_tiles - 1) * kBN) + 15) & ~15;     // MMA N of the last N tile
 
     if (warp == kBLoaderWarp || warp == kBLoaderWarp2) {
@@ -366,8 +369,7 @@ int launch_tc_gemm_rows(TcGemmParams& g, int num_sms, cudaStream_t stream) {
     const int grid = g.m_tiles < num_sms ? g.m_tiles : num_sms;
     auto launch = [&](auto kernel) -> int {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
-        kernel<<<grid, kThreads, smem_bytes, stream>>>(rp);
-        return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
+        return launch_pdl(kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem_bytes), stream, rp) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };
     switch (g.act) {
         case ADSR_ACT_NONE: return launch(tc_gemm_rows_kernel<ADSR_ACT_NONE>);
