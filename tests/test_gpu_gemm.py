@@ -164,9 +164,11 @@ def test_conv_halo_tile_kernel(B, H, W, Cin, Cout, act):
     wc = pw.compact
     code = {"none": ops.ACT_NONE, "lrelu": ops.ACT_LRELU, "relu": ops.ACT_RELU}[act]
     n_store = (Cout + 15) // 16 * 16
-    out = torch.full((B * H * W, n_store + 24), -3.0, device=DEV, dtype=torch.bfloat16)
+    out_g = torch.full((B * H * W + 64, n_store + 24), -3.0, device=DEV, dtype=torch.bfloat16)     # 32 guard rows on either side
+    out = out_g[32:-32]
     n_parts = ops.halo_parts(H, W)
-    parts = torch.full((B * n_parts, wc.BN), float("nan"), device=DEV)           # every entry must be written
+    parts_g = torch.full((B * n_parts + 16, wc.BN), float("nan"), device=DEV)   # every entry must be written, none outside
+    parts = parts_g[8:-8]
     st = abi.lib().adsr_conv3x3_halo_bf16(abi.ptr(x), x.stride(0), B, H, W, Cin, abi.ptr(wc.data), abi.ptr(wc.bias), wc.N, wc.BN, code,
                                           0.1, abi.ptr(out), out.stride(0), 8, n_store, abi.ptr(parts), abi.num_sms(), abi.stream_ptr())
     assert st == 0, f"status {st}"
@@ -193,6 +195,8 @@ def test_conv_halo_tile_kernel(B, H, W, Cin, Cout, act):
     want_scale = torch.sigmoid(F.relu(mean @ w1.t() + b1) @ w2.t() + b2)
     assert float((scale - want_scale).abs().max()) < 1e-5
     assert bool((out[:, :8] == -3.0).all()) and bool((out[:, 8 + n_store:] == -3.0).all())
+    assert bool((out_g[:32] == -3.0).all()) and bool((out_g[-32:] == -3.0).all())
+    assert bool(torch.isnan(parts_g[:8]).all()) and bool(torch.isnan(parts_g[-8:]).all())
     assert bool((out[:, 8 + Cout:8 + n_store] == 0).all())                      # padded output channels: zero weights, zero bias
     # the streaming kernel computes the same sums in a different K order: equal to bf16 rounding
     ref = torch.zeros(B * H * W, n_store, device=DEV, dtype=torch.bfloat16)
