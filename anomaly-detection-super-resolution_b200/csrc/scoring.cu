@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(1024, 1) score_images_fast_kernel(const ScoreP
     extern __shared__ double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
+    const int part = blockIdx.y, nparts = gridDim.y;                    // small batches: the window sizes of an image split over CTAs
     const long long srb = static_cast<long long>(b) * p.sr.sb, hrb = static_cast<long long>(b) * p.hr.sb;
     double* red = sm;                                                   // [32]
     double* wbase = sm + 32;                                            // per worker: wtot [2][5][4], pref [2][5][W+1]
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(1024, 1) score_images_fast_kernel(const ScoreP
     for (int o = 16; o > 0; o >>= 1) acc_mse += __shfl_xor_sync(0xffffffffu, acc_mse, o);
     if (lane == 0) red[warp] = acc_mse;
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && part == 0) {
         double t = 0;
         for (int w = 0; w < 32; ++w) t += red[w];
         const double mse = t / (static_cast<double>(H) * W * C);
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(1024, 1) score_images_fast_kernel(const ScoreP
     double* pref = wtot + 2 * 5 * 4;                                    // [2][5][W + 1]
     const bool zp = p.zero_pad != 0;
     const double C1 = p.C1, C2 = p.C2;
-    for (int j = worker; j < n_ws; j += kFastWorkers) {
+    for (int j = worker + kFastWorkers * part; j < n_ws; j += kFastWorkers * nparts) {
         const int ws = p.wl.ws[j], pad = ws / 2;
         const double inv_n = 1.0 / (static_cast<double>(ws) * ws);
         double v[5] = {0, 0, 0, 0, 0};
@@ -346,7 +347,21 @@ int launch_score(adsr::ScoreParams& p, int B, const int32_t* host_ws_list, int n
     if (p.W <= 128 && fast_smem <= 227 * 1024 && n_ws > 0) {
         if (cudaFuncSetAttribute(score_images_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fast_smem)) != cudaSuccess)
             return ADSR_ERR_CUDA;
-        score_images_fast_kernel<<<B, 1024, fast_smem, st>>>(p);
+        // a CTA costs ~0.3 units (gray planes + MSE) + one unit per window size of its busiest worker; with few images (DRN-L's
+        // batch of 64 fills 64 of 148 SMs) two CTAs per image halve the sweep, with many (256) the extra waves would cost more
+        static int sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+                sms = 148;
+        }
+        auto cost = [&](int parts) {
+            const int waves = (B * parts + sms - 1) / sms;
+            const int per_worker = (n_ws + kFastWorkers * parts - 1) / (kFastWorkers * parts);
+            return waves * (0.3 + per_worker);
+        };
+        const int parts = (n_ws > kFastWorkers && cost(2) < cost(1)) ? 2 : 1;
+        score_images_fast_kernel<<<dim3(B, parts), 1024, fast_smem, st>>>(p);
         return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     }
     const int threads = ((p.W + 31) / 32) * 32;
