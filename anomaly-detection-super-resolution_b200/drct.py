@@ -174,6 +174,10 @@ class DRCT(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("DRCT parameters must live on a CUDA device (no CPU fallback); call .cuda()")
         f32 = lambda t: t.detach().float().contiguous()
+        # tensor-core images are packed on the HOST from CPU copies of the parameters and uploaded with one copy per buffer
+        # (pack.to_device): loading a model launches no device kernel
+        cpu = lambda t: None if t is None else t.detach().float().cpu()
+        up = lambda o: pack.to_device(o, dev)
         P: dict = {"blocks": []}
         P["mean"] = self.mean.to(dev).float().reshape(-1).contiguous()
         P["cf_w"], P["cf_b"] = f32(self.conv_first.weight), f32(self.conv_first.bias)
@@ -189,33 +193,33 @@ class DRCT(nn.Module):
                 b.adjust_out, b.last = adj.out_channels, k == 4
                 b.n1w, b.n1b, b.n2w, b.n2b = f32(sw.norm1.weight), f32(sw.norm1.bias), f32(sw.norm2.weight), f32(sw.norm2.bias)
                 b.table = f32(sw.attn.relative_position_bias_table)
-                b.qkv = pack.pack_qkv_weight(sw.attn.qkv.weight, sw.attn.qkv.bias, b.heads, sw.norm1.weight, sw.norm1.bias,
-                                             sw.norm1.eps)
-                b.proj = pack.pack_proj_weight(sw.attn.proj.weight, sw.attn.proj.bias, b.heads)
+                qkv_w, qkv_b, n1w, n1b = cpu(sw.attn.qkv.weight), cpu(sw.attn.qkv.bias), cpu(sw.norm1.weight), cpu(sw.norm1.bias)
+                proj_w, proj_b = cpu(sw.attn.proj.weight), cpu(sw.attn.proj.bias)
+                fc1_w, fc1_b, fc2_w, fc2_b = cpu(sw.mlp.fc1.weight), cpu(sw.mlp.fc1.bias), cpu(sw.mlp.fc2.weight), cpu(sw.mlp.fc2.bias)
+                n2w, n2b, adj_w, adj_b = cpu(sw.norm2.weight), cpu(sw.norm2.bias), cpu(adj.weight), cpu(adj.bias)
+                b.qkv = up(pack.pack_qkv_weight(qkv_w, qkv_b, b.heads, n1w, n1b, sw.norm1.eps))
+                b.proj = up(pack.pack_proj_weight(proj_w, proj_b, b.heads))
                 # fused attention half (csrc/swin_attn.cu): 2 = qkv + attention + proj + residual in one kernel,
                 # 1 = qkv + attention (proj stays a row-tile GEMM), 0 = shape not covered (separate kernels)
                 b.attn_mode = ops.swin_attn_mode(b.dim, b.heads, b.hdp) if (b.ws == 8 and _FUSED_ATTN) else 0
-                b.attn = pack.pack_swin_attn(sw.attn.qkv.weight, sw.attn.qkv.bias, sw.norm1.weight, sw.norm1.bias, sw.norm1.eps,
-                                             sw.attn.proj.weight, sw.attn.proj.bias, b.heads) if b.attn_mode else None
+                b.attn = up(pack.pack_swin_attn(qkv_w, qkv_b, n1w, n1b, sw.norm1.eps, proj_w, proj_b, b.heads)) if b.attn_mode else None
                 # the 32-channel adjust convs ride in the MLP kernel's last epilogue where its tiling leaves room (z is then never
                 # written); otherwise (and for adjust5) the adjust conv stays a GEMM of its own
                 b.mlp = None
                 if k < 4 and adj.out_channels == 32 and _FUSED_ADJUST:
                     try:
-                        b.mlp = pack.pack_swin_mlp(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias, sw.norm2.eps,
-                                                   sw.mlp.fc2.weight, sw.mlp.fc2.bias, adj.weight, adj.bias)
+                        b.mlp = up(pack.pack_swin_mlp(fc1_w, fc1_b, n2w, n2b, sw.norm2.eps, fc2_w, fc2_b, adj_w, adj_b))
                     except ValueError:
                         b.mlp = None
                 if b.mlp is None:
-                    b.mlp = pack.pack_swin_mlp(sw.mlp.fc1.weight, sw.mlp.fc1.bias, sw.norm2.weight, sw.norm2.bias, sw.norm2.eps,
-                                               sw.mlp.fc2.weight, sw.mlp.fc2.bias)
-                b.adjust = pack.pack_gemm_weight(adj.weight, adj.bias, rows_kernel=(k == 4))
+                    b.mlp = up(pack.pack_swin_mlp(fc1_w, fc1_b, n2w, n2b, sw.norm2.eps, fc2_w, fc2_b))
+                b.adjust = up(pack.pack_gemm_weight(adj_w, adj_b, rows_kernel=(k == 4)))
                 blocks.append(b)
             P["blocks"].append(blocks)
         P["norm_w"], P["norm_b"] = f32(self.norm.weight), f32(self.norm.bias)
-        P["cab"] = pack.pack_conv3x3_weight(self.conv_after_body.weight, self.conv_after_body.bias)
-        P["cbu"] = pack.pack_conv3x3_weight(self.conv_before_upsample[0].weight, self.conv_before_upsample[0].bias)
-        P["ups"] = [pack.pack_conv3x3_weight(m.weight, m.bias) for m in self.upsample if isinstance(m, nn.Conv2d)]
+        P["cab"] = up(pack.pack_conv3x3_weight(cpu(self.conv_after_body.weight), cpu(self.conv_after_body.bias)))
+        P["cbu"] = up(pack.pack_conv3x3_weight(cpu(self.conv_before_upsample[0].weight), cpu(self.conv_before_upsample[0].bias)))
+        P["ups"] = [up(pack.pack_conv3x3_weight(cpu(m.weight), cpu(m.bias))) for m in self.upsample if isinstance(m, nn.Conv2d)]
         P["cl_w"], P["cl_b"] = f32(self.conv_last.weight), f32(self.conv_last.bias)
         self._packed, self._packed_key = P, key
         return P

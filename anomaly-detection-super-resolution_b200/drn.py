@@ -108,32 +108,34 @@ class DRN(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("DRN parameters must live on a CUDA device (no CPU fallback); call .cuda()")
         f32 = lambda t: t.detach().float().contiguous()
+        # packed on the HOST from CPU copies of the parameters, uploaded with one copy per buffer (pack.to_device)
+        cpu = lambda t: None if t is None else t.detach().float().cpu()
+        up = lambda o: pack.to_device(o, dev)
+        pconv = lambda w, b: up(pack.pack_conv3x3_weight(cpu(w), cpu(b)))
         nc = self.n_colors
         P = {"sub_w": f32(self.sub_mean.weight).view(nc, nc).contiguous(), "sub_b": f32(self.sub_mean.bias),
              "head_w": f32(self.head.weight), "head_b": f32(self.head.bias), "down": [], "levels": [], "tails": []}
         for d in self.down:
-            P["down"].append((pack.pack_conv3x3_weight(d.dual_module[0][0].weight, None),
-                              pack.pack_conv3x3_weight(d.dual_module[1].weight, None)))
+            P["down"].append((pconv(d.dual_module[0][0].weight, None), pconv(d.dual_module[1].weight, None)))
         for seq in self.up_blocks:
             mods = list(seq)
             rcabs = []
             for m in mods[:self.n_blocks]:
                 ca = m.body[3].conv_du
                 c, cr = ca[0].in_channels, ca[0].out_channels
-                rcabs.append(dict(c1=pack.pack_conv3x3_weight(m.body[0].weight, m.body[0].bias),
-                                  c2=pack.pack_conv3x3_weight(m.body[2].weight, m.body[2].bias),
+                rcabs.append(dict(c1=pconv(m.body[0].weight, m.body[0].bias), c2=pconv(m.body[2].weight, m.body[2].bias),
                                   w1=f32(ca[0].weight).view(cr, c).contiguous(), b1=f32(ca[0].bias),
                                   w2=f32(ca[2].weight).view(c, cr).contiguous(), b2=f32(ca[2].bias), c=c, cr=cr))
             up_conv, conv1 = mods[self.n_blocks][0], mods[self.n_blocks + 1]
-            P["levels"].append(dict(rcabs=rcabs, up=pack.pack_conv3x3_weight(up_conv.weight, up_conv.bias),
-                                    c1x1=pack.pack_gemm_weight(conv1.weight, conv1.bias), c=up_conv.in_channels,
+            P["levels"].append(dict(rcabs=rcabs, up=pconv(up_conv.weight, up_conv.bias),
+                                    c1x1=up(pack.pack_gemm_weight(cpu(conv1.weight), cpu(conv1.bias))), c=up_conv.in_channels,
                                     cout=conv1.out_channels))
         # add_mean (a 1x1 conv) is folded into each tail conv: W' = A W, b' = A b + a   (exact)
-        A, a = f32(self.add_mean.weight).view(nc, nc), f32(self.add_mean.bias)
+        A, a = cpu(self.add_mean.weight).view(nc, nc), cpu(self.add_mean.bias)
         for t in self.tail:
-            w = torch.einsum("oc,cikl->oikl", A, f32(t.weight)).contiguous()
-            P["tails"].append((w, (A @ f32(t.bias) + a).contiguous(), t.in_channels))
-        P["zero_mean"] = torch.zeros(nc, dtype=torch.float32, device=dev)
+            w = torch.einsum("oc,cikl->oikl", A, cpu(t.weight)).contiguous()
+            P["tails"].append((w.to(dev), (A @ cpu(t.bias) + a).contiguous().to(dev), t.in_channels))
+        P["zero_mean"] = torch.zeros(nc, dtype=torch.float32).to(dev)
         self._packed, self._packed_key = P, key
         return P
 

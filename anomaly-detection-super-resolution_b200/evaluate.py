@@ -191,13 +191,15 @@ class BatchedEvaluator:
         replay the graph.  The returned table (and last_sr_u8) are the graph's static outputs: valid until the next replay."""
         if not self.use_graph or ops.PROFILE is not None:
             return self._score(lr_d, hr_d)
+        target = self.model.model if hasattr(self.model, 'model') else self.model
+        packed = target._pack() if hasattr(target, '_pack') else None     # repacked weights (new parameters) -> a new graph
         key = (lr_d.data_ptr(), hr_d.data_ptr(), tuple(lr_d.shape), tuple(hr_d.shape), lr_d.dtype, hr_d.dtype,
-               tuple(self.window_sizes) if self.window_sizes is not None else None)
+               tuple(self.window_sizes) if self.window_sizes is not None else None, id(packed))
         ent = self._graphs.get(key)
         if ent is None:
-            if len(self._graphs) > 8:
-                self._graphs.clear()
-            self._graphs[key] = {"graph": None, "keep": (lr_d, hr_d)}
+            while len(self._graphs) >= 8:                     # evict the oldest entry only (no recapture thrash)
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = {"graph": None, "keep": (lr_d, hr_d, packed)}
             return self._score(lr_d, hr_d)
         if ent["graph"] is None:
             try:
@@ -210,6 +212,9 @@ class BatchedEvaluator:
                 ent["launches"] = ops.LAUNCHES - n0
                 ops.LAUNCHES = n0
                 ent["graph"] = g
+                # the graph holds raw addresses of the model's workspaces: keep them alive for as long as the graph is, even
+                # if the model's own workspace cache evicts them
+                ent["ws"] = dict(getattr(target, '_ws_cache', {}))
             except Exception as e:                            # capture not possible: stay on the eager path (still no fallback
                 self.use_graph = False                        # away from the CUDA kernels)
                 print(f"[adsr] CUDA graph capture disabled: {e}", file=sys.stderr)
@@ -249,6 +254,9 @@ class BatchedEvaluator:
             buf = [key, torch.empty(lr.shape, dtype=lr.dtype, device=self.device), torch.empty(hr.shape, dtype=hr.dtype, device=self.device),
                    None]                                       # [key, lr_d, hr_d, event: the compute that last read this set]
             self._bufs[k] = buf
+            # fresh blocks may be memory the caching allocator just took back from kernels still pending on the compute
+            # stream (per-call temporaries, the previous sr_u8): the copies below must not overtake them
+            self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self._copy_stream):
             if buf[3] is not None:
                 self._copy_stream.wait_event(buf[3])           # the batch computed from this buffer set two submits ago is done
@@ -269,7 +277,8 @@ class BatchedEvaluator:
         return scores
 
     def run_pipelined(self, batches):
-        """Iterates (lr, hr) host batches with one batch of copy look-ahead; yields the device score table of each batch."""
+        """Iterates (lr, hr) host batches with one batch of copy look-ahead; yields the device score table of each batch
+        (a private copy: the CUDA graph's static output tensor is overwritten by the next replay of the same buffer set)."""
         it = iter(batches)
         try:
             nxt = self.submit(*next(it))
@@ -281,7 +290,7 @@ class BatchedEvaluator:
                 nxt = self.submit(*next(it))
             except StopIteration:
                 nxt = None
-            yield self.step_submitted(cur)
+            yield self.step_submitted(cur).clone()
 
 
 def _dist_info():
@@ -292,31 +301,38 @@ def _dist_info():
     return 0, 1
 
 
-def gather_scores(local_scores: torch.Tensor, local_ids: torch.Tensor, n_total: int) -> Optional[np.ndarray]:
-    """all_gather of the per-rank score rows (NCCL over NVLink when sharded); rank 0 returns the table ordered by
-    image id, other ranks None.  <= 8*(n_ws+2)+8 bytes per image: latency only."""
+def gather_scores(local_scores: torch.Tensor, local_ids: torch.Tensor, n_total: int, to_host: bool = True):
+    """ONE all_gather (NCCL over NVLink when sharded) of the per-rank score rows with the image id as an extra fp64 column
+    (ids < 2^53 are exact); <= 8*(n_ws+3) bytes per image: latency only.
+    to_host=True: rank 0 returns the numpy table ordered by image id, other ranks None.
+    to_host=False: every rank returns the gathered DEVICE tensor [world * n_max, C + 1] (pad rows carry id -1) without any
+    host synchronisation; pass it to `scores_table` when the table is consumed."""
     import torch.distributed as dist
 
     rank, world = _dist_info()
+    c = local_scores.shape[1]
+    n = local_scores.shape[0]
+    n_max = n if world == 1 else (n_total + world - 1) // world
+    packed = local_scores.new_full((n_max, c + 1), -1.0)
+    packed[:n, :c] = local_scores
+    packed[:n, c] = local_ids.to(local_scores.dtype)
     if world == 1:
-        out = np.empty((n_total, local_scores.shape[1]), dtype=np.float64)
-        out[local_ids.cpu().numpy()] = local_scores.cpu().numpy()
-        return out
-    n_max = (n_total + world - 1) // world
-    pad = n_max - local_scores.shape[0]
-    s = torch.cat([local_scores, local_scores.new_zeros(pad, local_scores.shape[1])]) if pad else local_scores
-    i = torch.cat([local_ids, local_ids.new_full((pad,), -1)]) if pad else local_ids
-    all_s = [torch.empty_like(s) for _ in range(world)]
-    all_i = [torch.empty_like(i) for _ in range(world)]
-    dist.all_gather(all_s, s.contiguous())
-    dist.all_gather(all_i, i.contiguous())
-    if rank != 0:
-        return None
-    out = np.empty((n_total, local_scores.shape[1]), dtype=np.float64)
-    for ss, ii in zip(all_s, all_i):
-        ii = ii.cpu().numpy()
-        keep = ii >= 0
-        out[ii[keep]] = ss.cpu().numpy()[keep]
+        gathered = packed
+    else:
+        gathered = packed.new_empty((world * n_max, c + 1))
+        dist.all_gather_into_tensor(gathered, packed)
+    if not to_host:
+        return gathered
+    return scores_table(gathered, n_total) if rank == 0 else None
+
+
+def scores_table(gathered: torch.Tensor, n_total: int) -> np.ndarray:
+    """Gathered device rows (gather_scores(..., to_host=False)) -> host table [n_total, C] ordered by image id."""
+    arr = gathered.cpu().numpy()
+    c = arr.shape[1] - 1
+    keep = arr[:, c] >= 0
+    out = np.empty((n_total, c), dtype=np.float64)
+    out[arr[keep, c].astype(np.int64)] = arr[keep, :c]
     return out
 
 
@@ -345,9 +361,19 @@ def evaluate_on_test(opt, checkpoint_model_path, output_dir: str, save_images: b
         print('Test set lacks both classes; AUC not available')
         return None
 
+    # SSIM window sizes come from the smallest HR dimension over the WHOLE test set (src/evaluate.py:233-235), known from the
+    # PNG headers before the images are sharded: every rank sweeps the same sizes, also one that holds no image at all
+    from PIL import Image
+
+    min_dim = None
+    for _, _, f_hr, f_lr in entries:
+        with Image.open(f_hr) as im_hr, Image.open(f_lr) as im_lr:
+            dims = (min(im_hr.size[1], im_lr.size[1] * scale), min(im_hr.size[0], im_lr.size[0] * scale))
+        min_dim = min(dims) if min_dim is None else min(min_dim, *dims)
+
     opt.pre_train = checkpoint_model_path
     model = Model(opt, None)
-    ev = BatchedEvaluator(model, opt.rgb_range)
+    ev = BatchedEvaluator(model, opt.rgb_range, metrics.window_sizes_for(min_dim))
     bs = batch_size or getattr(opt, 'eval_batch_size', None) or 64
     mine = list(range(rank, len(entries), world))            # image index i -> rank i mod R
     rows, ids = [], []
@@ -373,7 +399,7 @@ def evaluate_on_test(opt, checkpoint_model_path, output_dir: str, save_images: b
                 for j, i in enumerate(order[k]):
                     name = os.path.splitext(os.path.basename(entries[i][2]))[0]
                     save_sr_image(sr_np[j], output_dir, name, entries[i][1], scale)
-    n_cols = len(ev.window_sizes) + 2 if ev.window_sizes else 3
+    n_cols = len(ev.window_sizes) + 2
     local = torch.cat(rows) if rows else torch.empty(0, n_cols, dtype=torch.float64, device='cuda')
     table = gather_scores(local, torch.tensor(ids, dtype=torch.int64, device='cuda'), len(entries))
     if table is None:

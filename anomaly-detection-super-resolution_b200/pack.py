@@ -22,6 +22,24 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def to_device(obj, device):
+    """Packed images are built on the HOST (the pack_* functions run wherever their inputs live; the models hand them CPU
+    copies of the parameters) and reach the GPU with one plain copy per buffer: no device kernel runs at load time.
+    Moves every tensor field of a Packed* dataclass (recursively) except the host-side `plan`."""
+    import dataclasses
+
+    if obj is None or not dataclasses.is_dataclass(obj):
+        return obj
+    for f in dataclasses.fields(obj):
+        v = getattr(obj, f.name)
+        if isinstance(v, torch.Tensor):
+            if f.name != "plan":
+                setattr(obj, f.name, v.to(device))
+        elif dataclasses.is_dataclass(v):
+            to_device(v, device)
+    return obj
+
+
 def choose_bn(n: int) -> tuple[int, int]:
     """(BN, n_tiles): BN a multiple of 32 (epilogue chunks of 32 columns never straddle N tiles), <= 256, and the
     (n_tiles, BN) pair with the least padded columns, each extra tile being charged like 40 padded columns (per-tile

@@ -31,6 +31,10 @@ def _worker(rank, world, port, n_total, n_ws, out_path):
     full = torch.from_numpy(np.random.default_rng(0).random((n_total, n_ws + 2)))
     ids = torch.arange(rank, n_total, world, dtype=torch.int64)          # the evaluator's sharding rule
     table = evaluate.gather_scores(full[ids].clone(), ids, n_total)
+    # the sync-free form: every rank gets the gathered device rows, the host table is built when it is consumed
+    dev_rows = evaluate.gather_scores(full[ids].clone(), ids, n_total, to_host=False)
+    assert isinstance(dev_rows, torch.Tensor) and dev_rows.shape == (world * ((n_total + world - 1) // world), n_ws + 3)
+    assert np.array_equal(evaluate.scores_table(dev_rows, n_total), full.numpy())
     if rank == 0:
         np.save(out_path, table)
     else:
@@ -39,7 +43,7 @@ def _worker(rank, world, port, n_total, n_ws, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_total", [10, 7])        # 7: ranks hold different counts -> padded gather
+@pytest.mark.parametrize("n_total", [10, 7, 1])     # 7: ranks hold different counts -> padded gather; 1: a rank with no image
 def test_gather_scores_two_ranks(tmp_path, n_total):
     n_ws = 3
     out = str(tmp_path / "table.npy")

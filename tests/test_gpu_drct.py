@@ -18,6 +18,7 @@ def _model(cfg: O.DrctCfg, sd):
     drct = mod("drct")
     opt = DrctOpt(img_size=cfg.img_size, n_colors=cfg.n_colors, embed_dim=cfg.embed_dim, layers=cfg.num_layers,
                   heads=cfg.num_heads, upscale=cfg.upscale)
+    opt.window_size = cfg.window_size
     m = drct.DRCT(opt)
     res = m.load_state_dict(sd, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
@@ -83,10 +84,59 @@ def test_drct_l_64px_lr_vs_oracle():
     cfg = O.DrctCfg(img_size=64, window_size=16)
     sd = O.make_state_dict(cfg, seed=4, affine_jitter=0.05)
     m = _model(cfg, sd)
-    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(11)) * 255.0
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(11)) * 255.0
     with torch.no_grad():
         want = O.drct_forward(sd, x, cfg)
     got = m(x.to(DEV)).cpu()
-    assert got.shape == (1, 3, 256, 256)
+    assert got.shape == (2, 3, 256, 256)
     err = float((got - want).abs().max()) / 255.0
     assert err < TOL, f"max|dSR|/rgb_range = {err}"
+
+
+def test_drct_rgb_range_1_full_model():
+    """rgb_range = 1 through the whole model (both input scalings are run): inputs in [0, 1], the uint8
+    truncation multiplies by 255 / rgb_range (src/evaluate.py:214)."""
+    from oracle import scoring_oracle as S
+    cfg = O.DrctCfg(num_layers=2)
+    sd = O.make_state_dict(cfg, seed=8, affine_jitter=0.05)
+    drct = mod("drct")
+    opt = DrctOpt(layers=2, rgb_range=1)
+    m = drct.DRCT(opt)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    x = torch.rand(3, 3, 32, 32, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        want = O.drct_forward(sd, x, cfg)
+    sr, u8 = m.run(x.to(DEV), want_float=True, want_u8=True)
+    err = float((sr.cpu() - want).abs().max()) / 1.0
+    assert err < TOL, f"max|dSR|/rgb_range = {err}"
+    assert np.array_equal(u8.cpu().numpy(), S.quantize_u8(sr.cpu().numpy(), 1.0))
+
+
+def test_drct_odd_window_count_falls_back_inside_forward():
+    """B * nW odd (one image of 24 x 24 px = 9 windows): the fused attention half needs window pairs, so the forward takes the
+    separate qkv / attention / proj kernels for every block -- same result as the oracle."""
+    cfg = O.DrctCfg(img_size=24, n_colors=3, embed_dim=180, num_layers=1, num_heads=6, window_size=8)
+    sd = O.make_state_dict(cfg, seed=12, affine_jitter=0.05)
+    m = _model(cfg, sd)
+    ops = mod("ops")
+    x = torch.rand(1, 3, 24, 24, generator=torch.Generator().manual_seed(5)) * 255.0
+    with torch.no_grad():
+        want = O.drct_forward(sd, x, cfg)
+    ops.PROFILE = []
+    try:
+        got = m(x.to(DEV)).cpu()
+        kinds = [p[0] for p in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+    assert "swin_attn" not in kinds and kinds.count("window_attention") == 5
+    assert float((got - want).abs().max()) / 255.0 < TOL
+    x2 = torch.cat([x, x.flip(-1)])                        # two images: 18 windows, the fused kernel runs again
+    ops.PROFILE = []
+    try:
+        got2 = m(x2.to(DEV)).cpu()
+        kinds2 = [p[0] for p in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+    assert kinds2.count("swin_attn") == 5
+    assert float((got2[0] - want[0]).abs().max()) / 255.0 < TOL

@@ -105,3 +105,113 @@ def test_evaluator_graph_and_pipelined_paths_match_eager():
     dl, dh = batches[0][0].cuda(), batches[0][1].cuda()                # device-resident inputs: graph keyed by the buffer pair
     for _ in range(3):
         assert torch.equal(ev.step(dl, dh).cpu(), want[0][0])
+
+
+def test_evaluate_cli_drn_l_matches_oracle(tmp_path, capsys):
+    """`--model-type drn-l` through the CLI (src/evaluate.py:210-211: the LAST element of DRN's output list is scored)."""
+    from oracle import drn_oracle as DO
+
+    evaluate = importlib.import_module(PKG + ".evaluate")
+    n = 24
+    root = str(tmp_path / "mvtec_128")
+    hr, lr, labels = _write_dataset(root, "carpet", 3, n)
+    cfg = DO.DrnCfg()
+    sd = DO.make_state_dict(cfg, seed=4)
+    for k in sd:                                   # keep 80 residual blocks numerically tame with random weights
+        if ".body.0." in k or ".body.2." in k:
+            sd[k] = sd[k] * 0.5
+    ckpt = str(tmp_path / "model_best.pt")
+    torch.save(sd, ckpt)
+    res = evaluate.main(["--model-type", "drn-l", "--classe", "carpet", "--scale", "4", "--resolution", "128", "--data-root",
+                         root, "--checkpoint", ckpt, "--batch-size", "8", "--output-dir", str(tmp_path / "out")])
+    assert capsys.readouterr().out.strip().splitlines()[-1].startswith("Test AUCs - SSIM(best ws=")
+
+    order = np.argsort(labels, kind="stable")
+    x = torch.from_numpy(np.ascontiguousarray(lr[order].transpose(0, 3, 1, 2))).float()
+    with torch.no_grad():
+        sr = torch.cat([DO.drn_forward(sd, x[i:i + 8], cfg)[-1] for i in range(0, n, 8)])
+    sr_u8 = S.quantize_u8(sr.numpy(), 255.0)
+    wss = S.window_sizes_for(128)
+    ssim, mse, psnr = S.score_images(list(sr_u8), list(hr[order]), wss)
+    y = labels[order]
+    best_ws, a_ssim, a_mse, a_psnr = S.aucs_from_scores(y, ssim, mse, psnr, wss)
+    assert np.abs(res["scores"][:, :len(wss)] - ssim).max() < 2e-2
+    assert np.abs(res["scores"][:, len(wss)] - mse).max() < 2e-2 * max(mse.max(), 1e-3) + 1e-5
+    # AUC is a rank statistic: identical unless bf16 noise swaps a near-tie; with 12 x 12 pairs one swap moves it by 0.007
+    assert abs(res["auc_mse"] - a_mse) <= 1.5e-2 and abs(res["auc_psnr"] - a_psnr) <= 1.5e-2 and abs(res["auc_ssim"] - a_ssim) <= 1.5e-2
+
+
+class _TableModel:
+    """Stands in for the SR network: `run` returns precomputed uint8 SR images for the LR batch it is handed (the LR tensor's
+    first element carries the index of the batch's first image), so the evaluator's batching, scoring, gather and AUC logic can
+    be driven over a large image set without a forward pass."""
+
+    def __init__(self, sr_u8: torch.Tensor):
+        self.sr_u8 = sr_u8
+
+    def run(self, lr_d, want_float=False, want_u8=True):
+        i0 = int(lr_d[0, 0, 0, 0].item())
+        return None, self.sr_u8[i0:i0 + lr_d.shape[0]]
+
+
+@pytest.mark.timeout(900)
+def test_auc_over_1024_images_matches_oracle():
+    """>= 1024 images for the AUC check.  Synthetic good / bad uint8 pairs (SR = HR + reconstruction noise; bad
+    images keep a residual defect) go through BatchedEvaluator batches of 128 + gather_scores; best window and the three AUCs
+    must equal the oracle's (numpy SSIM sweep + rank-statistic AUC) on the same uint8 inputs."""
+    evaluate = importlib.import_module(PKG + ".evaluate")
+    metrics = importlib.import_module(PKG + ".metrics")
+    n, bs = 1024, 128
+    hr, _, labels = S.synthetic_dataset(n, hr=128, nc=3, scale=4, seed=31)
+    rng = np.random.default_rng(7)
+    sr = hr.astype(np.int16) + rng.integers(-5, 6, hr.shape)
+    for i in np.nonzero(labels)[0]:                       # the SR model "repairs" the defect only partly
+        y0, x0 = rng.integers(0, 96, 2)
+        sr[i, y0:y0 + 24, x0:x0 + 24] += rng.integers(4, 40)
+    sr = np.clip(sr, 0, 255).astype(np.uint8)
+    wss = S.window_sizes_for(128)
+    ev = evaluate.BatchedEvaluator(_TableModel(torch.from_numpy(sr).cuda()), 255.0, wss)
+    ev.use_graph = False
+    rows, ids = [], []
+    for i0 in range(0, n, bs):
+        lr_tag = torch.full((bs, 1, 1, 1), float(i0), device="cuda")
+        rows.append(ev.step(lr_tag, torch.from_numpy(hr[i0:i0 + bs]).cuda()).clone())
+        ids += list(range(i0, i0 + bs))
+    table = evaluate.gather_scores(torch.cat(rows), torch.tensor(ids, device="cuda"), n)
+    got = metrics.aucs_from_scores(labels, table, wss)
+    ssim, mse, psnr = S.score_images(list(sr), list(hr), wss)
+    want = S.aucs_from_scores(labels, ssim, mse, psnr, wss)
+    assert np.abs(table[:, :len(wss)] - ssim).max() < 1e-5 and np.abs(table[:, len(wss)] - mse).max() < 1e-7
+    assert got[0] == want[0], f"best window {got[0]} != oracle {want[0]}"
+    assert np.allclose(got[1:], want[1:], atol=1e-3), f"AUCs {got[1:]} vs oracle {want[1:]}"
+
+
+def test_evaluate_on_test_many_equal_batches_match_eager(tmp_path, capsys, monkeypatch):
+    """evaluate_on_test over >= 6 equal-shape batches: CUDA-graph replays reuse ONE static output tensor per buffer set, so the
+    per-batch score rows must be copied before the next replay.  The table must equal the eager (no graph) run bit for bit."""
+    evaluate = importlib.import_module(PKG + ".evaluate")
+    n = 28                                               # batch 4 -> 7 batches per run
+    root = str(tmp_path / "mvtec_128")
+    _write_dataset(root, "carpet", 3, n)
+    cfg = O.DrctCfg(num_layers=1)
+    sd = O.make_state_dict(cfg, seed=9)
+    ckpt = str(tmp_path / "model_best.pt")
+    torch.save(sd, ckpt)
+    main_mod = importlib.import_module(PKG + ".main")
+    orig = main_mod.setup_opt_drct
+
+    def one_rdg(*a, **k):                                # a 1-RDG DRCT keeps the test short; the evaluator logic is unchanged
+        opt = orig(*a, **k)
+        opt.depths, opt.num_heads = (6,), (6,)
+        return opt
+
+    monkeypatch.setattr(evaluate, "setup_opt_drct", one_rdg)
+    argv = ["--model-type", "drct", "--classe", "carpet", "--scale", "4", "--resolution", "128", "--data-root", root,
+            "--checkpoint", ckpt, "--batch-size", "4", "--output-dir", str(tmp_path / "out")]
+    monkeypatch.setenv("ADSR_CUDA_GRAPH", "0")
+    want = evaluate.main(argv)
+    monkeypatch.setenv("ADSR_CUDA_GRAPH", "1")
+    got = evaluate.main(argv)
+    capsys.readouterr()
+    assert np.array_equal(got["scores"], want["scores"])
+    assert len({tuple(r) for r in got["scores"].round(9).tolist()}) > n // 2     # rows are not copies of one batch
