@@ -89,6 +89,10 @@ int encode_tmap_rows_bf16(CUtensorMap* map, const void* base, long long rows, lo
 int launch_window_attention_tc(const void* qkv, long long ldq, void* out, long long ldo, const float* table, int B, int H, int W,
                                int shift, int nH, int hd, int hdp, int num_sms, cudaStream_t stream);
 
+// ---- tcgen05 window attention for 16x16 windows (attention_tc16.cu: DRCT-L at 64 px LR); ADSR_ERR_BAD_SHAPE = shape not covered
+int launch_window_attention_tc16(const void* qkv, long long ldq, void* out, long long ldo, const float* table, int B, int H, int W,
+                                 int shift, int nH, int hd, int hdp, int num_sms, cudaStream_t stream);
+
 // ---- fused Swin MLP (swin_mlp.cu)
 struct SwinMlpParams {
     CUtensorMap tmap_y;   // [M x C] bf16, box 64 x 128, 128-byte swizzle (loads)

@@ -476,6 +476,14 @@ extern "C" int adsr_window_attention(const void* qkv, int64_t ldq, void* out, in
     p.total_slots = B * p.nW * N;
     p.scale_log2e = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ws == 16 && g_attn_tc_enabled != 0) {
+        // DRCT-L at 64 px LR (BASELINE configs[3]): tcgen05 kernel with S / P / O of the 256-key windows in TMEM
+        int num_sms = 0, dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return ADSR_ERR_CUDA;
+        const int rc = launch_window_attention_tc16(qkv, ldq, out, ldo, bias_table, B, H, W, shift, nH, hd, hdp, num_sms, st);
+        if (rc != ADSR_ERR_BAD_SHAPE) return rc;
+    }
     if (ws == 8 && (g_attn_tc_enabled == 2 || (g_attn_tc_enabled == 1 && hdp <= 64))) {
         // (heads wider than 64 channels need two panels per operand and only a 2-deep ring: the mma.sync kernel is still faster there)
         // DRCT-L shape: tcgen05 kernel (S and O in TMEM); shapes it does not cover fall through to the mma.sync kernels

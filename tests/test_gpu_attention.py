@@ -93,3 +93,62 @@ def test_window_attention_both_kernels(heads, hd, shift, mode):
     assert err < 0.03, f"mode {mode}: attention max abs err {err}"
     if hdp > hd:
         assert float(got[:, :, hd:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("heads,hd", [(6, 30), (4, 53), (2, 122), (6, 46), (4, 77)])
+@pytest.mark.parametrize("shift", [0, 8])
+@pytest.mark.parametrize("mode", [1, 0])
+def test_window_attention_ws16_batch(heads, hd, shift, mode):
+    """BASELINE configs[3] (64 px LR, 16 x 16 windows, N = 256): the tcgen05 kernel of csrc/attention_tc16.cu (mode 1) and the
+    mma.sync kernel (mode 0) against torch for the five DRCT-L block widths, shifted and unshifted, at batch 5
+    (80 windows: several units per CTA, so the K / V / Q rings wrap and both TMEM halves are reused)."""
+    import ctypes
+    ops, pack, abi = mod("ops"), mod("pack"), mod("_abi")
+    setter = abi.lib().adsr_debug_set_attention_tc
+    setter.restype, setter.argtypes = None, [ctypes.c_int]
+    torch.manual_seed(hd + shift)
+    B, H, ws = 5, 64, 16
+    M = B * H * H
+    hdp = pack.head_pad(hd)
+    q, k, v = (torch.randn(M, heads, hd, device=DEV) for _ in range(3))
+    q, k = q * 1.5, k * 1.5
+    table = torch.randn((2 * ws - 1) ** 2, heads, device=DEV) * 0.5
+    qkv = torch.zeros(M, 3 * heads * hdp, device=DEV, dtype=torch.bfloat16)
+    for i, t in enumerate((q, k, v)):
+        qkv.view(M, 3, heads, hdp)[:, i, :, :hd] = t.to(torch.bfloat16)
+    out = torch.full((M, heads * hdp), 3.0, device=DEV, dtype=torch.bfloat16)
+    setter(mode)
+    try:
+        ops.window_attention(qkv, out, table, B, H, H, ws, shift, heads, hd, hdp)
+        torch.cuda.synchronize()
+    finally:
+        setter(1)
+    r = lambda t: t.to(torch.bfloat16).float()
+    want = _attention_want(r(q), r(k), r(v), table, B, H, H, ws, shift, heads, hd)
+    got = out.view(M, heads, hdp).float()
+    err = float((got[:, :, :hd] - want).abs().max())
+    assert err < 0.03, f"mode {mode}: attention max abs err {err}"
+    if hdp > hd:
+        assert float(got[:, :, hd:].abs().max()) == 0.0, "head padding columns must be exact zeros"
+
+
+@pytest.mark.parametrize("H,W,B,shift", [(32, 64, 3, 8), (48, 16, 2, 8), (16, 16, 1, 0)])
+def test_window_attention_ws16_rect_and_tiny(H, W, B, shift):
+    """16 x 16 windows on rectangular grids and on a single window (fewer windows than CTAs per head)."""
+    ops, pack = mod("ops"), mod("pack")
+    torch.manual_seed(H + W)
+    heads, hd, ws = 4, 53, 16
+    M = B * H * W
+    hdp = pack.head_pad(hd)
+    q, k, v = (torch.randn(M, heads, hd, device=DEV) for _ in range(3))
+    table = torch.randn((2 * ws - 1) ** 2, heads, device=DEV) * 0.5
+    qkv = torch.zeros(M, 3 * heads * hdp, device=DEV, dtype=torch.bfloat16)
+    for i, t in enumerate((q, k, v)):
+        qkv.view(M, 3, heads, hdp)[:, i, :, :hd] = t.to(torch.bfloat16)
+    out = torch.full((M, heads * hdp), 3.0, device=DEV, dtype=torch.bfloat16)
+    ops.window_attention(qkv, out, table, B, H, W, ws, shift, heads, hd, hdp)
+    torch.cuda.synchronize()
+    r = lambda t: t.to(torch.bfloat16).float()
+    want = _attention_want(r(q), r(k), r(v), table, B, H, W, ws, shift, heads, hd)
+    got = out.view(M, heads, hdp).float()
+    assert float((got[:, :, :hd] - want).abs().max()) < 0.03
