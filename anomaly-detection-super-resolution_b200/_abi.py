@@ -11,7 +11,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadsr_b200.so")
+# ADSR_LIB: developer override for A/B timing of two builds in one session (tools/build_variant.sh); never a fallback
+LIB_PATH = os.environ.get("ADSR_LIB") or os.path.join(_HERE, "libadsr_b200.so")
 ABI_VERSION = 9
 
 ACT_NONE, ACT_LRELU, ACT_GELU, ACT_RELU = 0, 1, 2, 3

@@ -161,6 +161,7 @@ struct SwinAttnParams {
     int rsz, nreg;            // TMEM: columns per head region, number of regions (2 = next head's q|k|v runs one head ahead)
     int col_o;                // TMEM column of O (fuse_proj: behind the region; else O overlays the region's q columns)
     int col_acc;              // fuse_proj with spare TMEM: separate q|k|v accumulator columns, else -1 (accumulators = the region)
+    int early_setup;          // per-row tile set-up (token, mask bits, LayerNorm statistics) one tile ahead, under the first S wait
     int w_slots, w_slot_bytes;   // qkv weight ring
     int p_slots, p_slot_bytes;   // proj weight ring (fuse_proj)
     long long* trace;         // optional clock64 timeline of CTA 0 (tools/attn_trace.py), else nullptr
@@ -171,6 +172,9 @@ int encode_tmap_nhwc_box3_bf16(CUtensorMap* map, const void* base, int B, int H,
                                int box_h);
 int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj);   // 0 = not covered, 1 = qkv + attention, 2 = + proj
 int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream);
+// two heads in flight (swin_attn2.cu): qkv + attention only, the 16 epilogue warps split into two groups that own the even / odd heads
+int swin_attn2_plan(SwinAttnParams& p, int C, int nH, int hdp);                   // 1 = covered, 0 = use swin_attn.cu
+int launch_swin_attn2(SwinAttnParams& p, int num_sms, cudaStream_t stream);
 
 // ---- halo-tile 3x3 conv with resident weights (conv_halo.cu)
 struct ConvHaloParams {

@@ -499,33 +499,57 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         const int t128 = grp * 32 + lane;
         const uint32_t cpr_magic = (65536u + static_cast<uint32_t>(p.hdp >> 3) - 1u) / static_cast<uint32_t>(p.hdp >> 3);   // id / (hdp / 8), id < 512
 
+        // ---- per-tile set-up of my row: slot -> token (closed form of roll + window_partition), the mask bits of my 16 keys and the
+        // LayerNorm statistics.  The (sum, sumsq) slots are a COLD global load (written by the previous kernel), so the set-up of
+        // tile it + 1 runs while tile it waits for its first S anyway (the load latency disappears in that wait)
+        auto row_setup = [&](int tile, int& tok_o, uint32_t& mbits_o, float& rstd_o, float& nrm_o) {
+            const int win = tile * 2 + (r >> 6);
+            const int b = win / nW, w = win - b * nW;
+            const int wy = (w / nwx) * 8, wx = (w % nwx) * 8;
+            const int ys = wy + ny, xs = wx + nx;
+            int y = ys + p.shift; if (y >= p.H) y -= p.H;
+            int x = xs + p.shift; if (x >= p.W) x -= p.W;
+            const int tok = (b * p.H + y) * p.W + x;
+            uint32_t mbits = 0xffffu;
+            if (p.shift > 0) {
+                // key k lies in my mask region iff its row AND its column do (region id = 3 ry + rx, src/drct.py:449-470)
+                const int my_ry = region_1d_(ys, p.H, p.shift), my_rx = region_1d_(xs, p.W, p.shift);
+                const int kw = blk4 ? 4 : 8, kh = 16 / kw;             // my keys: kh rows of kw
+                uint32_t xmask = 0;
+                for (int j = 0; j < kw; ++j) xmask |= (region_1d_(wx + kx0 + j, p.W, p.shift) == my_rx ? 1u : 0u) << j;
+                mbits = 0u;
+                for (int i = 0; i < kh; ++i)
+                    if (region_1d_(wy + ky0 + i, p.H, p.shift) == my_ry) mbits |= xmask << (i * kw);
+            }
+            const float2* sp = p.stats_in + static_cast<long long>(tok) * p.stats_in_stride;
+            float s1 = 0.f, s2 = 0.f;
+            for (int k = 0; k < p.stats_in_slots; ++k) {
+                const float2 v = __ldg(sp + k);
+                s1 += v.x;
+                s2 += v.y;
+            }
+            const float inv_c = 1.0f / static_cast<float>(p.C);
+            const float mean = s1 * inv_c;
+            const float rs = rsqrtf(fmaxf(s2 * inv_c - mean * mean, 0.f) + p.ln_eps);
+            tok_o = tok; mbits_o = mbits; rstd_o = rs; nrm_o = -mean * rs;
+        };
+        int tok = 0;
+        uint32_t mbits = 0xffffu;
+        float rstd = 0.f, nrm = 0.f;
+        // p.early_setup (plans whose next q|k|v runs ahead, so that a tile does NOT start with a long wait that would hide the loads):
+        // the set-up of tile it + 1 runs while tile it waits for its first S; otherwise it runs at the tile top, under the
+        // q|k|v wait, with the statistics pulled into L1 one tile ahead
+        int tok_n = 0;
+        uint32_t mbits_n = 0xffffu;
+        float rstd_n = 0.f, nrm_n = 0.f;
+        const bool early = p.early_setup != 0;
+        if (early && my_tiles > 0) row_setup(static_cast<int>(blockIdx.x), tok, mbits, rstd, nrm);
+
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
             const int mb = it & 1;
-            // ---- my row: slot -> token (closed form of roll + window_partition) and the mask bits of my 16 keys
-            int tok;
-            uint32_t mbits = 0xffffu;
-            {
-                const int win = tile * 2 + (r >> 6);
-                const int b = win / nW, w = win - b * nW;
-                const int wy = (w / nwx) * 8, wx = (w % nwx) * 8;
-                const int ys = wy + ny, xs = wx + nx;
-                int y = ys + p.shift; if (y >= p.H) y -= p.H;
-                int x = xs + p.shift; if (x >= p.W) x -= p.W;
-                tok = (b * p.H + y) * p.W + x;
-                if (p.shift > 0) {
-                    // key k lies in my mask region iff its row AND its column do (region id = 3 ry + rx, src/drct.py:449-470)
-                    const int my_ry = region_1d_(ys, p.H, p.shift), my_rx = region_1d_(xs, p.W, p.shift);
-                    const int kw = blk4 ? 4 : 8, kh = 16 / kw;         // my keys: kh rows of kw
-                    uint32_t xmask = 0;
-                    for (int j = 0; j < kw; ++j) xmask |= (region_1d_(wx + kx0 + j, p.W, p.shift) == my_rx ? 1u : 0u) << j;
-                    mbits = 0u;
-                    for (int i = 0; i < kh; ++i)
-                        if (region_1d_(wy + ky0 + i, p.H, p.shift) == my_ry) mbits |= xmask << (i * kw);
-                }
-            }
-            if (grp == 0) s_tok[mb * 128 + r] = tok;
-            if (grp == 1 && it + 1 < my_tiles) {
+            if (!early) {
+              if (grp == 1 && it + 1 < my_tiles) {
                 // the (sum, sumsq) slots of my row in the NEXT tile: fetched cold at the tile start they cost ~2k cycles of exposed
                 // latency, so their line is pulled into L1 a whole tile ahead (same closed-form token map)
                 const int win = (tile + static_cast<int>(gridDim.x)) * 2 + (r >> 6);
@@ -534,21 +558,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 int x = (w % nwx) * 8 + nx + p.shift; if (x >= p.W) x -= p.W;
                 const char* np_ = reinterpret_cast<const char*>(p.stats_in + static_cast<long long>((b * p.H + y) * p.W + x) * p.stats_in_stride);
                 for (int o = 0; o < p.stats_in_slots * 8; o += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(np_ + o));
+              }
+              row_setup(tile, tok, mbits, rstd, nrm);
             }
-            float rstd, nrm;
-            {
-                const float2* sp = p.stats_in + static_cast<long long>(tok) * p.stats_in_stride;
-                float s1 = 0.f, s2 = 0.f;
-                for (int k = 0; k < p.stats_in_slots; ++k) {
-                    const float2 v = __ldg(sp + k);
-                    s1 += v.x;
-                    s2 += v.y;
-                }
-                const float inv_c = 1.0f / static_cast<float>(p.C);
-                const float mean = s1 * inv_c;
-                rstd = rsqrtf(fmaxf(s2 * inv_c - mean * mean, 0.f) + p.ln_eps);
-                nrm = -mean * rstd;
-            }
+            if (grp == 0) s_tok[mb * 128 + r] = tok;
             const float2 rstd2 = f2_(rstd, rstd), nrm2 = f2_(nrm, nrm);
 
             for (int h = 0; h < p.nH; ++h) {
@@ -601,6 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 2);
 
                 // ---- softmax over my window's 64 keys, 16 per thread
+                if (early && h == 0 && it + 1 < my_tiles) row_setup(tile + static_cast<int>(gridDim.x), tok_n, mbits_n, rstd_n, nrm_n);
                 mbar_wait(&bars->s_full, par);
                 tc_fence_after_sync();
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 3);
@@ -638,15 +652,29 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     const float2 nmx = f2_(-mx, -mx);
                     float2 acc = f2_(0.f, 0.f);
                     uint32_t pk[8];
+#ifndef ADSR_NO_FASTPATH
+                    if (__all_sync(0xffffffffu, mbits == 0xffffu)) {     // no key of this warp's rows is masked (warp-uniform: a divergent
+                                                                         // branch would run the exponentials twice)
 #pragma unroll
-                    for (int k = 0; k < 16; k += 2) {
-                        const float2 d = __fadd2_rn(f2_(t[k], t[k + 1]), nmx);
-                        float2 e = f2_(ex2_approx(d.x), ex2_approx(d.y));
-                        // keys of another mask region get -100 in the reference: their probability is exp(-100) ~ 0
-                        if (!((mbits >> k) & 1u)) e.x = 0.f;
-                        if (!((mbits >> (k + 1)) & 1u)) e.y = 0.f;
-                        acc = __fadd2_rn(acc, e);
-                        pk[k >> 1] = pack_bf16x2(e.x, e.y);
+                        for (int k = 0; k < 16; k += 2) {
+                            const float2 d = __fadd2_rn(f2_(t[k], t[k + 1]), nmx);
+                            const float2 e = f2_(ex2_approx(d.x), ex2_approx(d.y));
+                            acc = __fadd2_rn(acc, e);
+                            pk[k >> 1] = pack_bf16x2(e.x, e.y);
+                        }
+                    } else
+#endif
+                    {
+#pragma unroll
+                        for (int k = 0; k < 16; k += 2) {
+                            const float2 d = __fadd2_rn(f2_(t[k], t[k + 1]), nmx);
+                            float2 e = f2_(ex2_approx(d.x), ex2_approx(d.y));
+                            // keys of another mask region get -100 in the reference: their probability is exp(-100) ~ 0
+                            if (!((mbits >> k) & 1u)) e.x = 0.f;
+                            if (!((mbits >> (k + 1)) & 1u)) e.y = 0.f;
+                            acc = __fadd2_rn(acc, e);
+                            pk[k >> 1] = pack_bf16x2(e.x, e.y);
+                        }
                     }
                     s_sum[grp * 128 + r] = acc.x + acc.y;
                     // P in place: key j of the tile -> packed column j / 2; the same keys' slots of the OTHER window get zeros
@@ -795,6 +823,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 }
                 named_bar_sync(1 + quad, 128);   // panels copied out / s_stat consumed before the next tile's k, v, s_max, s_sum writes
             }
+            if (early) { tok = tok_n; mbits = mbits_n; rstd = rstd_n; nrm = nrm_n; }
         }
     }
 
@@ -834,6 +863,7 @@ int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj) {
     // spare TMEM (the narrowest block): q|k|v gets accumulator columns of its own behind O, so that the next head's q|k|v MMAs can
     // be issued as soon as S is (they no longer overwrite P) instead of after P V
     p.col_acc = (p.fuse_proj && p.cp + 2 * hdp + 128 + 3 * hdp <= 512) ? p.cp + 2 * hdp + 128 : -1;
+    p.early_setup = p.col_acc >= 0 ? 1 : 0;
     // a [3 hdp x 64] qkv slab is one ring slot and one issue step (every step costs ~400 cycles of wait / commit bookkeeping on
     // top of its MMAs, so steps are kept as large as the MMA N limit of 256 allows); 3 hdp > 256: two N pieces
     const int n3 = 3 * hdp;

@@ -106,3 +106,29 @@ def test_swin_attn_many_tiles_per_cta_and_rect():
     _case(40, 32, 32, 180, 6, 4, True, seed=7)          # 320 window pairs on 148 SMs: several tiles per CTA
     _case(2, 16, 40, 212, 4, 4, True, seed=8)           # rectangular image, wrap in both directions
     _case(1, 8, 16, 276, 6, 0, True, seed=9)            # a single tile
+
+
+def _set_attn2(enabled: int):
+    import ctypes
+    abi = mod("_abi")
+    f = abi.lib().adsr_debug_set_swin_attn2
+    f.restype, f.argtypes = None, [ctypes.c_int]
+    f(enabled)
+
+
+@pytest.mark.parametrize("C,heads", [(180, 6), (212, 4), (276, 6)])
+@pytest.mark.parametrize("shift", [0, 4])
+@pytest.mark.parametrize("variant", [1, 0])
+def test_swin_attn2_two_heads_in_flight(C, heads, shift, variant):
+    """qkv + attention only (proj stays a GEMM): the two-heads-in-flight kernel of csrc/swin_attn2.cu (variant 1: two epilogue
+    groups own the even / odd heads) and the one-head-at-a-time kernel of csrc/swin_attn.cu (variant 0) on the DRCT-L block
+    shapes whose two TMEM regions + two k/v panel sets fit, several tiles per CTA."""
+    abi, pack = mod("_abi"), mod("pack")
+    assert abi.lib().adsr_swin_attn2_covers(C, heads, pack.head_pad(C // heads)) == 1
+    _set_attn2(variant)
+    try:
+        _case(40, 32, 32, C, heads, shift, False, seed=C + shift + variant)
+        _case(1, 8, 16, C, heads, 0, False, seed=3)            # a single tile: only one head per group in flight at the end
+        _case(3, 16, 24, C, heads, shift, False, seed=5)       # 9 tiles on 148 SMs: one tile per CTA, rectangular
+    finally:
+        _set_attn2(1)

@@ -54,7 +54,30 @@ for (C, heads, shift) in shapes:
         ops.window_attention(qkv, att, table, B, H, W, 8, shift, heads, hd, hdp)
         ops.tc_gemm(att, heads * hdp, pp, y, res=x, stats_out=(st_y, 0))
 
+    def attn_only():
+        ops.swin_attn(x, pa, table, att, B, H, W, shift, (stats, 2), False)
+
+    def proj_only():
+        ops.tc_gemm(att, heads * hdp, pp, y, res=x, stats_out=(st_y, 0))
+
     bf, af = timeit(fused)
     bs, as_ = timeit(separate)
-    print(f"attn half C={C} heads={heads} hd={hd:3d} shift={shift} mode={mode}: fused {bf*1e3:7.1f} us (avg {af*1e3:7.1f}) "
-          f"{fl/bf/1e9:6.1f} TFLOP/s   separate {bs*1e3:7.1f} us")
+    line = (f"attn half C={C} heads={heads} hd={hd:3d} shift={shift} mode={mode}: fused {bf*1e3:7.1f} us (avg {af*1e3:7.1f}) "
+            f"{fl/bf/1e9:6.1f} TFLOP/s   separate {bs*1e3:7.1f} us")
+    import ctypes
+    lib = importlib.import_module(PKG + "._abi").lib()
+    has2 = hasattr(lib, "adsr_debug_set_swin_attn2")
+    if has2:
+        lib.adsr_debug_set_swin_attn2.restype, lib.adsr_debug_set_swin_attn2.argtypes = None, [ctypes.c_int]
+    fa = 2.0 * M * C * 3 * C + 4.0 * M * 64 * C
+    for variant in ((1, 0) if has2 else (0,)):
+        if has2:
+            lib.adsr_debug_set_swin_attn2(variant)
+        covers = lib.adsr_swin_attn2_covers(C, heads, hdp) if has2 else 0
+        ba, _ = timeit(attn_only)
+        line += f"   | attn-only v{variant}{'*' if covers else ' '} {ba*1e3:7.1f} us {fa/ba/1e9:6.1f} TF"
+    if has2:
+        lib.adsr_debug_set_swin_attn2(1)
+    bp, _ = timeit(proj_only)
+    line += f"   proj GEMM {bp*1e3:6.1f} us"
+    print(line)
