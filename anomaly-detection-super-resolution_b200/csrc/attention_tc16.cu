@@ -86,15 +86,10 @@ __device__ __forceinline__ void tm_ld32(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tm_st32(uint32_t taddr, const uint32_t* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
-        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
-        "r"(v[31])
-        : "memory");
+__device__ __forceinline__ void tm_st8x(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
 }
 __device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
@@ -119,8 +114,9 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn16_tc_kernel(const __g
     uint8_t* stage = q_ring + 2 * p.nbuf * q_bytes;                    // [stream] 128 rows x 64 B
     float* s_tab = reinterpret_cast<float*>(stage + 2 * kStageBytes);  // [4 copies][kTabCopy]
     float* s_max = s_tab + 4 * kTabCopy;                               // [stream][half][128]
+    float* s_bmax = reinterpret_cast<float*>(smem + p.nbuf * (2 * kv_bytes + 2 * q_bytes) + 2 * kStageBytes + 4 * kTabCopy * 4 + 2 * 512 * 4);   // [20 warps]
     float* s_sum = s_max + 512;                                        // [stream][half][128]
-    Bars16* bars = reinterpret_cast<Bars16*>(s_sum + 512);
+    Bars16* bars = reinterpret_cast<Bars16*>(s_sum + 512 + 32);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -131,12 +127,18 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn16_tc_kernel(const __g
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     // copy s of the x-reversed table: C_s[dy][i] = T[dy][30 - (i + s)] * log2(e)   (dy = yq - yk + 15, dx = xq - xk + 15;
     // the 16 keys kx = 0..15 of a key row are C_s[dy][(15 - xq - s) + kx] with s = (15 - xq) % 4: 16-byte aligned)
+    float bmax_part = 0.f;                                             // upper bound of the bias (>= 0: the pad entries are zeros)
     for (int i = threadIdx.x; i < 4 * kTabCopy; i += kThreads) {
         const int s = i / kTabCopy, rem = i - s * kTabCopy;
         const int dy = rem / kTabPitch, j = rem - dy * kTabPitch;
         const int e = j + s;
-        s_tab[i] = (dy < 31 && e <= 30) ? __ldg(p.table + (dy * 31 + (30 - e)) * p.nH + head) * 1.4426950408889634f : 0.f;
+        const float v = (dy < 31 && e <= 30) ? __ldg(p.table + (dy * 31 + (30 - e)) * p.nH + head) * 1.4426950408889634f : 0.f;
+        s_tab[i] = v;
+        bmax_part = fmaxf(bmax_part, v);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bmax_part = fmaxf(bmax_part, __shfl_xor_sync(0xffffffffu, bmax_part, o));
+    if (lane == 0) s_bmax[warp] = bmax_part;
     if (warp == kMmaWarp && lane == 0) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->k_full[b], kProducerWarps * 32);
@@ -326,6 +328,8 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn16_tc_kernel(const __g
         const int t256 = (half * 4 + quad) * 32 + lane;                // thread index inside the stream
         const uint32_t stage_g = smem_u32(stage + g * kStageBytes);
         const float ninf = -INFINITY;
+        float bmax = 0.f;
+        for (int w = 0; w < kThreads / 32; ++w) bmax = fmaxf(bmax, s_bmax[w]);
 
         for (int i = 0; i < n_units; ++i) {
             const int win = slot + i * p.n_slots;
@@ -344,50 +348,30 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn16_tc_kernel(const __g
             const bool masked = (ymask & xmask) != 0xffffu;
             const uint32_t par = static_cast<uint32_t>(i) & 1;
 
-            // ---- pass A: logits = S * scale + bias (+ mask) back in place, row max
+            // ---- pass A: an UPPER BOUND of the row's largest logit, scale * max_k S + max(bias): softmax is shift-invariant, so any
+            // bound within a few units of the true maximum serves (the bias spans a few units; the probabilities stay far from
+            // underflow) -- no bias look-ups, no write-back
             mbar_wait(&bars->s_full[g], par);
             tc_fence_after_sync();
             float mx = ninf;
+            {
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t col = static_cast<uint32_t>(128 * half + 32 * c);
-                uint32_t raw[32];
-                tm_ld32(treg + col, raw);
-                tmem_ld_wait();
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t ra[32];
+                    tm_ld32(treg + static_cast<uint32_t>(128 * half + 32 * c), ra);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int kr = 0; kr < 2; ++kr) {
-                    const int ky = 8 * half + 2 * c + kr;
-                    const uint32_t bp = tab + static_cast<uint32_t>((yq - ky + 15) * kTabPitch * 4);
-                    const bool yok = (ymask >> ky) & 1u;
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        float4 bv;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bv.x), "=f"(bv.y), "=f"(bv.z), "=f"(bv.w) : "r"(bp + 16u * m));
-                        const int o = 16 * kr + 4 * m;
-                        float2 v0 = __ffma2_rn(make_float2(__uint_as_float(raw[o]), __uint_as_float(raw[o + 1])), sc2, make_float2(bv.x, bv.y));
-                        float2 v1 = __ffma2_rn(make_float2(__uint_as_float(raw[o + 2]), __uint_as_float(raw[o + 3])), sc2, make_float2(bv.z, bv.w));
-                        if (masked) {                                  // -100 in the reference: exp(-100) of the row max ~ 0
-                            const uint32_t xm = yok ? (xmask >> (4 * m)) : 0u;
-                            if (!(xm & 1u)) v0.x = ninf;
-                            if (!(xm & 2u)) v0.y = ninf;
-                            if (!(xm & 4u)) v1.x = ninf;
-                            if (!(xm & 8u)) v1.y = ninf;
-                        }
-                        mx = fmaxf(mx, fmaxf(fmaxf(v0.x, v0.y), fmaxf(v1.x, v1.y)));
-                        raw[o] = __float_as_uint(v0.x);
-                        raw[o + 1] = __float_as_uint(v0.y);
-                        raw[o + 2] = __float_as_uint(v1.x);
-                        raw[o + 3] = __float_as_uint(v1.y);
-                    }
+                    for (int k = 0; k < 32; k += 4)
+                        mx = fmaxf(fmaxf(mx, fmaxf(__uint_as_float(ra[k]), __uint_as_float(ra[k + 1]))),
+                                   fmaxf(__uint_as_float(ra[k + 2]), __uint_as_float(ra[k + 3])));
                 }
-                tm_st32(treg + col, raw);
             }
             *my_max = mx;
-            tmem_st_wait();
             named_bar_sync(pair_bar, 64);
-            mx = fmaxf(mx, my_max[other]);
+            mx = fmaf(fmaxf(mx, my_max[other]), p.scale_log2e, bmax);
 
-            // ---- pass B: unnormalised probabilities in place (lower half ascending -> [0, 64), upper half descending -> [192, 256))
+            // ---- pass B: logits = S * scale + bias, unnormalised probabilities in place (lower key half ascending -> columns
+            // [0, 64), upper half descending -> [192, 256)); masked keys (-100 in the reference) get probability 0
             {
                 const float2 nmx = make_float2(-mx, -mx);
                 float2 acc = make_float2(0.f, 0.f);
@@ -396,16 +380,40 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn16_tc_kernel(const __g
                     const int c = half ? 3 - cc : cc;
                     uint32_t raw[32];
                     tm_ld32(treg + static_cast<uint32_t>(128 * half + 32 * c), raw);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
 #pragma unroll
-                    for (int k = 0; k < 32; k += 2) {
-                        const float2 d = __fadd2_rn(make_float2(__uint_as_float(raw[k]), __uint_as_float(raw[k + 1])), nmx);
-                        const float2 e = make_float2(ex2_approx(d.x), ex2_approx(d.y));
-                        acc = __fadd2_rn(acc, e);
-                        pk[k >> 1] = pack_bf16x2(e.x, e.y);
+                    for (int kr = 0; kr < 2; ++kr) {
+                        uint32_t pk[8];
+                        const int ky = 8 * half + 2 * c + kr;
+                        const uint32_t bp = tab + static_cast<uint32_t>((yq - ky + 15) * kTabPitch * 4);
+                        float4 bv[4];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bv[m].x), "=f"(bv[m].y), "=f"(bv[m].z), "=f"(bv[m].w) : "r"(bp + 16u * m));
+                        if (kr == 0) tmem_ld_wait();                   // the first key row's biases are already on their way
+                        const uint32_t ybit = (ymask >> ky) & 1u;
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const int o = 16 * kr + 4 * m;
+                            const float2 d0 = __fadd2_rn(__ffma2_rn(make_float2(__uint_as_float(raw[o]), __uint_as_float(raw[o + 1])), sc2,
+                                                                    make_float2(bv[m].x, bv[m].y)), nmx);
+                            const float2 d1 = __fadd2_rn(__ffma2_rn(make_float2(__uint_as_float(raw[o + 2]), __uint_as_float(raw[o + 3])), sc2,
+                                                                    make_float2(bv[m].z, bv[m].w)), nmx);
+                            float2 e0 = make_float2(ex2_approx(d0.x), ex2_approx(d0.y));
+                            float2 e1 = make_float2(ex2_approx(d1.x), ex2_approx(d1.y));
+                            if (masked) {
+                                const uint32_t xm = ybit ? (xmask >> (4 * m)) : 0u;
+                                if (!(xm & 1u)) e0.x = 0.f;
+                                if (!(xm & 2u)) e0.y = 0.f;
+                                if (!(xm & 4u)) e1.x = 0.f;
+                                if (!(xm & 8u)) e1.y = 0.f;
+                            }
+                            acc = __fadd2_rn(acc, __fadd2_rn(e0, e1));
+                            pk[2 * m] = pack_bf16x2(e0.x, e0.y);
+                            pk[2 * m + 1] = pack_bf16x2(e1.x, e1.y);
+                        }
+                        // the chunk's 32 logits are in registers: its packed columns may be overwritten (8 per key row)
+                        tm_st8x(treg + static_cast<uint32_t>((half ? 192 : 0) + 16 * c + 8 * kr), pk);
                     }
-                    tm_st16(treg + static_cast<uint32_t>((half ? 192 : 0) + 16 * c), pk);
                 }
                 my_max[512] = acc.x + acc.y;
             }
@@ -500,7 +508,7 @@ int launch_window_attention_tc16(const void* qkv, long long ldq, void* out, long
     if (p.n_slots > p.n_win) p.n_slots = p.n_win;
     p.scale_log2e = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
     const int smem_bytes = p.nbuf * (2 * p.pan * 256 * 128 + 2 * p.pan * 128 * 128) + 2 * kStageBytes + 4 * kTabCopy * 4 + 2 * 512 * 4 +
-                           static_cast<int>(sizeof(Bars16)) + 64;
+                           static_cast<int>(sizeof(Bars16)) + 128 + 64;
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
     if (cudaFuncSetAttribute(window_attn16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
     window_attn16_tc_kernel<<<p.n_slots * nH, kThreads, smem_bytes, stream>>>(p);
