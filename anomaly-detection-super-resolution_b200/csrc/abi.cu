@@ -1,5 +1,7 @@
 #include <cstdlib>
 // extern "C" entry points that only marshal arguments (the kernels live in the other .cu files).
+#include <string.h>
+
 #include "adsr_kernels.h"
 
 using namespace adsr;
@@ -272,3 +274,62 @@ extern "C" int adsr_swin_attn_bf16(const void* x, int64_t ldx, int B, int H, int
     if (two) return launch_swin_attn2(p, num_sms, static_cast<cudaStream_t>(stream));
     return launch_swin_attn(p, num_sms, static_cast<cudaStream_t>(stream));
 }
+
+// ----------------------------------------------------------------------------- host-side weight packing + workspace sizes
+// (`pack_weights_*` and `*_workspace_bytes`).  Pure host code: loading a model launches no device kernel.
+static inline uint16_t bf16_bits_rn(float f) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(f);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+
+extern "C" int adsr_pack_slab_sw128(const float* host_src, int64_t ld, int rows, int cols, void* host_dst) {
+    if (host_src == nullptr || host_dst == nullptr || rows <= 0 || cols < 0 || cols > 64 || ld < cols) return ADSR_ERR_BAD_SHAPE;
+    uint16_t* dst = static_cast<uint16_t*>(host_dst);
+    for (int r = 0; r < rows; ++r) {
+        const float* src = host_src + static_cast<int64_t>(r) * ld;
+        for (int pos = 0; pos < 8; ++pos) {                    // 16-byte chunk c of the row is stored at position c ^ (r % 8)
+            const int c = pos ^ (r & 7);
+            for (int e = 0; e < 8; ++e) {
+                const int k = c * 8 + e;
+                dst[(static_cast<int64_t>(r) * 8 + pos) * 8 + e] = k < cols ? bf16_bits_rn(src[k]) : uint16_t(0);
+            }
+        }
+    }
+    return ADSR_OK;
+}
+
+extern "C" int adsr_pack_tiles_sw128(const float* host_w, int64_t ld, int n, int k, int bn, int n_tiles, void* host_dst) {
+    if (host_w == nullptr || host_dst == nullptr || n <= 0 || k <= 0 || bn <= 0 || n_tiles <= 0 || n > bn * n_tiles || ld < k) return ADSR_ERR_BAD_SHAPE;
+    const int ks = (k + 63) / 64;
+    uint8_t* dst = static_cast<uint8_t*>(host_dst);
+    const size_t slab = static_cast<size_t>(bn) * 128;
+    memset(dst, 0, slab * ks * n_tiles);
+    for (int t = 0; t < n_tiles; ++t)
+        for (int s = 0; s < ks; ++s) {
+            const int row0 = t * bn, rows = n - row0 < bn ? n - row0 : bn;
+            if (rows <= 0) continue;
+            const int cols = k - 64 * s < 64 ? k - 64 * s : 64;
+            const int st = adsr_pack_slab_sw128(host_w + static_cast<int64_t>(row0) * ld + 64 * s, ld, rows, cols, dst + (static_cast<size_t>(t) * ks + s) * slab);
+            if (st != ADSR_OK) return st;
+        }
+    return ADSR_OK;
+}
+
+extern "C" int64_t adsr_drct_workspace_bytes(int B, int H, int W, int embed_dim, int gc, int upscale, int qkv_cols, int att_cols) {
+    if (B <= 0 || H <= 0 || W <= 0 || embed_dim <= 0 || gc < 0 || upscale < 1 || (upscale & (upscale - 1))) return -1;
+    const int64_t M = static_cast<int64_t>(B) * H * W;
+    const int64_t pitch = (embed_dim + 4 * gc + 63) / 64 * 64, e16 = (embed_dim + 15) / 16 * 16;
+    int64_t bytes = M * (3 * pitch + qkv_cols + att_cols + 2 * e16 + 64) * 2      // slab, y, z, qkv, att, x0, body, f   (bf16 rows)
+                    + M * (12 + 8) * 2 * 4;                                       // per-row (sum, sumsq) slots of slab and y (fp32)
+    int64_t m = M;
+    for (int s = upscale; s > 1; s >>= 1) { m *= 4; bytes += m * 64 * 2; }        // PixelShuffle stages (64 channels)
+    return bytes;
+}
+
+extern "C" int64_t adsr_score_workspace_bytes(int B, int H, int W, int C, int n_ws) {
+    (void)B; (void)H; (void)W; (void)C; (void)n_ws;
+    return 0;                                                                     // the scorer keeps everything on chip
+}
+

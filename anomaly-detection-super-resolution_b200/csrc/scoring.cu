@@ -36,14 +36,22 @@ struct PixelView {
     int is_f32;                  // 0 = uint8, 1 = float
     float div;                   // value / div  (255 for uint8 -> [0,1]; rgb_range for ssim_torch; 1 otherwise)
     int clamp01;                 // clamp to [0,1] after the division (ssim_torch, src/metrics.py:86-87)
+    float quant;                 // > 0: the validation loop's `quantize` (src/trainer.py:45-47) on the raw value first:
+                                 // round_half_even(clamp(x * quant, 0, 255)) / quant with quant = 255 / rgb_range
 };
 
 __device__ __forceinline__ float fetch(const PixelView& v, long long off) {
     float x = v.is_f32 ? __ldg(static_cast<const float*>(v.base) + off)
                        : static_cast<float>(__ldg(static_cast<const uint8_t*>(v.base) + off));
+    if (v.quant > 0.f) x = __fdiv_rn(rintf(fminf(fmaxf(x * v.quant, 0.f), 255.f)), v.quant);
     if (v.div != 1.0f) x = x / v.div;
     if (v.clamp01) x = fminf(fmaxf(x, 0.f), 1.f);
     return x;
+}
+// the MSE / PSNR terms of the validation loop are NOT clamped (psnr_torch, src/metrics.py:70-79), its SSIM terms are
+__device__ __forceinline__ float fetch_mse(PixelView v, long long off, int noclamp) {
+    if (noclamp) v.clamp01 = 0;
+    return fetch(v, off);
 }
 
 // gray value exactly as the reference builds it: channels dotted with the fp32
@@ -61,6 +69,7 @@ struct ScoreParams {
     PixelView sr, hr;
     int H, W, C, n_ws;
     int zero_pad;               // 0 = np.pad(mode="reflect") (ssim_numpy), 1 = zero padding (F.conv2d, ssim_torch)
+    int mse_noclamp;            // the MSE / PSNR terms ignore clamp01 (validation loop: psnr_torch does not clamp, ssim_torch does)
     double C1, C2, psnr_peak2;  // SSIM constants and data_range^2 of the PSNR
     double* scores;
     WsList wl;
@@ -83,8 +92,8 @@ __global__ void __launch_bounds__(1024) score_images_kernel(const ScoreParams p)
             const int ch = static_cast<int>(i % C);
             const long long px = i / C;
             const int r = static_cast<int>(px / W), c = static_cast<int>(px - static_cast<long long>(r) * W);
-            const float d = fetch(p.sr, srb + r * p.sr.sr + c * p.sr.sc + ch * p.sr.sch) -
-                            fetch(p.hr, hrb + r * p.hr.sr + c * p.hr.sc + ch * p.hr.sch);
+            const float d = fetch_mse(p.sr, srb + r * p.sr.sr + c * p.sr.sc + ch * p.sr.sch, p.mse_noclamp) -
+                            fetch_mse(p.hr, hrb + r * p.hr.sr + c * p.hr.sc + ch * p.hr.sch, p.mse_noclamp);
             acc += static_cast<double>(d * d);          // (ref - out) ** 2 on float32 arrays
         }
         double v = acc;
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(1024, 1) score_images_fast_kernel(const ScoreP
         gx[idx] = gray_at(p.hr, oh, C);
         gy[idx] = gray_at(p.sr, os, C);
         for (int ch = 0; ch < C; ++ch) {
-            const float d = fetch(p.sr, os + ch * p.sr.sch) - fetch(p.hr, oh + ch * p.hr.sch);
+            const float d = fetch_mse(p.sr, os + ch * p.sr.sch, p.mse_noclamp) - fetch_mse(p.hr, oh + ch * p.hr.sch, p.mse_noclamp);
             acc_mse += static_cast<double>(d * d);
         }
     }
@@ -401,4 +410,19 @@ extern "C" int adsr_score_images_strided(const void* sr, const void* hr, int is_
     p.C1 = c1; p.C2 = c2; p.psnr_peak2 = psnr_peak * psnr_peak;
     p.scores = scores;
     return launch_score(p, B, host_ws_list, n_ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int adsr_validate_images(const void* sr, const void* hr, int B, int H, int W, int C, const int64_t* host_strides_sr,
+                                    const int64_t* host_strides_hr, float rgb_range, int win_size, double* scores, void* stream) {
+    if (rgb_range <= 0.f) return ADSR_ERR_BAD_SHAPE;
+    adsr::ScoreParams p{};
+    p.sr = {sr, host_strides_sr[0], host_strides_sr[1], host_strides_sr[2], host_strides_sr[3], 1, rgb_range, 1, 255.0f / rgb_range};
+    p.hr = {hr, host_strides_hr[0], host_strides_hr[1], host_strides_hr[2], host_strides_hr[3], 1, rgb_range, 1, 0.f};
+    p.H = H; p.W = W; p.C = C;
+    p.zero_pad = 1;
+    p.mse_noclamp = 1;
+    p.C1 = 0.01 * 0.01 * 255.0 * 255.0; p.C2 = 0.03 * 0.03 * 255.0 * 255.0; p.psnr_peak2 = 1.0;
+    p.scores = scores;
+    const int32_t ws = win_size;
+    return launch_score(p, B, &ws, 1, static_cast<cudaStream_t>(stream));
 }

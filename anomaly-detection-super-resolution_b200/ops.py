@@ -292,6 +292,21 @@ def score_images_strided(sr: torch.Tensor, hr: torch.Tensor, layout: str, window
     return out
 
 
+def validate_images(sr: torch.Tensor, hr: torch.Tensor, rgb_range: float, win_size: int = 11) -> torch.Tensor:
+    """fp32 [B, C, H, W] views (any strides, e.g. the shaved crop) -> fp64 [B, 3] = ssim_torch, mse, psnr_torch per image of the
+    ROUND-quantised SR against HR: the body of the reference's validation loop (src/trainer.py:266-281) in one launch."""
+    _cuda(sr, "sr")
+    assert sr.shape == hr.shape and sr.dtype == torch.float32 and hr.dtype == torch.float32
+    b, c, h, w = sr.shape
+    st = lambda t: (ctypes.c_int64 * 4)(t.stride(0), t.stride(2), t.stride(3), t.stride(1))
+    out = torch.empty(b, 3, dtype=torch.float64, device=sr.device)
+    _t = _begin()
+    check(lib().adsr_validate_images(ptr(sr), ptr(hr), b, h, w, c, st(sr), st(hr), float(rgb_range), int(win_size), ptr(out),
+                                     stream_ptr()), "adsr_validate_images")
+    _count("score_images", 0.0, _t)
+    return out
+
+
 def bicubic_affine(x: torch.Tensor, scale: int, mat: torch.Tensor, bias: torch.Tensor, out: torch.Tensor) -> None:
     _cuda(x, "x")
     b, nc, h, w = x.shape

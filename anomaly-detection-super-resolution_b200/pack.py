@@ -74,6 +74,13 @@ def _swizzle_tiles(w2d: torch.Tensor, bn: int, n_tiles: int) -> tuple[torch.Tens
     """w2d: fp32 [N, Kpad] with Kpad % 64 == 0 -> packed uint8 image."""
     n, kpad = w2d.shape
     ks = kpad // 64
+    if w2d.device.type == "cpu":                       # host parameters: the library's host-side packer (adsr_pack_tiles_sw128)
+        from . import _abi
+        src = w2d.detach().float().contiguous()
+        out = torch.empty(n_tiles * ks * bn * 128, dtype=torch.uint8)
+        _abi.check(_abi.lib().adsr_pack_tiles_sw128(src.data_ptr(), src.stride(0), n, kpad, bn, n_tiles, out.data_ptr()),
+                   "adsr_pack_tiles_sw128")
+        return out, ks
     wp = torch.zeros(n_tiles * bn, kpad, dtype=torch.float32, device=w2d.device)
     wp[:n] = w2d
     t = wp.to(torch.bfloat16).view(n_tiles, bn, ks, 8, 8).permute(0, 2, 1, 3, 4)   # [tile, ks, row, chunk, elem]
@@ -245,6 +252,12 @@ def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
 def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
     """[rows, 64] fp32 -> uint8 image, row r at r*128 B with its 16-byte chunk c at position c ^ (r % 8)."""
     rows = block.shape[0]
+    if block.device.type == "cpu":                     # host parameters: adsr_pack_slab_sw128
+        from . import _abi
+        src = block.detach().float().contiguous()
+        out = torch.empty(rows * 128, dtype=torch.uint8)
+        _abi.check(_abi.lib().adsr_pack_slab_sw128(src.data_ptr(), src.stride(0), rows, 64, out.data_ptr()), "adsr_pack_slab_sw128")
+        return out
     t = block.to(torch.bfloat16).view(rows, 8, 8)
     r = torch.arange(rows, device=block.device)
     pos = torch.arange(8, device=block.device)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 9
+#define ADSR_ABI_VERSION 10
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -224,6 +224,32 @@ int adsr_score_images_strided(const void* sr, const void* hr, int is_f32, int B,
                               const int64_t* host_strides_sr, const int64_t* host_strides_hr, float div,
                               int clamp01, int zero_pad, double c1, double c2, double psnr_peak,
                               const int32_t* host_ws_list, int n_ws, double* scores, void* stream);
+
+/* Validation metrics of the reference's training loop, `Trainer.test` (src/trainer.py:242-304), for a batch of fp32 image
+ * pairs: the SR value is first quantised with ROUNDING (`quantize`, src/trainer.py:45-47: round(clamp(x * 255 / rgb_range, 0,
+ * 255)) / (255 / rgb_range) -- the evaluator truncates instead), then calc_psnr / calc_ssim = psnr_torch / ssim_torch
+ * (src/metrics.py:70-108: / rgb_range, clamp [0,1] for the SSIM, zero-padded win_size box, C1/C2 scaled by 255^2).
+ * sr / hr: fp32 with element strides {image, row, column, channel} (pass the 4-px shaved crop as a strided view).
+ * scores: fp64 [B, 3] = ssim, mse (of the unclamped (sr_q - hr) / rgb_range), psnr per image. */
+int adsr_validate_images(const void* sr, const void* hr, int B, int H, int W, int C,
+                         const int64_t* host_strides_sr, const int64_t* host_strides_hr, float rgb_range, int win_size,
+                         double* scores, void* stream);
+
+/* ---- host-side weight packing and workspace sizes (pack_weights_*, *_workspace_bytes) -----------------
+ * Pure HOST functions (no stream, no device work): the tensor-core operand images are built once per checkpoint
+ * (replacing nothing in the reference: its nn.Linear / nn.Conv2d weights, src/drct.py:245-249, 334-374, are used as stored)
+ * and uploaded with one plain copy per buffer.
+ * adsr_pack_slab_sw128: fp32 [rows, >= cols] (row pitch ld, cols <= 64) -> bf16 [rows x 64] slab in the K-major 128-byte-swizzle
+ *   shared-memory layout (row r at byte r*128, its 16-byte chunk c at position c ^ (r % 8)); columns >= cols are zeros.
+ * adsr_pack_tiles_sw128: fp32 weight [n, k] (nn.Linear layout) -> n_tiles tiles x ceil(k/64) K slabs of [bn x 64] in that
+ *   layout (what adsr_tc_gemm_bf16 streams); rows >= n and columns >= k are zeros.  host_dst: n_tiles*ceil(k/64)*bn*128 bytes.
+ * adsr_drct_workspace_bytes: bytes of caller-owned scratch one DRCT forward of [B, *, H, W] LR inputs needs (dense slab, per-block
+ *   scratch rows with qkv_cols / att_cols head-padded columns, row-statistics slots, PixelShuffle stages); -1 on bad arguments.
+ * adsr_score_workspace_bytes: 0 (the scorer keeps its planes and prefix sums in shared memory). */
+int adsr_pack_slab_sw128(const float* host_src, int64_t ld, int rows, int cols, void* host_dst);
+int adsr_pack_tiles_sw128(const float* host_w, int64_t ld, int n, int k, int bn, int n_tiles, void* host_dst);
+int64_t adsr_drct_workspace_bytes(int B, int H, int W, int embed_dim, int gc, int upscale, int qkv_cols, int att_cols);
+int64_t adsr_score_workspace_bytes(int B, int H, int W, int C, int n_ws);
 
 #ifdef __cplusplus
 }

@@ -192,3 +192,61 @@ def synthetic_dataset(n_images: int, hr: int = 128, nc: int = 3, scale: int = 4,
         lrs.append(lr)
         labels.append(label)
     return np.stack(hrs), np.stack(lrs), np.asarray(labels)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# validation loop of the training script: Trainer.test (src/trainer.py:242-304)
+# ---------------------------------------------------------------------------------------------------------------------
+def quantize_round(img: np.ndarray, rgb_range: float) -> np.ndarray:
+    """`quantize` (src/trainer.py:45-47): img.mul(255 / rgb_range).clamp(0, 255).round().div(255 / rgb_range), fp32, round half to even."""
+    pr = np.float32(255.0 / rgb_range)
+    return (np.rint(np.clip(img.astype(np.float32) * pr, 0, 255)).astype(np.float32) / pr).astype(np.float32)
+
+
+def psnr_torch_np(sr: np.ndarray, hr: np.ndarray, rgb_range: float) -> float:
+    """`psnr_torch` (src/metrics.py:70-79) on [1, C, H, W] arrays: shave 4, no clamp."""
+    diff = (sr.astype(np.float32) - hr.astype(np.float32)) / np.float32(rgb_range)
+    if sr.shape[-1] > 8:
+        diff = diff[..., 4:-4, 4:-4]
+    mse = float(np.mean(diff.astype(np.float64) ** 2))
+    return float("inf") if mse == 0 else 10.0 * float(np.log10(1.0 / mse))
+
+
+def ssim_torch_np(sr: np.ndarray, hr: np.ndarray, rgb_range: float, win_size: int = 11) -> float:
+    """`ssim_torch` (src/metrics.py:82-108) on [1, C, H, W] arrays: / rgb_range, clamp [0, 1], shave 4, gray for 3 channels, ZERO-padded
+    win_size box filter (F.conv2d padding), C1 / C2 scaled by 255^2 (the reference's quirk), mean of the map."""
+    a = np.clip(sr.astype(np.float32) / np.float32(rgb_range), 0, 1)
+    b = np.clip(hr.astype(np.float32) / np.float32(rgb_range), 0, 1)
+    if a.shape[-1] > 8:
+        a, b = a[..., 4:-4, 4:-4], b[..., 4:-4, 4:-4]
+    if a.shape[1] > 1:
+        cv = (np.array([65.738, 129.057, 25.064], dtype=np.float32) / np.float32(256)).reshape(1, 3, 1, 1)
+        a, b = (a * cv).sum(1, keepdims=True), (b * cv).sum(1, keepdims=True)
+    a, b = a[0, 0].astype(np.float64), b[0, 0].astype(np.float64)
+    c1, c2 = 0.01 ** 2 * 255.0 ** 2, 0.03 ** 2 * 255.0 ** 2
+    h = win_size // 2
+
+    def box(x):
+        xp = np.pad(x, h, mode="constant")
+        c = np.zeros((xp.shape[0] + 1, xp.shape[1] + 1))
+        c[1:, 1:] = xp.cumsum(0).cumsum(1)
+        n0, n1 = x.shape
+        return (c[win_size:win_size + n0, win_size:win_size + n1] - c[:n0, win_size:win_size + n1] - c[win_size:win_size + n0, :n1] +
+                c[:n0, :n1]) / (win_size * win_size)
+
+    mu1, mu2 = box(a), box(b)
+    s1, s2, s12 = box(a * a) - mu1 * mu1, box(b * b) - mu2 * mu2, box(a * b) - mu1 * mu2
+    m = ((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (s1 + s2 + c2))
+    return float(m.mean())
+
+
+def validate_pairs(sr: np.ndarray, hr: np.ndarray, rgb_range: float):
+    """Body of Trainer.test over a set of [n, C, H, W] pairs, one image at a time (the loader's batch size is 1):
+    -> (per-image psnr, per-image ssim, eval_psnr, eval_ssim) with eval_* = sum / len(loader_test)."""
+    ps, ss = [], []
+    for i in range(sr.shape[0]):
+        q = quantize_round(sr[i:i + 1], rgb_range)
+        ps.append(psnr_torch_np(q, hr[i:i + 1], rgb_range))
+        ss.append(ssim_torch_np(q, hr[i:i + 1], rgb_range))
+    return np.asarray(ps), np.asarray(ss), float(sum(ps) / len(ps)), float(sum(ss) / len(ss))
+

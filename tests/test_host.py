@@ -192,3 +192,42 @@ def test_forward_refuses_cpu(pkg):
     m = drct.DRCT(Opt())
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 1, 16, 16))
+
+
+def test_host_side_pack_functions_match_torch_restatement():
+    """adsr_pack_slab_sw128 / adsr_pack_tiles_sw128 (host code in the C ABI, SURVEY.md 8b `pack_weights_*`): bit-identical to
+    the gather-based torch restatement of the K-major 128-byte-swizzle layout, zero padding included."""
+    import importlib
+    import torch
+    pack = importlib.import_module("anomaly-detection-super-resolution_b200.pack")
+    torch.manual_seed(0)
+    pos = torch.arange(8)
+    for rows in (16, 37, 240):
+        blk = torch.randn(rows, 64)
+        got = pack._swizzle_slab(blk)
+        t = blk.to(torch.bfloat16).view(rows, 8, 8)
+        r = torch.arange(rows)
+        src = (pos[None, :] ^ (r[:, None] % 8))[:, :, None].expand(rows, 8, 8)
+        assert torch.equal(got, torch.gather(t, 1, src).contiguous().view(torch.uint8).reshape(-1))
+    for (n, k, bn, nt) in ((200, 192, 128, 2), (32, 320, 32, 1), (540, 180, 128, 5)):
+        kpad = (k + 63) // 64 * 64
+        w = torch.zeros(n, kpad)
+        w[:, :k] = torch.randn(n, k)
+        data, ks = pack._swizzle_tiles(w, bn, nt)
+        wp = torch.zeros(nt * bn, kpad)
+        wp[:n] = w
+        t = wp.to(torch.bfloat16).view(nt, bn, ks, 8, 8).permute(0, 2, 1, 3, 4)
+        rr = torch.arange(bn)
+        idx = (pos[None, :] ^ (rr[:, None] % 8))[None, None, :, :, None].expand(nt, ks, bn, 8, 8)
+        assert torch.equal(data, torch.gather(t.contiguous(), 3, idx).contiguous().view(torch.uint8).reshape(-1))
+
+
+def test_workspace_queries():
+    import importlib
+    abi = importlib.import_module("anomaly-detection-super-resolution_b200._abi")
+    lib = abi.lib()
+    b1 = lib.adsr_drct_workspace_bytes(1, 32, 32, 180, 32, 4, 768, 320)
+    b256 = lib.adsr_drct_workspace_bytes(256, 32, 32, 180, 32, 4, 768, 320)
+    assert b1 > 0 and b256 == 256 * b1                       # linear in the batch
+    assert lib.adsr_drct_workspace_bytes(1, 32, 32, 180, 32, 3, 768, 320) == -1
+    assert lib.adsr_score_workspace_bytes(256, 128, 128, 3, 13) == 0

@@ -92,3 +92,17 @@ def test_quantize_truncates():
 def test_window_sizes():
     assert S.window_sizes_for(128) == list(range(3, 124, 10))
     assert len(S.window_sizes_for(256)) == 26
+
+
+def test_validation_oracle_matches_reference_goldens(golden_dir):
+    """quantize (rounding) + psnr_torch + ssim_torch, the body of Trainer.test: oracle restatement vs the reference's own outputs."""
+    import os
+    import numpy as np
+    from oracle import scoring_oracle as S
+    g = np.load(os.path.join(golden_dir, "validation.npz"))
+    for k in range(int(g["n"])):
+        ps, ss, ep, es = S.validate_pairs(g[f"c{k}.sr"], g[f"c{k}.hr"], float(g[f"c{k}.rgb_range"]))
+        want_p, want_s = g[f"c{k}.psnr"], g[f"c{k}.ssim"]
+        fin = np.isfinite(want_p)
+        assert np.array_equal(np.isinf(ps), np.isinf(want_p))
+        assert np.abs(ps[fin] - want_p[fin]).max() < 1e-5 and np.abs(ss - want_s).max() < 1e-6
