@@ -54,6 +54,7 @@ _SIGNATURES = {
                                c_void_p, c_float, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "adsr_conv_last_quant": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                      c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "adsr_u8_to_float_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "adsr_quantize_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "adsr_score_images": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int32), c_int, c_void_p,
                                   c_void_p]),

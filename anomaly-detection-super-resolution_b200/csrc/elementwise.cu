@@ -489,6 +489,17 @@ __global__ void quantize_u8_kernel(const float* __restrict__ x, int B, int nc, i
     }
 }
 
+// uint8 HWC (what the PNG decoder yields) -> fp32 NCHW scaled by rgb_range / 255: the loader's np2Tensor (src/data.py:11-17) on the device
+__global__ void u8_to_float_nchw_kernel(const uint8_t* __restrict__ x, int B, int nc, int H, int W, float scale, float* __restrict__ out) {
+    const long long total = static_cast<long long>(B) * H * W;
+    for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total;
+         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = pix / (H * W);
+        const long long rem = pix - b * H * W;
+        for (int c = 0; c < nc; ++c) out[(b * nc + c) * H * W + rem] = static_cast<float>(__ldg(x + pix * nc + c)) * scale;
+    }
+}
+
 inline int grid_for(long long work_items, int per_block, int cap = 148 * 16) {
     long long g = (work_items + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -594,6 +605,14 @@ extern "C" int adsr_conv_last_quant(const void* in, int64_t ld_in, int B, int H,
     conv_last_quant_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(in), ld_in, B, H, W, Cin, weight, bias, nc, mean, 1.0f / img_range,
         static_cast<float>(255.0 / static_cast<double>(rgb_range)), out_nchw, out_u8_hwc);
+    return check_launch();
+}
+
+extern "C" int adsr_u8_to_float_nchw(const uint8_t* x_u8_hwc, int B, int nc, int H, int W, float rgb_range, float* out_nchw, void* stream) {
+    if (B <= 0) return ADSR_OK;
+    if (x_u8_hwc == nullptr || out_nchw == nullptr || nc < 1 || H < 1 || W < 1) return ADSR_ERR_BAD_SHAPE;
+    u8_to_float_nchw_kernel<<<grid_for(static_cast<long long>(B) * H * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_u8_hwc, B, nc, H, W, static_cast<float>(static_cast<double>(rgb_range) / 255.0), out_nchw);
     return check_launch();
 }
 

@@ -146,14 +146,19 @@ def scan_split(data_dir: str, scale: int) -> Tuple[List[str], List[str]]:
     return names_hr, names_lr
 
 
-def load_pair(f_hr: str, f_lr: str, scale: int, n_colors: int, rgb_range: float):
-    """-> (lr [nc,h,w] float32, hr [nc,H,W] float32) in [0, rgb_range] (src/data.py:11-19, 84-92, 176-183)."""
+def load_pair(f_hr: str, f_lr: str, scale: int, n_colors: int, rgb_range: float, raw_u8: bool = False):
+    """-> (lr [nc,h,w] float32, hr [nc,H,W] float32) in [0, rgb_range] (src/data.py:11-19, 84-92, 176-183).
+    raw_u8: when both decoded images are uint8 and rgb_range == 255 (the reference default: the float conversion and the evaluator's
+    uint8 truncation are then exact inverses) return the uint8 HWC arrays instead -- a quarter of the bytes cross PCIe and the float
+    scaling runs on the device (adsr_u8_to_float_nchw); same results."""
     from PIL import Image
 
     hr = _set_channel(np.array(Image.open(f_hr)), n_colors)
     lr = _set_channel(np.array(Image.open(f_lr)), n_colors)
     ih, iw = lr.shape[:2]
     hr = hr[0:ih * scale, 0:iw * scale]
+    if raw_u8 and hr.dtype == np.uint8 and lr.dtype == np.uint8 and float(rgb_range) == 255.0:
+        return torch.from_numpy(np.ascontiguousarray(lr)), torch.from_numpy(np.ascontiguousarray(hr))
     to_t = lambda a: torch.from_numpy(np.ascontiguousarray(a.transpose(2, 0, 1))).float().mul_(rgb_range / 255)
     return to_t(lr), to_t(hr)
 
@@ -231,6 +236,8 @@ class BatchedEvaluator:
             hr_u8 = ops.quantize_u8(hr_d, self.rgb_range)
         h, w = hr_u8.shape[1], hr_u8.shape[2]
         target = self.model.model if hasattr(self.model, 'model') else self.model
+        if lr_d.dtype == torch.uint8:                         # decoded PNG bytes: np2Tensor (src/data.py:11-17) on the device
+            lr_d = ops.u8_to_float(lr_d, self.rgb_range)
         _, sr_u8 = target.run(lr_d, want_float=False, want_u8=True)
         if sr_u8.shape[1] != h or sr_u8.shape[2] != w:        # sr = sr[..., :h, :w]  (src/evaluate.py:212-213)
             sr_u8 = sr_u8[:, :h, :w, :].contiguous()
@@ -382,7 +389,9 @@ def evaluate_on_test(opt, checkpoint_model_path, output_dir: str, save_images: b
         """(lr, hr) pinned host batches in evaluation order; `order` records the image ids of each batch."""
         for s in range(0, len(mine), bs):
             idx = mine[s:s + bs]
-            pairs = [load_pair(entries[i][2], entries[i][3], scale, opt.n_colors, opt.rgb_range) for i in idx]
+            pairs = [load_pair(entries[i][2], entries[i][3], scale, opt.n_colors, opt.rgb_range, raw_u8=True) for i in idx]
+            if len({p[0].dtype for p in pairs}) > 1:           # mixed decodes (should not happen within a dataset): all float
+                pairs = [load_pair(entries[i][2], entries[i][3], scale, opt.n_colors, opt.rgb_range) for i in idx]
             shapes = {(tuple(p[0].shape), tuple(p[1].shape)) for p in pairs}
             groups = [list(range(len(idx)))] if len(shapes) == 1 else [[j] for j in range(len(idx))]
             for g in groups:                                  # mixed sizes fall back to one image per launch

@@ -236,6 +236,20 @@ def conv_last_quant(x: torch.Tensor, b: int, h: int, w: int, cin: int, weight, b
     _count("conv_last", 2.0 * b * h * w * 9 * cin * nc, _t)
 
 
+def u8_to_float(x_u8: torch.Tensor, rgb_range: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 NHWC (decoded PNGs) -> fp32 NCHW in [0, rgb_range]: the loader's `np2Tensor` (src/data.py:11-17) on the device."""
+    _cuda(x_u8, "x_u8")
+    assert x_u8.dtype == torch.uint8 and x_u8.dim() == 4
+    x_u8 = x_u8.contiguous()
+    b, h, w, nc = x_u8.shape
+    if out is None:
+        out = torch.empty(b, nc, h, w, dtype=torch.float32, device=x_u8.device)
+    _t = _begin()
+    check(lib().adsr_u8_to_float_nchw(ptr(x_u8), b, nc, h, w, rgb_range, ptr(out), stream_ptr()), "adsr_u8_to_float_nchw")
+    _count("u8_to_float", 0.0, _t)
+    return out
+
+
 def quantize_u8(x: torch.Tensor, rgb_range: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 NCHW in [0, rgb_range] -> uint8 NHWC, truncating (src/evaluate.py:214-215)."""
     _cuda(x, "x")

@@ -330,8 +330,10 @@ def run_workload(mods, workload: str, B: int, steps: int, warmup: int, dev, rank
     base = min(B, 64)                                   # distinct images generated per rank (tiled up to B)
     hr_u8, lr_u8, labels = synthetic_pairs(base, seed=1234 + rank, hr=hr_side)
     reps = (B + base - 1) // base
-    lr_h = to_float_nchw(np.tile(lr_u8, (reps, 1, 1, 1))[:B]).pin_memory()
-    hr_h = to_float_nchw(np.tile(hr_u8, (reps, 1, 1, 1))[:B]).pin_memory()
+    # decoded-PNG bytes (uint8 HWC), exactly what evaluate_on_test hands the evaluator: the float scaling of the loader
+    # (src/data.py:11-17) runs on the device, a quarter of the bytes cross PCIe
+    lr_h = torch.from_numpy(np.ascontiguousarray(np.tile(lr_u8, (reps, 1, 1, 1))[:B])).pin_memory()
+    hr_h = torch.from_numpy(np.ascontiguousarray(np.tile(hr_u8, (reps, 1, 1, 1))[:B])).pin_memory()
     labels = np.tile(labels, reps)[:B]
     lr_d, hr_d = lr_h.to(dev), hr_h.to(dev)
     wss = metrics.window_sizes_for(hr_side)
@@ -396,7 +398,7 @@ def run_workload(mods, workload: str, B: int, steps: int, warmup: int, dev, rank
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * B * steps / float(dt.item())
-    h2d = lr_h.numel() * 4 + hr_h.numel() * 4
+    h2d = lr_h.numel() * lr_h.element_size() + hr_h.numel() * hr_h.element_size()
     d2h = B * (len(wss) + 2) * 8
 
     # ---- AUC on the gathered table (host, rank 0): the step's real consumer
@@ -457,7 +459,7 @@ def run_workload(mods, workload: str, B: int, steps: int, warmup: int, dev, rank
         "config": {"workload": wl + f", inference + scoring ({n_ws}-window SSIM sweep + MSE + PSNR per image)",
                    "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world} (images sharded by rank; "
                    "one all_gather of score rows + ids)", "l2": "flushed between steps (256 MiB write)",
-                   "weights": "random init, seed 1", "auc": auc},
+                   "weights": "random init, seed 1", "inputs": "uint8 HWC image pairs (decoded-PNG bytes)", "auc": auc},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks.summary(),

@@ -187,6 +187,10 @@ int adsr_conv_last_quant(const void* in, int64_t ld_in, int B, int H, int W, int
                          const float* weight, const float* bias, int nc, const float* mean, float img_range,
                          float rgb_range, float* out_nchw, uint8_t* out_u8_hwc, void* stream);
 
+/* uint8 HWC images (PNG decoder output, host-pinned then copied as bytes: a quarter of the fp32 traffic) -> fp32 NCHW in
+ * [0, rgb_range]: the reference loader's np2Tensor, `tensor.mul_(rgb_range / 255)` (src/data.py:11-17), on the device. */
+int adsr_u8_to_float_nchw(const uint8_t* x_u8_hwc, int B, int nc, int H, int W, float rgb_range, float* out_nchw, void* stream);
+
 /* ---- uint8 truncation of an fp32 NCHW image batch (HR side of src/evaluate.py:215) ----------------------- */
 int adsr_quantize_u8(const float* x_nchw, int B, int nc, int H, int W, float rgb_range, uint8_t* out_u8_hwc,
                      void* stream);

@@ -215,3 +215,29 @@ def test_evaluate_on_test_many_equal_batches_match_eager(tmp_path, capsys, monke
     capsys.readouterr()
     assert np.array_equal(got["scores"], want["scores"])
     assert len({tuple(r) for r in got["scores"].round(9).tolist()}) > n // 2     # rows are not copies of one batch
+
+
+def test_u8_inputs_equal_float_inputs():
+    """uint8 HWC batches (decoded PNG bytes; the loader's float scaling runs on the device) give bit-identical scores and SR
+    images to the float NCHW tensors the reference's loader yields (rgb_range 255)."""
+    evaluate, drct, metrics, ops = (importlib.import_module(f"{PKG}.{m}") for m in ("evaluate", "drct", "metrics", "ops"))
+    from gpu_common import DrctOpt
+
+    cfg = O.DrctCfg(num_layers=1)
+    sd = O.make_state_dict(cfg, seed=6)
+    model = drct.DRCT(DrctOpt(layers=1))
+    model.load_state_dict(sd, strict=True)
+    model = model.to("cuda").eval()
+    hr, lr, _ = S.synthetic_dataset(6, hr=128, nc=3, scale=4, seed=15)
+    lr_u8, hr_u8 = torch.from_numpy(lr).cuda(), torch.from_numpy(hr).cuda()
+    to_t = lambda a: torch.from_numpy(np.ascontiguousarray(a.transpose(0, 3, 1, 2))).float().mul_(255.0 / 255)
+    got_f = ops.u8_to_float(lr_u8, 255.0)
+    assert torch.equal(got_f.cpu(), to_t(lr))
+    assert torch.equal(ops.u8_to_float(lr_u8, 1.0).cpu(), torch.from_numpy(np.ascontiguousarray(lr.transpose(0, 3, 1, 2))).float().mul_(1.0 / 255))
+    wss = metrics.window_sizes_for(128)
+    ev = evaluate.BatchedEvaluator(model, 255.0, wss)
+    ev.use_graph = False
+    a = ev.step(to_t(lr).cuda(), to_t(hr).cuda()).cpu()
+    a_sr = ev.last_sr_u8.cpu()
+    b = ev.step(lr_u8, hr_u8).cpu()
+    assert torch.equal(a, b) and torch.equal(a_sr, ev.last_sr_u8.cpu())
