@@ -436,7 +436,10 @@ def run_workload(mods, workload: str, B: int, steps: int, warmup: int, dev, rank
             traffic = json.load(open(tpath)).get(DOMINANT_KERNEL_NAMES.get(dom, dom), {}).get("dram_bytes_per_launch")
         flops = sum(f for f, _ in gemm)
         tms = sum(d for _, d in gemm)
-        roofline = {"bound": "tensor", "kernel": DOMINANT_KERNEL_NAMES.get(dom, dom), "achieved": dom_tf, "peak": peaks["sustained"],
+        kname = DOMINANT_KERNEL_NAMES.get(dom, dom)
+        if dom == "window_attention" and lr_side == 64:
+            kname = "window_attn16_tc_kernel"                # 16 x 16 windows: csrc/attention_tc16.cu
+        roofline = {"bound": "tensor", "kernel": kname, "achieved": dom_tf, "peak": peaks["sustained"],
                     "unit": "TFLOP/s", "frac": dom_tf / peaks["sustained"], "frac_of_burst": dom_tf / peaks["burst"],
                     "peak_source": peaks["source"] + " (sustained bf16: the kernel is timed inside a long step)",
                     "traffic": traffic, "launches": n_by_kind[dom], "flops_per_launch": flops_by_kind[dom] / n_by_kind[dom],
