@@ -65,6 +65,11 @@ class DRN(nn.Module):
         self.scale = list(opt.scale)
         self.phase = len(self.scale)
         nb, nf, nc = opt.n_blocks, opt.n_feats, opt.n_colors
+        if nf % 4:
+            # the skip copies live in channel slices [c, 2c) of the later torch.cat buffers; the tensor-core loaders need 16-byte aligned
+            # slices, i.e. 2 * n_feats a multiple of 8 (DRN-L x4: n_feats = 20 is; the reference's x8 setting n_feats = 10 is not)
+            raise ValueError(f"n_feats={nf} is not supported by the B200 build: channel slices must be 16-byte aligned (n_feats % 4 == 0); "
+                             "the reference's scale-8 configuration (n_feats=10) needs padded slices, which are not implemented")
         self.n_blocks, self.n_feats, self.n_colors = nb, nf, nc
         self.rgb_range, self.negval = float(opt.rgb_range), float(opt.negval)
         self.upsample = nn.Upsample(scale_factor=max(self.scale), mode='bicubic', align_corners=False)

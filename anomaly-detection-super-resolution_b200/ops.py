@@ -125,7 +125,8 @@ def swin_attn(x: torch.Tensor, pa, table: torch.Tensor, out: torch.Tensor, b: in
                                     ptr(pa.bias_qkv), ptr(pa.colsum_qkv), ptr(pa.bias_p), ptr(table), pa.ln_eps, ptr(si_t), si_n,
                                     si_t.shape[1], int(fuse_proj), ptr(out), out.stride(0), ptr(so_t), so_0,
                                     so_t.shape[1] if so_t is not None else 0, _abi.num_sms(), stream_ptr()), "adsr_swin_attn_bf16")
-    flops = 2.0 * m * pa.C * 3 * pa.C + 4.0 * m * 64 * pa.C + (2.0 * m * pa.C * pa.C if fuse_proj else 0.0)
+    n_keys = 64                                                # this kernel covers 8 x 8 windows only (16 x 16: window_attention)
+    flops = 2.0 * m * pa.C * 3 * pa.C + 4.0 * m * n_keys * pa.C + (2.0 * m * pa.C * pa.C if fuse_proj else 0.0)
     _count("swin_attn", flops, _t)
 
 

@@ -231,3 +231,19 @@ def test_workspace_queries():
     assert b1 > 0 and b256 == 256 * b1                       # linear in the batch
     assert lib.adsr_drct_workspace_bytes(1, 32, 32, 180, 32, 3, 768, 320) == -1
     assert lib.adsr_score_workspace_bytes(256, 128, 128, 3, 13) == 0
+
+
+def test_drn_rejects_unaligned_channel_slices_up_front():
+    """The reference's x8 DRN setting (n_feats = 10) would need padded channel slices in the cat buffers: rejected at construction
+    with a clear message instead of failing with ADSR_ERR_BAD_ALIGN in the middle of a forward."""
+    import importlib
+    import pytest as _pytest
+    drn = importlib.import_module("anomaly-detection-super-resolution_b200.drn")
+
+    class Opt:
+        scale, n_blocks, n_feats, n_colors, rgb_range, negval = [2, 4, 8], 2, 10, 3, 255, 0.2
+
+    with _pytest.raises(ValueError, match="n_feats=10"):
+        drn.DRN(Opt())
+    Opt.scale, Opt.n_feats = [2, 4], 20
+    assert sum(p.numel() for p in drn.DRN(Opt()).parameters()) > 0
