@@ -182,6 +182,8 @@ class BatchedEvaluator:
         self.use_graph = os.environ.get('ADSR_CUDA_GRAPH', '1') != '0'
         self._bufs = [None, None]
         self._next_buf = 0
+        self._host_ring = [None, None, None]
+        self._host_next = 0
 
     def step(self, lr: torch.Tensor, hr: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         lr_d = lr.to(self.device, non_blocking=True)
@@ -282,6 +284,21 @@ class BatchedEvaluator:
         buf[3] = torch.cuda.Event()
         buf[3].record(cur)
         return scores
+
+    def to_host_async(self, t: torch.Tensor):
+        """Starts the device -> host read of a (small) result tensor into a pinned ring buffer and returns (host tensor, event):
+        the caller enqueues the NEXT step first and only then `event.synchronize()`s -- the GPU never idles while the host turns
+        a step around.  The host tensor is valid until three more reads have been started."""
+        k = self._host_next
+        self._host_next = (k + 1) % len(self._host_ring)
+        buf = self._host_ring[k]
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._host_ring[k] = buf
+        buf.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return buf, ev
 
     def run_pipelined(self, batches):
         """Iterates (lr, hr) host batches with one batch of copy look-ahead; yields the device score table of each batch

@@ -387,12 +387,23 @@ def run_workload(mods, workload: str, B: int, steps: int, warmup: int, dev, rank
     barrier()
     t0 = time.perf_counter()
     nxt = ev.submit(lr_h, hr_h)
-    table = None
+    table, pending = None, None
+
+    def consume(p_):                                     # the step's result on the host (every step's table is read back)
+        p_[1].synchronize()
+        return evaluate.scores_table(p_[0], world * B) if world > 1 else p_[0].numpy().copy()
+
     for i in range(steps):
         flush.zero_()
         cur, nxt = nxt, (ev.submit(lr_h, hr_h) if i + 1 < steps else None)
         s = ev.step_submitted(cur)
-        table = evaluate.gather_scores(s, ids, world * B) if world > 1 else s.cpu().numpy()
+        if world > 1:
+            s = evaluate.gather_scores(s, ids, world * B, to_host=False)
+        h = ev.to_host_async(s)                          # D2H read of step i starts; the host first enqueues step i + 1 ...
+        if pending is not None:
+            table = consume(pending)                     # ... and only then waits for step i - 1's table
+        pending = h
+    table = consume(pending)
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
