@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 10
+#define ADSR_ABI_VERSION 11
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -254,6 +254,24 @@ int adsr_pack_slab_sw128(const float* host_src, int64_t ld, int rows, int cols, 
 int adsr_pack_tiles_sw128(const float* host_w, int64_t ld, int n, int k, int bn, int n_tiles, void* host_dst);
 int64_t adsr_drct_workspace_bytes(int B, int H, int W, int embed_dim, int gc, int upscale, int qkv_cols, int att_cols);
 int64_t adsr_score_workspace_bytes(int B, int H, int W, int C, int n_ws);
+
+/* ---- first slice of the training step (reference: Trainer.train src/trainer.py:141-227, Loss "1*L1" src/loss.py:83-84, 108-121,
+ * Adam src/trainer.py:49-59).  The backward of the tcgen05 blocks is not built; these cover the loss and the last layer.
+ * adsr_l1_loss_grad: nn.L1Loss (mean) of fp32 sr / hr (n elements, 16-byte aligned) and d loss / d sr = sign(sr - hr) * grad_scale / n
+ *   in one pass; partial_ws: fp64 [n_partial] scratch (n_partial = number of thread blocks); loss: fp32 [1] on the device.
+ * adsr_conv_last_bwd: backward of conv_last (3x3, pad 1, Cin = 64 -> nc <= 3, src/drct.py:847, 895): x bf16 NHWC rows (pitch ldx),
+ *   grad_out fp32 NCHW [B, nc, H, W], weight fp32 [nc, 64, 3, 3] -> dx bf16 NHWC rows (may be NULL), dw fp32 [nc, 64, 3, 3] and db
+ *   fp32 [nc] (both NULL to skip); workspace: adsr_conv_last_bwd_workspace_bytes(B, H, 64) bytes; reductions in a fixed order.
+ * adsr_adam_step: torch.optim.Adam step `step` (1-based; amsgrad off) fused over many fp32 tensors: tensor_table = device array of
+ *   {float* p; const float* g; float* m; float* v; int64 n}, chunk_table = device array of int32 pairs {tensor index, chunk index},
+ *   one thread block per chunk of chunk_elems elements. */
+int adsr_l1_loss_grad(const float* sr, const float* hr, int64_t n, float grad_scale, float* grad, double* partial_ws, int n_partial,
+                      float* loss, void* stream);
+int64_t adsr_conv_last_bwd_workspace_bytes(int B, int H, int Cin);
+int adsr_conv_last_bwd(const void* x, int64_t ldx, const float* grad_out_nchw, const float* weight, int B, int H, int W, int Cin, int nc,
+                       void* dx, int64_t ld_dx, float* dw, float* db, float* workspace, void* stream);
+int adsr_adam_step(const void* tensor_table, const void* chunk_table, int n_chunks, int chunk_elems, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,3 +65,32 @@ def test_aucs_from_scores_matches_oracle():
     got = metrics.aucs_from_scores(y, table, wss)
     want = S.aucs_from_scores(y, ssim, mse, psnr, wss)
     assert got[0] == want[0] and np.allclose(got[1:], want[1:], atol=1e-12)
+
+
+def _grad_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    training = importlib.import_module(PKG + ".training")
+    g = torch.Generator().manual_seed(100 + rank)
+    grads = [torch.randn(s, generator=g) for s in ((7, 5), (13,), (2, 3, 3, 3))]
+    training.allreduce_gradients(grads)
+    if rank == 0:
+        torch.save(grads, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_two_ranks(tmp_path):
+    """Data-parallel gradient exchange of the training step (one flat bucket, averaged): world size 2 on gloo."""
+    out = str(tmp_path / "grads.pt")
+    mp.spawn(_grad_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    want = []
+    for s in ((7, 5), (13,), (2, 3, 3, 3)):
+        want.append(None)
+    gens = [torch.Generator().manual_seed(100 + r) for r in range(2)]
+    per_rank = [[torch.randn(s, generator=g) for s in ((7, 5), (13,), (2, 3, 3, 3))] for g in gens]
+    for i, gt in enumerate(got):
+        assert torch.allclose(gt, (per_rank[0][i] + per_rank[1][i]) / 2, atol=1e-7)
+
