@@ -44,10 +44,11 @@ extern "C" int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K, const
                                  int64_t ldres, void* out, int64_t ldo, int ocol0, int n_store,
                                  const float* ln_colsum, float ln_eps, const float* ln_stats_in, int stats_in_slots,
                                  int stats_in_stride, float* stats_out, int stats_out_slot0, int stats_out_stride,
-                                 int num_sms, void* stream) {
+                                 int reverse_tiles, int num_sms, void* stream) {
     if (M <= 0) return ADSR_OK;
     if (K <= 0 || N <= 0 || n_store > n_tiles * BN || lda < K) return ADSR_ERR_BAD_SHAPE;
     TcGemmParams p{};
+    p.rev_tiles = reverse_tiles != 0;
     p.A = static_cast<const __nv_bfloat16*>(A);
     p.lda = lda;
     p.M = M;
@@ -190,10 +191,11 @@ static int swin_mlp_common(SwinMlpParams& p, const void* y, int64_t ldy, int M, 
 extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, const void* w1_packed, const void* w2_packed,
                                   const float* bias1, const float* colsum1, const float* bias2, const int32_t* plan, int plan_len,
                                   float ln_eps, const float* ln_stats_in, int stats_in_slots, int stats_in_stride, void* z,
-                                  int64_t ldz, int num_sms, void* stream) {
+                                  int64_t ldz, int reverse_tiles, int num_sms, void* stream) {
     if (M <= 0) return ADSR_OK;
     if (ldz < C) return ADSR_ERR_BAD_SHAPE;
     SwinMlpParams p{};
+    p.rev = reverse_tiles != 0;
     const int st = swin_mlp_common(p, y, ldy, M, C, w1_packed, w2_packed, bias1, colsum1, bias2, plan, plan_len, ln_eps, ln_stats_in,
                                    stats_in_slots, stats_in_stride);
     if (st != ADSR_OK) return st;
@@ -205,10 +207,11 @@ extern "C" int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int 
                                          int plan_len, float ln_eps, const float* ln_stats_in, int stats_in_slots,
                                          int stats_in_stride, const void* wadj_packed, const float* bias_adj, float slope,
                                          void* out, int64_t ldo, int ocol0, float* stats_out, int stats_out_slot0,
-                                         int stats_out_stride, int num_sms, void* stream) {
+                                         int stats_out_stride, int reverse_tiles, int num_sms, void* stream) {
     if (M <= 0) return ADSR_OK;
     if (plan_len < 23 || wadj_packed == nullptr || bias_adj == nullptr || out == nullptr || ldo < ocol0 + 32) return ADSR_ERR_BAD_SHAPE;
     SwinMlpParams p{};
+    p.rev = reverse_tiles != 0;
     const int st = swin_mlp_common(p, y, ldy, M, C, w1_packed, w2_packed, bias1, colsum1, bias2, plan, plan_len, ln_eps, ln_stats_in,
                                    stats_in_slots, stats_in_stride);
     if (st != ADSR_OK) return st;

@@ -76,6 +76,7 @@ struct TcGemmParams {
     __nv_bfloat16* out;
     long long ldo;
     int ocol0, out_mode;
+    int rev_tiles;       // row-tile kernel: walk the M tiles from the last one down (the rows the producer of A wrote last are still in L2)
 };
 
 int launch_tc_gemm(TcGemmParams& p, int num_sms, cudaStream_t stream);
@@ -106,6 +107,7 @@ struct SwinMlpParams {
     int stats_in_slots, stats_in_stride;
     float ln_eps;
     int C, M, m_tiles;
+    int rev;              // walk the row tiles from the last one down (what the producer wrote last is still in L2)
     int ks1, k1steps;     // 64-wide panels / K=16 steps of the y tile
     int nc, hc;           // hidden chunks, chunk stride in bias1 / colsum1 (= TMEM columns per fc1 accumulator)
     int hcw[8];           // MMA N of each chunk (multiple of 16, <= 128)

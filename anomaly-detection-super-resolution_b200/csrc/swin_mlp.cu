@@ -98,6 +98,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int my_tiles = static_cast<int>(blockIdx.x) < p.m_tiles ? (p.m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto tile_of = [&](int it) -> int {                                // forward, or from the last tile down (p.rev)
+        const int t = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+        return p.rev ? p.m_tiles - 1 - t : t;
+    };
 
     if ((smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         // ============================================================ y-tile loads / z-tile stores (same buffers)
         auto load_a = [&](int it) {
             const int ab = it & 1;
-            const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
+            const int m0 = tile_of(it) * 128;
             if (lane == 0) {
                 mbar_arrive_expect_tx(&bars->a_full[ab], static_cast<uint32_t>(p.a_buf_bytes));
                 for (int pn = 0; pn < p.ks1; ++pn)
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         if (my_tiles > 1) load_a(1);
         for (int it = 0; it < my_tiles; ++it) {
             const int ab = it & 1;
-            const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
+            const int m0 = tile_of(it) * 128;
             if (p.fuse_adj) {
                 // z only feeds the fused adjust conv: nothing is stored; the buffer is free once the adjust MMAs have read it
                 mbar_wait(&bars->adj_done[ab], static_cast<uint32_t>(it >> 1) & 1);
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         const bool tr = TRACE && warp == 0;
 
         auto row_stats = [&](int it, float& rstd, float& nrm) {
-            const int row = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128 + r_in_tile;
+            const int row = tile_of(it) * 128 + r_in_tile;
             rstd = 1.f;
             nrm = 0.f;                                                // nrm = -mean * rstd
             if (row < p.M) {
@@ -463,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
 
         // ---- fused adjust: 32 new slab columns = LReLU(acc + bias), stored at the tile's token rows, + their row statistics
         auto epi3 = [&](int it) {
-            const int row = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128 + r_in_tile;
+            const int row = tile_of(it) * 128 + r_in_tile;
             mbar_wait(&bars->adj_full, static_cast<uint32_t>(it) & 1);
             tc_fence_after_sync();
             if (grp < 2) {
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         // the (sum, sumsq) slots of a row were written by the previous kernel: fetched cold they cost ~2k cycles of exposed latency per
         // tile (clock64 timeline), so the lines of tile it + 1 are pulled into L1 while the chunks of tile it are converted
         auto prefetch_stats = [&](int it) {
-            const int row = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128 + r_in_tile;
+            const int row = tile_of(it) * 128 + r_in_tile;
             if (grp == 0 && row < p.M) {
                 const char* sp = reinterpret_cast<const char*>(p.stats_in + static_cast<long long>(row) * p.stats_in_stride);
                 for (int o = 0; o < p.stats_in_slots * 8; o += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + o));

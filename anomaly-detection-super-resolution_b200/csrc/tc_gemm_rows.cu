@@ -46,6 +46,7 @@ struct __align__(8) RowBarriers {
 struct RowParams {
     TcGemmParams g;
     int ks1, n_abuf, n_slots;
+    int rev;                                  // walk the M tiles from the last one down
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
@@ -87,6 +88,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_rows_kernel(const __grid_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int my_tiles = static_cast<int>(blockIdx.x) < p.m_tiles ? (p.m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // tile order: forward, or from the LAST tile down (rev) when the producer of A wrote it front to back: the rows it wrote last
+    // are the ones still in L2
+    auto tile_of = [&](int it) -> int {
+        const int t = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+        return rp.rev ? p.m_tiles - 1 - t : t;
+    };
     const bool has_res = p.res != nullptr;
 
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_rows_kernel(const __grid_
         if (lane == 0) tma_prefetch_desc(&p.tmap_a);
         for (int it = 0; it < my_tiles; ++it) {
             const int ab = rp.n_abuf == 2 ? (it & 1) : 0;
-            const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
+            const int m0 = tile_of(it) * 128;
             mbar_wait(&bars->a_empty[ab], (static_cast<uint32_t>(rp.n_abuf == 2 ? (it >> 1) : it) & 1) ^ 1);
             if (lane == 0) {
                 mbar_arrive_expect_tx(&bars->a_full[ab], static_cast<uint32_t>(a_bytes));
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_rows_kernel(const __grid_
             };
             auto fetch_res = [&]() {
                 if (rq_it >= my_tiles) return;
-                const int m0 = (rq_it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
+                const int m0 = tile_of(rq_it) * 128;
                 mbar_arrive_expect_tx(&bars->stg_free[rq % kStg], kPanelBytes);
                 tma_load_2d(stg + (rq % kStg) * kPanelBytes, &p.tmap_res, rq_nt * kBN + rq_sl * 64, m0, &bars->stg_free[rq % kStg]);
                 advance(rq_it, rq_nt, rq_sl);
@@ -224,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_rows_kernel(const __grid_
                 for (int i = 0; i < kStg; ++i) fetch_res();
             int it = 0, nt = 0, sl = 0;
             while (it < my_tiles) {
-                const int m0 = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128;
+                const int m0 = tile_of(it) * 128;
                 mbar_wait(&bars->stg_ready[q % kStg], static_cast<uint32_t>(q / kStg) & 1);
                 tma_store_2d_box(&p.tmap_out, stg + (q % kStg) * kPanelBytes, p.ocol0 + nt * kBN + sl * 64, m0);
                 bulk_commit_group();
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_rows_kernel(const __grid_
         const float2 alpha2 = f2(p.alpha, p.alpha);
         int q = 0, c = 0;
         for (int it = 0; it < my_tiles; ++it) {
-            const int row = (it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x)) * 128 + r;
+            const int row = tile_of(it) * 128 + r;
             float rstd = 1.f, nrm = 0.f;
             if (p.ln_fold && row < p.M) {
                 const float2* sp = p.stats_in + static_cast<long long>(row) * p.stats_in_stride;
@@ -351,6 +358,7 @@ bool tc_gemm_rows_eligible(const TcGemmParams& p) {
 
 int launch_tc_gemm_rows(TcGemmParams& g, int num_sms, cudaStream_t stream) {
     RowParams rp{};
+    rp.rev = g.rev_tiles;
     rp.ks1 = g.num_k_stages;
     const int fixed = kStg * kPanelBytes + 2 * kMaxN * 4 + 2 * 4 * 128 * 8 + static_cast<int>(sizeof(RowBarriers)) + 64;
     const int a_bytes = rp.ks1 * kPanelBytes;

@@ -29,6 +29,7 @@ from .pack import PackedWeight, round_up
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # src/drct.py:774
 _FUSED_ADJUST = os.environ.get("ADSR_FUSED_ADJUST", "1") != "0"  # A/B switch: 0 = adjust convs as separate GEMMs
+_ALT_TILE_ORDER = os.environ.get("ADSR_ALT_TILE_ORDER", "1") != "0"  # A/B switch: 0 = every kernel walks its row tiles front to back
 _FUSED_ATTN = os.environ.get("ADSR_FUSED_ATTN", "1") != "0"    # A/B switch for profiling: 0 = separate qkv / attention / proj kernels
 
 
@@ -298,6 +299,11 @@ class DRCT(nn.Module):
         ops.drct_head(x, P["cf_w"], P["cf_b"], P["mean"], float(self.img_range), P["pe_w"], P["pe_b"], D, ws["x0"], slab,
                       stats_out=st_slab)
 
+        # Tile order: the persistent row-tile kernels (proj / adjust GEMMs, fused MLP) can walk their 128-row tiles backwards.  A batch-256
+        # activation (94 - 168 MB) does not fit the 126 MB L2 next to everything else, but the rows its producer wrote LAST are still
+        # there: each of these kernels runs opposite to the kernel that produced its input (the attention kernels always run forward).
+        rev = _ALT_TILE_ORDER
+        slab_fwd = True                                   # direction in which the current slab contents were written
         for blocks in P["blocks"]:
             xs = 2 * blocks[-1].adjust.n_tiles        # st_slab: x owns the first xs slots (written by adjust5), each x_j two more
             for k, b in enumerate(blocks):
@@ -309,26 +315,33 @@ class DRCT(nn.Module):
                 if fused == 2:
                     ops.swin_attn(slab, b.attn, b.table, y, B, H, W, b.shift, (st_slab, xs + 2 * k), True, stats_out=(st_y, 0))
                     y_slots = 1
+                    y_fwd = True
                 elif fused == 1:
                     ops.swin_attn(slab, b.attn, b.table, att, B, H, W, b.shift, (st_slab, xs + 2 * k), False)
-                    ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0))
+                    ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0), reverse=rev)
+                    y_fwd = not rev
                 else:
-                    ops.tc_gemm(slab, C, b.qkv, qkv, stats_in=(st_slab, xs + 2 * k))
+                    ops.tc_gemm(slab, C, b.qkv, qkv, stats_in=(st_slab, xs + 2 * k), reverse=rev and slab_fwd)
                     ops.window_attention(qkv, att, b.table, B, H, W, b.ws, b.shift, b.heads, b.hd, b.hdp)
-                    ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0))
+                    ops.tc_gemm(att, b.heads * b.hdp, b.proj, y, res=slab, stats_out=(st_y, 0), reverse=rev)
+                    y_fwd = not rev
                 # ---- MLP half (src/drct.py:510, 185-189): norm2 + fc1 + GELU + fc2 + residual in ONE kernel, the hidden
                 #      activations never leave the SM
+                mlp_rev = rev and y_fwd
                 if b.mlp.wadj is not None:
                     # ... and the adjust 1x1 conv (+LeakyReLU 0.2) into the slab slice (src/drct.py:389-393) in the same kernel
-                    ops.swin_mlp_adjust(y, C, b.mlp, slab, C, stats_in=(st_y, y_slots), stats_out=(st_slab, xs + 2 * k))
+                    ops.swin_mlp_adjust(y, C, b.mlp, slab, C, stats_in=(st_y, y_slots), stats_out=(st_slab, xs + 2 * k), reverse=mlp_rev)
+                    slab_fwd = not mlp_rev
                     continue
-                ops.swin_mlp(y, C, b.mlp, z, stats_in=(st_y, y_slots))
+                ops.swin_mlp(y, C, b.mlp, z, stats_in=(st_y, y_slots), reverse=mlp_rev)
                 # ---- adjust 1x1 conv (+LeakyReLU 0.2) into the slab slice / 0.2*x5 + x  (src/drct.py:389-396)
+                adj_rev = rev and not mlp_rev
                 if not b.last:
                     ops.tc_gemm(z, C, b.adjust, slab, act=ops.ACT_LRELU, slope=0.2, ocol0=C, n_store=b.adjust_out,
-                                stats_out=(st_slab, xs + 2 * k))
+                                stats_out=(st_slab, xs + 2 * k), reverse=adj_rev)
                 else:
-                    ops.tc_gemm(z, C, b.adjust, slab, alpha=0.2, res=slab, stats_out=(st_slab, 0))
+                    ops.tc_gemm(z, C, b.adjust, slab, alpha=0.2, res=slab, stats_out=(st_slab, 0), reverse=adj_rev)
+                slab_fwd = not adj_rev
 
         # final norm -> conv_after_body + x0 -> conv_before_upsample + LeakyReLU(0.01) -> upsample -> conv_last
         ops.layernorm_rows(slab, ln, P["norm_w"], P["norm_b"], D)

@@ -45,13 +45,14 @@ def _cuda(t: torch.Tensor, name: str) -> None:
 
 def tc_gemm(a: torch.Tensor, k: int, w: PackedWeight, out: torch.Tensor, *, act: int = ACT_NONE, slope: float = 0.0,
             alpha: float = 1.0, res: Optional[torch.Tensor] = None, ocol0: int = 0, n_store: Optional[int] = None,
-            m: Optional[int] = None, stats_in: Optional[tuple] = None, stats_out: Optional[tuple] = None) -> None:
+            m: Optional[int] = None, stats_in: Optional[tuple] = None, stats_out: Optional[tuple] = None, reverse: bool = False) -> None:
     """out[:, ocol0:ocol0+n_store] = alpha * act(a[:, :k] @ W^T + b) (+ res[:, :N]).
 
     If `w` was packed with pack_ln_gemm_weight the rows of `a` are layer-normalised over their first k columns on the fly;
     their (sum, sumsq) come from stats_in = (fp32 tensor [M, S, 2], number of leading slots to add up).
     stats_out = (fp32 tensor [M, S, 2], first slot) makes this call write such partials for ITS output rows
-    (slots first .. first + 2*n_tiles - 1)."""
+    (slots first .. first + 2*n_tiles - 1).
+    reverse: the row-tile kernel walks its 128-row tiles from the last one down (the rows the producer of `a` wrote last are in L2)."""
     _cuda(a, "a")
     m = a.shape[0] if m is None else m
     n_store = (w.N + 15) // 16 * 16 if n_store is None else n_store
@@ -63,12 +64,12 @@ def tc_gemm(a: torch.Tensor, k: int, w: PackedWeight, out: torch.Tensor, *, act:
     check(lib().adsr_tc_gemm_bf16(ptr(a), a.stride(0), m, k, ptr(w.data), ptr(w.bias), w.N, w.BN, w.n_tiles, act, slope,
                                   alpha, ptr(res), res.stride(0) if res is not None else 0, ptr(out), out.stride(0), ocol0,
                                   n_store, ptr(w.colsum), w.ln_eps, ptr(si_t), si_n, si_t.shape[1] if si_t is not None else 0,
-                                  ptr(so_t), so_0, so_t.shape[1] if so_t is not None else 0, _abi.num_sms(), stream_ptr()),
+                                  ptr(so_t), so_0, so_t.shape[1] if so_t is not None else 0, int(reverse), _abi.num_sms(), stream_ptr()),
           "adsr_tc_gemm_bf16")
     _count("tc_gemm", 2.0 * m * k * w.N, _t)
 
 
-def swin_mlp(y: torch.Tensor, c: int, pm, z: torch.Tensor, stats_in: tuple, m: Optional[int] = None) -> None:
+def swin_mlp(y: torch.Tensor, c: int, pm, z: torch.Tensor, stats_in: tuple, m: Optional[int] = None, reverse: bool = False) -> None:
     """z[:, :c] = y + fc2(GELU(fc1(LayerNorm(y[:, :c]))))  -- one fused kernel (csrc/swin_mlp.cu); `pm` from
     pack.pack_swin_mlp, stats_in = (fp32 [M, S, 2] partial (sum, sumsq) of the rows of y, slots to add up)."""
     _cuda(y, "y")
@@ -80,12 +81,12 @@ def swin_mlp(y: torch.Tensor, c: int, pm, z: torch.Tensor, stats_in: tuple, m: O
     _t = _begin()
     check(lib().adsr_swin_mlp_bf16(ptr(y), y.stride(0), m, c, ptr(pm.w1), ptr(pm.w2), ptr(pm.bias1), ptr(pm.colsum1), ptr(pm.bias2),
                                    pm.plan.data_ptr(), pm.plan.numel(), pm.ln_eps, ptr(si_t), si_n, si_t.shape[1],
-                                   ptr(z), z.stride(0), _abi.num_sms(), stream_ptr()), "adsr_swin_mlp_bf16")
+                                   ptr(z), z.stride(0), int(reverse), _abi.num_sms(), stream_ptr()), "adsr_swin_mlp_bf16")
     _count("swin_mlp", 4.0 * m * pm.C * pm.H, _t)
 
 
 def swin_mlp_adjust(y: torch.Tensor, c: int, pm, out: torch.Tensor, ocol0: int, stats_in: tuple, stats_out: Optional[tuple] = None,
-                    slope: float = 0.2, m: Optional[int] = None) -> None:
+                    slope: float = 0.2, m: Optional[int] = None, reverse: bool = False) -> None:
     """out[:, ocol0:ocol0+32] = LReLU_slope(adjust(z)),  z = y + fc2(GELU(fc1(LayerNorm(y[:, :c]))))  -- the fused MLP kernel with
     the RDG's adjust 1x1 conv in its last epilogue; z is never written.  `pm` from pack.pack_swin_mlp(..., adjust_w, adjust_b)."""
     _cuda(y, "y")
@@ -99,7 +100,7 @@ def swin_mlp_adjust(y: torch.Tensor, c: int, pm, out: torch.Tensor, ocol0: int, 
     check(lib().adsr_swin_mlp_adjust_bf16(ptr(y), y.stride(0), m, c, ptr(pm.w1), ptr(pm.w2), ptr(pm.bias1), ptr(pm.colsum1), ptr(pm.bias2),
                                           pm.plan.data_ptr(), pm.plan.numel(), pm.ln_eps, ptr(si_t), si_n, si_t.shape[1],
                                           ptr(pm.wadj), ptr(pm.bias_adj), slope, ptr(out), out.stride(0), ocol0, ptr(so_t), so_0,
-                                          so_t.shape[1] if so_t is not None else 0, _abi.num_sms(), stream_ptr()),
+                                          so_t.shape[1] if so_t is not None else 0, int(reverse), _abi.num_sms(), stream_ptr()),
           "adsr_swin_mlp_adjust_bf16")
     _count("swin_mlp", 4.0 * m * pm.C * pm.H + 2.0 * m * pm.C * 32, _t)
 

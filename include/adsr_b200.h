@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 11
+#define ADSR_ABI_VERSION 12
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -54,7 +54,9 @@ int adsr_device_check(int* host_num_sms);
  * ln_colsum[n] = sum_k gamma_k W[n,k]; row mean / rstd come from ln_stats_in: per row `stats_in_stride` (sum, sumsq)
  * float pairs of which the first `stats_in_slots` are added up.
  * stats_out != NULL makes THIS call emit such partials for its own output rows (over the N valid columns, after
- * bias / activation / alpha / residual): slot = stats_out_slot0 + 2 * n_tile + {0,1}; needs slot0 + 2*n_tiles <= stride. */
+ * bias / activation / alpha / residual): slot = stats_out_slot0 + 2 * n_tile + {0,1}; needs slot0 + 2*n_tiles <= stride.
+ * reverse_tiles != 0 (row-tile kernel, also adsr_swin_mlp*_bf16): the persistent CTAs walk the 128-row tiles from the LAST one down --
+ * when the kernel that produced A wrote it front to back, the rows it wrote last are the ones still in the 126 MB L2. */
 int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K,
                       const void* w_packed, const float* bias_padded, int N, int BN, int n_tiles,
                       int act, float slope, float alpha,
@@ -62,7 +64,7 @@ int adsr_tc_gemm_bf16(const void* A, int64_t lda, int M, int K,
                       void* out, int64_t ldo, int ocol0, int n_store,
                       const float* ln_colsum, float ln_eps, const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
                       float* stats_out, int stats_out_slot0, int stats_out_stride,
-                      int num_sms, void* stream);
+                      int reverse_tiles, int num_sms, void* stream);
 
 /* ---- fused Swin MLP half: z = y + fc2(GELU(fc1(LayerNorm(y))))   (one kernel, hidden activations stay in TMEM) ----
  * replaces norm2 + Mlp.forward + the second residual of SwinTransformerBlock.forward (src/drct.py:510, 173-190).
@@ -76,7 +78,7 @@ int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C,
                        const float* bias1, const float* colsum1, const float* bias2,
                        const int32_t* plan, int plan_len, float ln_eps,
                        const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
-                       void* z, int64_t ldz, int num_sms, void* stream);
+                       void* z, int64_t ldz, int reverse_tiles, int num_sms, void* stream);
 
 /* Same kernel with the adjust 1x1 conv of the RDG fused in (src/drct.py:389-393: x_k = LReLU_0.2(adjust_k(swin_k(...))) appended to
  * the dense feature slab): out[:, ocol0 + n] = LReLU(z W_adj^T + b_adj)[n] for the 32 new channels, where z is the MLP result above.
@@ -90,7 +92,7 @@ int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int C,
                               const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
                               const void* wadj_packed, const float* bias_adj, float slope,
                               void* out, int64_t ldo, int ocol0,
-                              float* stats_out, int stats_out_slot0, int stats_out_stride, int num_sms, void* stream);
+                              float* stats_out, int stats_out_slot0, int stats_out_stride, int reverse_tiles, int num_sms, void* stream);
 
 /* ---- fused attention half of a Swin block for 8 x 8 windows ------------------------------------------------------
  *   y = x + proj( WindowAttention( LayerNorm(x) ) )

@@ -236,6 +236,10 @@ def test_gemm_with_folded_layernorm(K, N, act, rows):
     out = torch.zeros(M, 1024, device=DEV, dtype=torch.bfloat16)
     ops.tc_gemm(a, K, pw, out, act=ops.ACT_GELU if act == "gelu" else ops.ACT_NONE, stats_in=(st, 2))
     torch.cuda.synchronize()
+    out_rev = torch.zeros(M, 1024, device=DEV, dtype=torch.bfloat16)           # row tiles walked from the last one down: same bits
+    ops.tc_gemm(a, K, pw, out_rev, act=ops.ACT_GELU if act == "gelu" else ops.ACT_NONE, stats_in=(st, 2), reverse=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_rev)
     want = F.linear(F.layer_norm(a[:, :K].float(), (K,), g, bt, 1e-5), w, b)
     if act == "gelu":
         want = F.gelu(want)
@@ -258,6 +262,10 @@ def test_gemm_emits_row_statistics(N, res, rows):
     st = torch.full((M, 10, 2), 7.0, device=DEV)
     ops.tc_gemm(a, K, pw, out, res=r, stats_out=(st, 2))
     torch.cuda.synchronize()
+    out_rev, st_rev = torch.zeros_like(out), torch.full((M, 10, 2), 7.0, device=DEV)
+    ops.tc_gemm(a, K, pw, out_rev, res=r, stats_out=(st_rev, 2), reverse=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_rev) and torch.equal(st, st_rev)
     used = 2 * pw.n_tiles
     got = st[:, 2:2 + used].sum(1)
     o = out[:, :N].float()

@@ -31,6 +31,10 @@ def _mlp_case(M, C, H, seed=0):
     stats[:, 2] = 1e9
     ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2))
     torch.cuda.synchronize()
+    z_rev = torch.full((M, ld), -7.0, device=DEV, dtype=torch.bfloat16)     # tiles walked from the last one down: same bits
+    ops.swin_mlp(y, C, pm, z_rev, stats_in=(stats, 2), reverse=True)
+    torch.cuda.synchronize()
+    assert torch.equal(z, z_rev), "reverse tile order must not change the result"
     want = yf + F.linear(F.gelu(F.linear(F.layer_norm(yf, (C,), gamma, beta, 1e-5), w1, b1)), w2, b2)
     err = rel_err(z[:, :C], want)
     assert err < 0.012, f"M={M} C={C} H={H}: rel err {err}"
