@@ -31,6 +31,7 @@ _SIGNATURES = {
                                           c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int64,
                                           c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "adsr_swin_attn_mode": (c_int, [c_int, c_int, c_int, c_int]),
+    "adsr_swin_attn2_covers": (c_int, [c_int, c_int, c_int]),
     "adsr_swin_attn_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int,
                                     c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -30,7 +30,8 @@ from .pack import PackedWeight, round_up
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # src/drct.py:774
 _FUSED_ADJUST = os.environ.get("ADSR_FUSED_ADJUST", "1") != "0"  # A/B switch: 0 = adjust convs as separate GEMMs
 _ALT_TILE_ORDER = os.environ.get("ADSR_ALT_TILE_ORDER", "1") != "0"  # A/B switch: 0 = every kernel walks its row tiles front to back
-_FUSED_ATTN = os.environ.get("ADSR_FUSED_ATTN", "1") != "0"    # A/B switch for profiling: 0 = separate qkv / attention / proj kernels
+_FUSED_ATTN = os.environ.get("ADSR_FUSED_ATTN", "1") != "0"
+_PREFER_ATTN2 = os.environ.get("ADSR_PREFER_ATTN2", "0") != "0"  # A/B switch: 1 = swin_attn2 (+ proj GEMM) wherever it covers the block shape    # A/B switch for profiling: 0 = separate qkv / attention / proj kernels
 
 
 def _heads_for(dim: int, k: int, nh: int) -> int:
@@ -203,6 +204,8 @@ class DRCT(nn.Module):
                 # fused attention half (csrc/swin_attn.cu): 2 = qkv + attention + proj + residual in one kernel,
                 # 1 = qkv + attention (proj stays a row-tile GEMM), 0 = shape not covered (separate kernels)
                 b.attn_mode = ops.swin_attn_mode(b.dim, b.heads, b.hdp) if (b.ws == 8 and _FUSED_ATTN) else 0
+                if b.attn_mode == 2 and _PREFER_ATTN2 and ops.swin_attn2_covers(b.dim, b.heads, b.hdp):
+                    b.attn_mode = 1           # two-heads-in-flight attention kernel + proj as a row-tile GEMM
                 b.attn = up(pack.pack_swin_attn(qkv_w, qkv_b, n1w, n1b, sw.norm1.eps, proj_w, proj_b, b.heads)) if b.attn_mode else None
                 # the 32-channel adjust convs ride in the MLP kernel's last epilogue where its tiling leaves room (z is then never
                 # written); otherwise (and for adjust5) the adjust conv stays a GEMM of its own

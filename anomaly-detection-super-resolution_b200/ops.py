@@ -110,6 +110,11 @@ def swin_attn_mode(c: int, heads: int, hdp: int, allow_proj: bool = True) -> int
     return int(lib().adsr_swin_attn_mode(c, heads, hdp, int(allow_proj)))
 
 
+def swin_attn2_covers(c: int, heads: int, hdp: int) -> bool:
+    """True when the two-heads-in-flight attention kernel (csrc/swin_attn2.cu) covers this block shape."""
+    return bool(lib().adsr_swin_attn2_covers(c, heads, hdp))
+
+
 def swin_attn(x: torch.Tensor, pa, table: torch.Tensor, out: torch.Tensor, b: int, h: int, w: int, shift: int, stats_in: tuple,
               fuse_proj: bool, stats_out: Optional[tuple] = None) -> None:
     """fuse_proj: out[:, :C] = x + proj(W-MSA(LayerNorm(x[:, :C])))  else  out = attention rows [M, heads*hdp]
