@@ -177,7 +177,9 @@ static int swin_mlp_common(SwinMlpParams& p, const void* y, int64_t ldy, int M, 
     p.piece_col[0] = 0; p.piece_col[1] = plan[8];
     p.w1_slots = plan[10]; p.w1_slot_bytes = plan[11]; p.w2_slots = plan[12]; p.w2_slot_bytes = plan[13];
     for (int j = 0; j < 8; ++j) p.hcw[j] = plan[14 + j];
-    if (p.ks1 != (C + 63) / 64 || p.k1steps != (C + 15) / 16 || p.n2 != (C + 15) / 16 * 16) return ADSR_ERR_BAD_SHAPE;
+    // plan[23] != 0: folded adjust -- the fc2 ring carries W_adj W2 (32 rows), so the accumulator is 32 columns, not C
+    const bool fold = plan_len >= 24 && plan[23] != 0;
+    if (p.ks1 != (C + 63) / 64 || p.k1steps != (C + 15) / 16 || p.n2 != (fold ? 32 : (C + 15) / 16 * 16)) return ADSR_ERR_BAD_SHAPE;
     p.w1p = static_cast<const uint8_t*>(w1_packed);
     p.w2p = static_cast<const uint8_t*>(w2_packed);
     p.bias1 = bias1; p.colsum1 = colsum1; p.bias2 = bias2;
@@ -193,7 +195,7 @@ extern "C" int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C, cons
                                   float ln_eps, const float* ln_stats_in, int stats_in_slots, int stats_in_stride, void* z,
                                   int64_t ldz, int reverse_tiles, int num_sms, void* stream) {
     if (M <= 0) return ADSR_OK;
-    if (ldz < C) return ADSR_ERR_BAD_SHAPE;
+    if (ldz < C || (plan != nullptr && plan_len >= 24 && plan[23] != 0)) return ADSR_ERR_BAD_SHAPE;   // a folded-adjust pack has no z
     SwinMlpParams p{};
     p.rev = reverse_tiles != 0;
     const int st = swin_mlp_common(p, y, ldy, M, C, w1_packed, w2_packed, bias1, colsum1, bias2, plan, plan_len, ln_eps, ln_stats_in,
@@ -215,7 +217,7 @@ extern "C" int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int 
     const int st = swin_mlp_common(p, y, ldy, M, C, w1_packed, w2_packed, bias1, colsum1, bias2, plan, plan_len, ln_eps, ln_stats_in,
                                    stats_in_slots, stats_in_stride);
     if (st != ADSR_OK) return st;
-    p.fuse_adj = 1;
+    p.fuse_adj = (plan_len >= 24 && plan[23] != 0) ? 2 : 1;
     p.adj_tcol = plan[22];
     p.wadj = static_cast<const uint8_t*>(wadj_packed);
     p.bias_adj = bias_adj;

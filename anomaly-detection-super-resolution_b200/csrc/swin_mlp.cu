@@ -54,12 +54,11 @@ struct __align__(16) MlpBarriers {
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float absf_bits(float x) { return __uint_as_float(__float_as_uint(x) & 0x7fffffffu); }
 
 // 2 * GELU(x) for a pair:  x + |x| * (1 - erfc(|x| / sqrt 2)),  erfc(a / sqrt 2) ~ 2^(a * q(a)) with q a NEGATED quadratic:
 // |error| <= 8.6e-5 after the 0.5 that lives in the fc2 weights (activations are rounded to bf16 right after).
 __device__ __forceinline__ float2 gelu2_pair(float2 x) {
-    const float2 a = f2(absf_bits(x.x), absf_bits(x.y));
+    const float2 a = f2(fabsf(x.x), fabsf(x.y));          // folds into |R| operand modifiers of FFMA2 / FMUL2
     float2 q = __ffma2_rn(f2(-0.027645503f, -0.027645503f), a, f2(-0.48822206f, -0.48822206f));
     q = __ffma2_rn(q, a, f2(-1.1409364f, -1.1409364f));
     const float2 m = __fmul2_rn(q, a);
@@ -130,8 +129,9 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         mbar_init(&bars->acc2_free, kEpiWarps);
         mbar_init(&bars->adj_w_full, 1);
         mbar_init(&bars->adj_full, 1);
-        mbar_init(&bars->adj_done[0], 1);
-        mbar_init(&bars->adj_done[1], 1);
+        // folded adjust: the tile buffer is free once BOTH its fc1 MMAs and its y W_adj^T MMAs (two issuing warps) have completed
+        mbar_init(&bars->adj_done[0], p.fuse_adj == 2 ? 2 : 1);
+        mbar_init(&bars->adj_done[1], p.fuse_adj == 2 ? 2 : 1);
         fence_barrier_init();
     }
     if (warp == kTileWarp) tmem_alloc<512>(&bars->tmem_base);
@@ -198,7 +198,9 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(a_buf));
         const uint32_t a_units = static_cast<uint32_t>(p.a_buf_bytes >> 4);
         for (int it = 0; it < my_tiles; ++it) {
+            trace_ev<TRACE>(p.trace, 0, it, 1, 0);
             mbar_wait(&bars->a_full[it & 1], static_cast<uint32_t>(it >> 1) & 1);
+            trace_ev<TRACE>(p.trace, 0, it, 1, 1);
             const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((it & 1) * a_units);
             for (int j = 0; j < p.nc; ++j) {
                 const int cg = it * p.nc + j;                         // running chunk counter: buffer = cg & 1, use = cg >> 1
@@ -220,7 +222,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                         if (ksteps > 2) umma_bf16(acc1, adesc + 4, bdesc + 4, idesc, 1u);
                         if (ksteps > 3) umma_bf16(acc1, adesc + 6, bdesc + 6, idesc, 1u);
                         umma_commit(&bars->w1_empty[slot]);
-                        if (s == p.ks1 - 1) umma_commit(&bars->acc1_full[b]);
+                        if (s == p.ks1 - 1) {
+                            umma_commit(&bars->acc1_full[b]);
+                            if (p.fuse_adj == 2 && j == p.nc - 1) umma_commit(&bars->adj_done[it & 1]);   // last read of the y tile by fc1
+                        }
                     }
                     __syncwarp();
                     if (++slot == p.w1_slots) { slot = 0; phase ^= 1; }
@@ -257,6 +262,25 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             }
             __syncwarp();
         };
+        // folded adjust (fuse_adj == 2): W_adj (y + fc2(g)) = y W_adj^T + g (W_adj W2)^T -- the fc2 ring carries the 32 rows of
+        // W_adj W2, the accumulator is 32 columns wide, and the y term goes in first, straight from the tile buffer
+        auto issue_adj_y = [&](int it) {
+            if (it == 0) mbar_wait(&bars->adj_w_full, 0);
+            mbar_wait(&bars->a_full[it & 1], static_cast<uint32_t>(it >> 1) & 1);
+            tc_fence_after_sync();
+            if (elect_one_sync()) {
+                const uint64_t a_desc = adj_a_desc0 + static_cast<uint64_t>((it & 1) * static_cast<uint32_t>(p.a_buf_bytes >> 4));
+                const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[0]);
+                for (int s = 0; s < p.ks1; ++s) {
+                    const int ksteps = min(4, p.k1steps - 4 * s);
+                    for (int j = 0; j < ksteps; ++j)
+                        umma_bf16(d, a_desc + static_cast<uint64_t>(s * (kPanelBytes >> 4)) + 2 * j,
+                                  adj_b_desc + static_cast<uint64_t>(s * (kAdjSlabBytes >> 4)) + 2 * j, adj_idesc, (s > 0 || j > 0) ? 1u : 0u);
+                }
+                umma_commit(&bars->adj_done[it & 1]);
+            }
+            __syncwarp();
+        };
         for (int it = 0; it < my_tiles; ++it) {
             for (int j = 0; j < p.nc; ++j) {
                 const int cg = it * p.nc + j;
@@ -269,11 +293,12 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                     mbar_wait(&bars->h_ready[b][s], static_cast<uint32_t>(cg >> 1) & 1);
                     if (j == 0 && s == 0) {
                         mbar_wait(&bars->acc2_free, (static_cast<uint32_t>(it) & 1) ^ 1);
-                        if (p.fuse_adj && it > 0) issue_adj(it - 1);      // the previous tile's z is complete: adjust goes first
+                        if (p.fuse_adj == 1 && it > 0) issue_adj(it - 1);      // the previous tile's z is complete: adjust goes first
+                        if (p.fuse_adj == 2) issue_adj_y(it);                  // folded adjust: the accumulator starts as y W_adj^T
                     }
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 1);
                     const uint32_t at = acc1 + static_cast<uint32_t>(64 * s);     // K=16 step u of the chunk lives at column 16 u
-                    const uint32_t first_acc = (j == 0 && s == 0) ? 0u : 1u;
+                    const uint32_t first_acc = (j == 0 && s == 0 && p.fuse_adj != 2) ? 0u : 1u;
                     for (int pc = 0; pc < p.n_pieces; ++pc) {
                         const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.piece_rows[pc]));
                         const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[pc]);
@@ -298,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                 }
             }
         }
-        if (p.fuse_adj && my_tiles > 0) issue_adj(my_tiles - 1);
+        if (p.fuse_adj == 1 && my_tiles > 0) issue_adj(my_tiles - 1);
     } else if (warp == kTileWarp) {
         // ============================================================ y-tile loads / z-tile stores (same buffers)
         auto load_a = [&](int it) {
@@ -325,7 +350,9 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                 // z only feeds the fused adjust conv: nothing is stored; the buffer is free once the adjust MMAs have read it
                 mbar_wait(&bars->adj_done[ab], static_cast<uint32_t>(it >> 1) & 1);
             } else {
+                trace_ev<TRACE>(p.trace, 0, it, 0, 0);
                 mbar_wait(&bars->z_ready[ab], static_cast<uint32_t>(it >> 1) & 1);
+                trace_ev<TRACE>(p.trace, 0, it, 0, 1);
                 if (lane == 0) {        // bulk-group bookkeeping is per thread: the same lane stores and waits
                     for (int pn = 0; pn < p.ks1; ++pn)
                         tma_store_2d_box(&p.tmap_z, a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, pn * 64, m0);
@@ -333,8 +360,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                     bulk_wait_group_read0();
                 }
                 __syncwarp();
+                trace_ev<TRACE>(p.trace, 0, it, 0, 2);
             }
             if (it + 2 < my_tiles) load_a(it + 2);                    // the buffer is free again: fetch the tile after next
+            trace_ev<TRACE>(p.trace, 0, it, 0, 3);
         }
         if (lane == 0) bulk_wait_group0();
         __syncwarp();
@@ -468,12 +497,20 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         // ---- fused adjust: 32 new slab columns = LReLU(acc + bias), stored at the tile's token rows, + their row statistics
         auto epi3 = [&](int it) {
             const int row = tile_of(it) * 128 + r_in_tile;
-            mbar_wait(&bars->adj_full, static_cast<uint32_t>(it) & 1);
+            const bool fold = p.fuse_adj == 2;                        // folded adjust: the 32 columns ARE the fc2 accumulator
+            mbar_wait(fold ? &bars->acc2_full : &bars->adj_full, static_cast<uint32_t>(it) & 1);
             tc_fence_after_sync();
+            uint32_t raw[16];
             if (grp < 2) {
-                uint32_t raw[16];
                 tmem_ld16(tmem + lane_off + static_cast<uint32_t>(p.adj_tcol + 16 * grp), raw);
                 tmem_ld_wait();
+            }
+            if (fold) {                                               // the next tile's MMAs may overwrite the accumulator
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc2_free);
+            }
+            if (grp < 2) {
                 float st = 0.f, sq = 0.f;
                 uint32_t pk[8];
 #pragma unroll
@@ -525,14 +562,15 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         for (int it = 0; it < my_tiles; ++it) {
             if (it > 0 && it + 1 < my_tiles) prefetch_stats(it + 1);
             for (int j = 1; j < p.nc; ++j) epi1(it, j, rstd, nrm);
-            if (p.fuse_adj && it > 0) epi3(it - 1);                   // its MMAs were issued right after epi2(it - 1)
+            if (p.fuse_adj == 1 && it > 0) epi3(it - 1);              // its MMAs were issued right after epi2(it - 1)
             if (it + 1 < my_tiles) {
                 row_stats(it + 1, rstd, nrm);
                 epi1(it + 1, 0, rstd, nrm);
             }
-            epi2(it);
+            if (p.fuse_adj == 2) epi3(it);                            // folded adjust: no z, no residual pass
+            else epi2(it);
         }
-        if (p.fuse_adj && my_tiles > 0) epi3(my_tiles - 1);
+        if (p.fuse_adj == 1 && my_tiles > 0) epi3(my_tiles - 1);
     }
 
     tc_fence_before_sync();
@@ -568,9 +606,9 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
     p.a_buf_bytes = p.ks1 * kPanelBytes;
     if (p.fuse_adj) {
         if (p.wadj == nullptr || p.bias_adj == nullptr || p.adj_out == nullptr || (p.adj_col0 % 4) || (p.ld_adj % 4) || p.adj_tcol % 16 ||
-            p.adj_tcol < p.acc1_col[1] + p.hc || p.adj_tcol + 32 > 512 || (reinterpret_cast<uintptr_t>(p.wadj) & 15) ||
-            (reinterpret_cast<uintptr_t>(p.adj_out) & 7))
+            p.adj_tcol + 32 > 512 || (reinterpret_cast<uintptr_t>(p.wadj) & 15) || (reinterpret_cast<uintptr_t>(p.adj_out) & 7))
             return ADSR_ERR_BAD_SHAPE;
+        if (p.fuse_adj == 2 ? (p.n2 != 32 || p.n_pieces != 1 || p.adj_tcol != 0) : (p.adj_tcol < p.acc1_col[1] + p.hc)) return ADSR_ERR_BAD_SHAPE;
         if (p.adj_stats != nullptr && p.adj_stats_slot0 + 2 > p.adj_stats_stride) return ADSR_ERR_BAD_SHAPE;
     }
     const int smem_bytes = 2 * p.a_buf_bytes + p.w1_slots * p.w1_slot_bytes + p.w2_slots * p.w2_slot_bytes + kConstBytes +

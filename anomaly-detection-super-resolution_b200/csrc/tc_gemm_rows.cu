@@ -50,11 +50,10 @@ struct RowParams {
 };
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float absf_bits(float x) { return __uint_as_float(__float_as_uint(x) & 0x7fffffffu); }
 
 // exact-erf GELU (pair), 8.6e-5 absolute: see swin_mlp.cu
 __device__ __forceinline__ float2 gelu_pair(float2 x) {
-    const float2 a = f2(absf_bits(x.x), absf_bits(x.y));
+    const float2 a = f2(fabsf(x.x), fabsf(x.y));          // folds into |R| operand modifiers of FFMA2 / FMUL2
     float2 q = __ffma2_rn(f2(-0.027645503f, -0.027645503f), a, f2(-0.48822206f, -0.48822206f));
     q = __ffma2_rn(q, a, f2(-1.1409364f, -1.1409364f));
     const float2 m = __fmul2_rn(q, a);

@@ -12,6 +12,7 @@ rebuilt whenever the parameters change.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -206,15 +207,16 @@ class PackedMlp:
 _ADJ_N = 32                     # output channels of the fusable adjust convs (gc of the RDG)
 
 
-def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
+def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False, fold_adj: bool = False) -> dict:
     """Static tiling of one fused MLP (swin_mlp.cu): hidden chunks of <= 128 columns (two fp32 chunk accumulators plus the
     fc2 accumulator must fit the 512 TMEM columns), the fc2 output issued in two pieces of >= 128 rows when it is wider
     than 255, and the shared memory left after the two y-tile buffers split between the fc1 and fc2 weight rings."""
-    n2 = round_up(c, 16)
+    # fold_adj: the adjust conv is folded INTO fc2 (W_adj W2, 32 rows), so the "fc2" accumulator is the 32 adjust columns
+    n2 = _ADJ_N if fold_adj else round_up(c, 16)
     k1steps = (c + 15) // 16
     ks1 = (c + 63) // 64
     # TMEM: fc2 accumulator (n2) + two fc1 chunk accumulators (2 hc) [+ 32 columns of the fused adjust accumulator]
-    hc_max = min(128, ((512 - n2 - (_ADJ_N if fuse_adj else 0)) // 2) // 16 * 16)
+    hc_max = min(128, ((512 - n2 - (_ADJ_N if fuse_adj and not fold_adj else 0)) // 2) // 16 * 16)
     nc = (h + hc_max - 1) // hc_max
     hc = round_up((h + nc - 1) // nc, 16)
     widths = [hc] * (nc - 1) + [round_up(h - hc * (nc - 1), 16)]
@@ -230,7 +232,7 @@ def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
     s2 = round_up(max(pieces) * 128, 1024)
     # bytes per tile through each ring decide how the slots are shared out (at least 2 each)
     n1, n2s = 2, 2
-    if avail < n1 * s1 + n2s * s2 or nc > 8 or n2 > 320 or nc * hc > 640:
+    if avail < n1 * s1 + n2s * s2 or nc > 8 or n2 > 320 or nc * hc > 640 or (fold_adj and not fuse_adj):
         raise ValueError(f"fused MLP does not fit: C={c} H={h}")
     while True:
         grew = False
@@ -246,7 +248,7 @@ def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
         if not grew:
             break
     return dict(ks1=ks1, k1steps=k1steps, nc=nc, hc=hc, n2=n2, widths=widths, pieces=pieces, w1_slots=n1, w1_slot_bytes=s1,
-                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(n2, n2 + hc), adj_tcol=n2 + 2 * hc)
+                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(n2, n2 + hc), adj_tcol=0 if fold_adj else n2 + 2 * hc, fold=int(fold_adj))
 
 
 def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
@@ -265,7 +267,12 @@ def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
     return torch.gather(t, 1, src).contiguous().view(torch.uint8).reshape(-1)
 
 
-def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, adjust_w=None, adjust_b=None) -> PackedMlp:
+# W_adj (y + fc2(g)) = y W_adj^T + g (W_adj W2)^T: fc2 and the adjust conv have nothing non-linear between them, and z itself is
+# never needed when the adjust conv is fused -- so its 32 rows replace fc2's C rows (6-10x fewer fc2 MMAs, no residual epilogue).
+_FOLD_ADJUST = os.environ.get("ADSR_FOLD_ADJUST", "1") != "0"
+
+
+def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, adjust_w=None, adjust_b=None, fold_adjust=None) -> PackedMlp:
     """norm2 + fc1 + GELU + fc2 of one Swin block (src/drct.py:438-441, 173-190) for adsr_swin_mlp_bf16: gamma folded into
     fc1 (pack_ln_gemm_weight's algebra), the 0.5 of GELU folded into fc2 (exact in bf16).  With adjust_w [32, C(,1,1)] the
     RDG's adjust 1x1 conv is packed along for adsr_swin_mlp_adjust_bf16 (raises ValueError if the tiling does not fit)."""
@@ -276,19 +283,24 @@ def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, adjust_w=None, a
     fuse_adj = adjust_w is not None
     if fuse_adj and adjust_w.shape[0] != _ADJ_N:
         raise ValueError("only 32-channel adjust convs can be fused")
-    pl = swin_mlp_plan(c, h, fuse_adj)
+    fold = fuse_adj and (_FOLD_ADJUST if fold_adjust is None else bool(fold_adjust))
+    wa32 = adjust_w.detach().float().reshape(_ADJ_N, -1) if fuse_adj else None
+    pl = swin_mlp_plan(c, h, fuse_adj, fold)
     if fuse_adj and pl["adj_tcol"] + _ADJ_N > 512:
         raise ValueError(f"fused adjust does not fit the tensor memory: C={c} H={h}")
     hc, nc, n2, ks1 = pl["hc"], pl["nc"], pl["n2"], pl["ks1"]
     w1g = torch.zeros(nc * hc, ks1 * 64, device=dev)
     w1g[:h, :c] = w1 * gamma.detach().float()[None, :]
     w2p = torch.zeros(n2, nc * hc + 64, device=dev)
-    w2p[:c, :h] = w2
+    if fold:
+        w2p[:, :h] = (wa32.double() @ w2.double()).float()
+    else:
+        w2p[:c, :h] = w2
     bias1 = torch.zeros(nc * hc, device=dev)
     bias1[:h] = w1 @ beta.detach().float() + (fc1_b.detach().float() if fc1_b is not None else 0.0)
     colsum1 = w1g.to(torch.bfloat16).float().sum(dim=1)
     bias2 = torch.zeros(n2, device=dev)
-    if fc2_b is not None:
+    if fc2_b is not None and not fold:
         bias2[:c] = fc2_b.detach().float()
     slabs1, slabs2 = [], []
     for j, wj in enumerate(pl["widths"]):
@@ -306,13 +318,16 @@ def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, adjust_w=None, a
                 dcol += rows
     pieces = pl["pieces"] + [0] * (2 - len(pl["pieces"]))
     plan = [ks1, pl["k1steps"], nc, hc, n2, pl["acc1_col"][0], pl["acc1_col"][1], len(pl["pieces"]), pieces[0], pieces[1],
-            pl["w1_slots"], pl["w1_slot_bytes"], pl["w2_slots"], pl["w2_slot_bytes"]] + pl["widths"] + [0] * (8 - nc) + [pl["adj_tcol"]]
+            pl["w1_slots"], pl["w1_slot_bytes"], pl["w2_slots"], pl["w2_slot_bytes"]] + pl["widths"] + [0] * (8 - nc) + [pl["adj_tcol"], pl["fold"]]
     wadj = bias_adj = None
     if fuse_adj:
         wa = torch.zeros(_ADJ_N, ks1 * 64, device=dev)
-        wa[:, :c] = adjust_w.detach().float().reshape(_ADJ_N, -1)
+        wa[:, :c] = wa32
         wadj = torch.cat([_swizzle_slab(wa[:, 64 * s:64 * s + 64].contiguous()) for s in range(ks1)]).contiguous()
-        bias_adj = (adjust_b.detach().float() if adjust_b is not None else torch.zeros(_ADJ_N, device=dev)).contiguous()
+        bias_adj = adjust_b.detach().float().clone() if adjust_b is not None else torch.zeros(_ADJ_N, device=dev)
+        if fold and fc2_b is not None:
+            bias_adj = bias_adj + (wa32.double() @ fc2_b.detach().double()).float()       # W_adj b2 joins the conv's own bias
+        bias_adj = bias_adj.contiguous()
     return PackedMlp(torch.cat(slabs1).contiguous(), torch.cat(slabs2).contiguous(), bias1, colsum1, bias2,
                      torch.tensor(plan, dtype=torch.int32), float(eps), c, h, wadj, bias_adj)
 

@@ -64,20 +64,24 @@ def test_mlp_many_tiles_per_cta():
     _mlp_case(128 * 148 * 3 + 5, 180, 360, seed=3)
 
 
-@pytest.mark.parametrize("C,H", [(180, 360), (212, 424), (244, 488), (60, 120)])
-def test_mlp_fused_adjust(C, H):
+@pytest.mark.parametrize("C,H,fold,M", [(180, 360, False, 677), (212, 424, False, 677), (244, 488, False, 677), (60, 120, False, 677),
+                                        (180, 360, True, 677), (212, 424, True, 677), (244, 488, True, 677), (276, 276, True, 677),
+                                        (288, 288, True, 677), (60, 120, True, 677), (180, 360, True, 128), (180, 360, True, 128 * 148 * 3 + 5)])
+def test_mlp_fused_adjust(C, H, fold, M):
     """Fused adjust 1x1 conv (src/drct.py:389-393): slab[:, C:C+32] = LReLU_0.2(adjust(z)), z never written; row statistics of the
-    32 new columns in the given slot, the following slot zeroed."""
+    32 new columns in the given slot, the following slot zeroed.  fold: the adjust conv folded into fc2 (W_adj W2 as the fc2
+    weights, accumulator started with y W_adj^T) -- same result, no residual pass."""
     ops, pack = mod("ops"), mod("pack")
     torch.manual_seed(C)
-    M, ld = 128 * 5 + 37, 320
+    ld = 320
     y = torch.full((M, ld), 5.0, device=DEV, dtype=torch.bfloat16)
     y[:, :C] = (torch.randn(M, C, device=DEV) * 1.5 + 0.3).to(torch.bfloat16)
     w1, b1 = torch.randn(H, C, device=DEV) * 0.08, torch.randn(H, device=DEV) * 0.2
     w2, b2 = torch.randn(C, H, device=DEV) * 0.08, torch.randn(C, device=DEV) * 0.2
     wa, ba = torch.randn(32, C, 1, 1, device=DEV) * 0.1, torch.randn(32, device=DEV) * 0.2
     gamma, beta = 1.0 + 0.2 * torch.randn(C, device=DEV), 0.1 * torch.randn(C, device=DEV)
-    pm = pack.pack_swin_mlp(w1, b1, gamma, beta, 1e-5, w2, b2, wa, ba)
+    pm = pack.pack_swin_mlp(w1, b1, gamma, beta, 1e-5, w2, b2, wa, ba, fold_adjust=fold)
+    assert pm.plan.tolist()[23] == int(fold)
     yf = y[:, :C].float()
     stats = torch.zeros(M, 2, 2, device=DEV)
     stats[:, 0, 0], stats[:, 0, 1] = yf.sum(1), (yf ** 2).sum(1)
@@ -85,13 +89,17 @@ def test_mlp_fused_adjust(C, H):
     st_out = torch.full((M, 6, 2), 1e9, device=DEV)
     ops.swin_mlp_adjust(y, C, pm, slab, C, stats_in=(stats, 1), stats_out=(st_out, 2))
     torch.cuda.synchronize()
+    slab_rev = torch.full((M, ld), -7.0, device=DEV, dtype=torch.bfloat16)
+    ops.swin_mlp_adjust(y, C, pm, slab_rev, C, stats_in=(stats, 1), stats_out=(torch.empty_like(st_out), 2), reverse=True)
+    torch.cuda.synchronize()
+    assert torch.equal(slab, slab_rev), "reverse tile order must not change the result"
     z = yf + F.linear(F.gelu(F.linear(F.layer_norm(yf, (C,), gamma, beta, 1e-5), w1, b1)), w2, b2)
     want = F.leaky_relu(F.linear(z, wa.view(32, C), ba), 0.2)
     got = slab[:, C:C + 32].float()
     err = float((got - want).abs().max() / want.abs().max())
     assert err < 0.015, f"C={C}: rel err {err}"
-    assert float((slab[:, :C].float() + 7.0).abs().max()) == 0.0 and float((slab[:, C + 32:].float() + 7.0).abs().max()) == 0.0, \
-        "wrote outside the 32-column slice"
+    outside = torch.cat([slab[:, :C], slab[:, C + 32:]], dim=1).float()
+    assert float((outside + 7.0).abs().max()) == 0.0, "wrote outside the 32-column slice"
     s1, s2 = got.sum(1), (got ** 2).sum(1)
     assert float((st_out[:, 2, 0] - s1).abs().max()) < 5e-3 * float(s1.abs().max()) + 1e-3
     assert float((st_out[:, 2, 1] - s2).abs().max()) < 5e-3 * float(s2.abs().max()) + 1e-3

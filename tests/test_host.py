@@ -152,7 +152,34 @@ def test_swin_mlp_plans_fit_the_sm():
             assert smem <= 232448 and pl["w1_slots"] >= 2 and pl["w2_slots"] >= 2 and nc * hc <= 640
     pm = pack.pack_swin_mlp(torch.randn(360, 180), torch.randn(360), torch.ones(180), torch.zeros(180), 1e-5, torch.randn(180, 360),
                             torch.randn(180), torch.randn(32, 180, 1, 1), torch.randn(32))
-    assert pm.wadj.numel() == 3 * 32 * 128 and pm.bias_adj.numel() == 32 and pm.plan.numel() == 23
+    assert pm.wadj.numel() == 3 * 32 * 128 and pm.bias_adj.numel() == 32 and pm.plan.numel() == 24
+
+
+def test_swin_mlp_folded_adjust_pack():
+    """Folded adjust (W_adj W2 as the fc2 weights): fits every DRCT-L width with a 32-column accumulator, and the packed slabs and
+    bias are the products they should be."""
+    pack = importlib.import_module(PKG + ".pack")
+    for c, h in [(180, 360), (212, 424), (244, 488), (276, 276), (308, 308)]:
+        pl = pack.swin_mlp_plan(c, h, True, True)
+        assert pl["n2"] == 32 and pl["pieces"] == [32] and pl["adj_tcol"] == 0 and pl["fold"] == 1 and pl["acc1_col"][0] == 32
+        assert 32 + 2 * pl["hc"] <= 512 and pl["w2_slot_bytes"] == 4096
+        smem = 2 * pl["ks1"] * 16384 + pl["w1_slots"] * pl["w1_slot_bytes"] + pl["w2_slots"] * 4096 + pack._MLP_FIXED_BYTES + pl["ks1"] * 4096 + 2048
+        assert smem <= 232448
+    torch.manual_seed(3)
+    w2, b2, wa, ba = torch.randn(180, 360), torch.randn(180), torch.randn(32, 180, 1, 1), torch.randn(32)
+    args = (torch.randn(360, 180), torch.randn(360), torch.ones(180), torch.zeros(180), 1e-5, w2, b2, wa, ba)
+    pm, pm0 = pack.pack_swin_mlp(*args, fold_adjust=True), pack.pack_swin_mlp(*args, fold_adjust=False)
+    assert pm.plan.tolist()[4] == 32 and pm.plan.tolist()[23] == 1 and pm0.plan.tolist()[23] == 0 and pm0.plan.tolist()[4] == 192
+    assert torch.allclose(pm.bias_adj, ba + wa.view(32, 180) @ b2, atol=1e-4) and torch.equal(pm0.bias_adj, ba)
+    wf = (wa.view(32, 180).double() @ (0.5 * w2).double()).float().to(torch.bfloat16)
+    img = pm.w2.view(torch.bfloat16).view(-1, 32, 8, 8)           # slabs of [32 rows x 64 hidden columns], (chunk, K slab) order
+    nc, hc = pm.plan.tolist()[2], pm.plan.tolist()[3]
+    assert nc * hc >= 360 and img.shape[0] == sum((w + 63) // 64 for w in pm.plan.tolist()[14:14 + nc])
+    for (n, k) in [(0, 0), (5, 77), (31, 200)]:
+        j, r = divmod(k, hc)
+        slab = sum((w + 63) // 64 for w in pm.plan.tolist()[14:14 + j]) + r // 64
+        chunk, e = divmod(r % 64, 8)
+        assert img[slab, n, chunk ^ (n % 8), e] == wf[n, k]
 
 
 def test_state_dict_matches_reference_layout(pkg):

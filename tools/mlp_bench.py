@@ -31,14 +31,20 @@ for (C, H) in shapes:
     fl = 4.0 * M * C * H
     print(f"swin_mlp C={C} H={H}: {best*1e3:8.1f} us (avg {avg*1e3:8.1f})  {fl/best/1e9:7.1f} TFLOP/s  {4.0*M*C/best/1e6:7.1f} GB/s(y+z)")
     # the same with the RDG's adjust 1x1 conv fused in (z never written) next to MLP + separate adjust GEMM
+    if C + 32 > 320: continue      # adjust5 is not a 32-channel conv
     wa, ba = torch.randn(32, C, device=dev) * 0.05, torch.randn(32, device=dev)
+    margs = (torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
+             torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev), wa, ba)
+    slab = torch.zeros(M, 320, device=dev, dtype=torch.bfloat16); st_s = torch.zeros(M, 12, 2, device=dev)
+    if hasattr(pack, "_FOLD_ADJUST"):
+        pmf = pack.pack_swin_mlp(*margs, fold_adjust=True)
+        bfo, afo = timeit(lambda: ops.swin_mlp_adjust(y, C, pmf, slab, C, stats_in=(stats, 2), stats_out=(st_s, 2)))
+        print(f"   + adjust FOLDED into fc2: {bfo*1e3:8.1f} us (avg {afo*1e3:8.1f})   plan {pmf.plan.tolist()[:14]}")
     try:
-        pma = pack.pack_swin_mlp(torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
-                                 torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev), wa, ba)
+        pma = pack.pack_swin_mlp(*margs, fold_adjust=False) if hasattr(pack, "_FOLD_ADJUST") else pack.pack_swin_mlp(*margs)
     except ValueError:
         continue
     padj = pack.pack_gemm_weight(wa, ba)
-    slab = torch.zeros(M, 320, device=dev, dtype=torch.bfloat16); st_s = torch.zeros(M, 12, 2, device=dev)
     bf, af = timeit(lambda: ops.swin_mlp_adjust(y, C, pma, slab, C, stats_in=(stats, 2), stats_out=(st_s, 2)))
     def sep():
         ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2))

@@ -23,6 +23,8 @@ nc = pm.plan.tolist()[2]
 rel = lambda v: int(v) - t0 if int(v) > 0 else -1
 for it in range(1, 5):
     print(f"---- tile {it}")
+    print(f" tile warp: z wait {rel(t[0,it,0,0]):7d} z_ready {rel(t[0,it,0,1]):7d} store read {rel(t[0,it,0,2]):7d} load(it+2) issued {rel(t[0,it,0,3]):7d}"
+          f" | fc1 a_full: wait {rel(t[0,it,1,0]):7d} ok {rel(t[0,it,1,1]):7d}")
     for j in range(nc):
         print(f" fc1 ch{j}: start {rel(t[1,it,j,0]):7d} acc1_free {rel(t[1,it,j,1]):7d} issued {rel(t[1,it,j,2]):7d}"
               f" | epi1: wait {rel(t[2,it,j,0]):7d} acc_ok {rel(t[2,it,j,1]):7d} slab0 {rel(t[2,it,j,2]):7d} slab1 {rel(t[2,it,j,3]):7d}")
