@@ -211,14 +211,13 @@ extern "C" int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int 
                                          void* out, int64_t ldo, int ocol0, float* stats_out, int stats_out_slot0,
                                          int stats_out_stride, int reverse_tiles, int num_sms, void* stream) {
     if (M <= 0) return ADSR_OK;
-    if (plan_len < 23 || wadj_packed == nullptr || bias_adj == nullptr || out == nullptr || ldo < ocol0 + 32) return ADSR_ERR_BAD_SHAPE;
+    if (plan_len < 24 || plan[23] == 0 || wadj_packed == nullptr || bias_adj == nullptr || out == nullptr || ldo < ocol0 + 32) return ADSR_ERR_BAD_SHAPE;
     SwinMlpParams p{};
     p.rev = reverse_tiles != 0;
     const int st = swin_mlp_common(p, y, ldy, M, C, w1_packed, w2_packed, bias1, colsum1, bias2, plan, plan_len, ln_eps, ln_stats_in,
                                    stats_in_slots, stats_in_stride);
     if (st != ADSR_OK) return st;
-    p.fuse_adj = (plan_len >= 24 && plan[23] != 0) ? 2 : 1;
-    p.adj_tcol = plan[22];
+    p.fuse_adj = 1;
     p.wadj = static_cast<const uint8_t*>(wadj_packed);
     p.bias_adj = bias_adj;
     p.adj_out = static_cast<__nv_bfloat16*>(out);

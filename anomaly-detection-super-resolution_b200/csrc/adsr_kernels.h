@@ -107,6 +107,7 @@ struct SwinMlpParams {
     int stats_in_slots, stats_in_stride;
     float ln_eps;
     int C, M, m_tiles;
+    float inv_c;          // 1 / C (set by the launcher)
     int rev;              // walk the row tiles from the last one down (what the producer wrote last is still in L2)
     int ks1, k1steps;     // 64-wide panels / K=16 steps of the y tile
     int nc, hc;           // hidden chunks, chunk stride in bias1 / colsum1 (= TMEM columns per fc1 accumulator)
@@ -117,10 +118,10 @@ struct SwinMlpParams {
     int acc1_col[2];
     int w1_slots, w1_slot_bytes, w2_slots, w2_slot_bytes, a_buf_bytes;
     long long* trace;     // optional [4 roles][8 tiles][64][8] clock64 timeline of CTA 0 (tools/mlp_trace.py), else nullptr
-    // optional fused adjust 1x1 conv (src/drct.py:389-393): adj_out[:, adj_col0 + n] = LReLU(z W_adj^T + b)[n], n < 32; z itself is
-    // then NOT written (nothing else reads it)
+    // optional adjust 1x1 conv (src/drct.py:389-393) FOLDED into fc2: adj_out[:, adj_col0 + n] = LReLU(z W_adj^T + b)[n], n < 32, computed
+    // as y W_adj^T + g (W_adj W2)^T + (b_adj + W_adj b2): the fc2 ring carries the 32 rows of W_adj W2 (n2 = 32), the accumulator
+    // starts with y W_adj^T, and z itself never exists
     int fuse_adj;
-    int adj_tcol;         // TMEM column of the [128 x 32] adjust accumulator
     const uint8_t* wadj;  // ks1 slabs [32 rows x 64 bf16], 128-byte swizzle; resident in shared memory
     const float* bias_adj;   // [32]
     __nv_bfloat16* adj_out;
@@ -129,8 +130,9 @@ struct SwinMlpParams {
     float adj_slope;
     float2* adj_stats;    // per-row (sum, sumsq) of the 32 new columns -> adj_stats[row * stride + slot0] (slot0 + 1 is zeroed)
     int adj_stats_slot0, adj_stats_stride;
+    int adj_stats_vec4;   // the two slots of a row form one aligned 16-byte store (set by the launcher)
 };
-int swin_mlp_fixed_smem_bytes();
+int swin_mlp_fixed_smem_bytes(int hidden_padded, int n2);
 int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, long long ldz, int num_sms, cudaStream_t stream);
 
 // ---- fused attention half of a Swin block (swin_attn.cu)

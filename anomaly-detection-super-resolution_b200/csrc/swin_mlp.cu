@@ -29,13 +29,17 @@ constexpr int kFc1Warp = 17;                  // fc1 MMA issuer
 constexpr int kFc2Warp = 18;                  // fc2 MMA issuer
 constexpr int kW2LoaderWarp = 19;             // fc2 weight slabs
 constexpr int kTileWarp = 20;                 // TMEM alloc, y-tile loads, z-tile stores
-constexpr int kThreads = 21 * 32;
+constexpr int kAuxWarp0 = 21;                 // warps 21..24 (TMEM lane quadrant = warp % 4): row mean / rstd two tiles ahead, folded-adjust epilogue
+constexpr int kThreads = 25 * 32;
 constexpr int kPanelBytes = 128 * 128;        // 128 rows x 64 bf16
 constexpr int kMaxHidden = 640;               // padded hidden columns (sum of chunk strides)
 constexpr int kMaxN2 = 320;
-constexpr int kConstBytes = (2 * kMaxHidden + kMaxN2) * 4;
+constexpr int kRowStatBytes = 2 * 128 * 8;    // (rstd, -mean * rstd) of two tiles
+// bias1 / colsum1 (padded hidden width each) / bias2 caches + row statistics
+__host__ __device__ constexpr int const_bytes(int hidden_padded, int n2) { return (2 * hidden_padded + n2) * 4 + kRowStatBytes; }
 constexpr int kSmemLimit = 232448;            // 227 KB
-constexpr int kAdjSlabBytes = 32 * 128;       // fused adjust: 32 output rows x 64 bf16
+constexpr int kAdjSlabBytes = 32 * 128;       // folded adjust: 32 output rows x 64 bf16
+constexpr int kAdjStageBytes = 4 * 32 * 64;   // folded adjust: one [32 rows x 32 bf16] staging box per aux warp (16-byte chunks swizzled)
 
 struct __align__(16) MlpBarriers {
     uint64_t w1_full[8], w1_empty[8];
@@ -47,9 +51,9 @@ struct __align__(16) MlpBarriers {
     uint64_t h_ready[2][2];                   // [accumulator buffer][64-column slab of the chunk]
     uint64_t acc2_full;
     uint64_t acc2_free;
-    uint64_t adj_w_full;                      // fused adjust: the resident weight slabs have landed
-    uint64_t adj_full;                        // adjust accumulator complete
-    uint64_t adj_done[2];                     // the adjust MMAs have finished reading the z tile in buffer b
+    uint64_t adj_w_full;                      // folded adjust: the resident W_adj slabs have landed
+    uint64_t adj_done[2];                     // folded adjust: fc1 and the y W_adj^T MMAs have finished reading the y tile in buffer b
+    uint64_t rs_full[2], rs_free[2];          // (rstd, -mean * rstd) of a tile's rows in s_rowstat[tile parity]
     uint32_t tmem_base;
 };
 
@@ -88,11 +92,12 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     uint8_t* ring1 = smem + 2 * p.a_buf_bytes;                        // w1_slots x w1_slot_bytes
     uint8_t* ring2 = ring1 + p.w1_slots * p.w1_slot_bytes;            // w2_slots x w2_slot_bytes
     uint8_t* wadj_s = ring2 + p.w2_slots * p.w2_slot_bytes;           // fused adjust: ks1 x [32 x 64] weight slabs (resident)
-    float* s_bias1 = reinterpret_cast<float*>(wadj_s + (p.fuse_adj ? p.ks1 * kAdjSlabBytes : 0));
-    float* s_colsum1 = s_bias1 + kMaxHidden;
-    float* s_bias2 = s_colsum1 + kMaxHidden;
-    float2* s_adj_stat = reinterpret_cast<float2*>(s_bias2 + kMaxN2);   // [2][128] fused adjust: row partials of the two column halves
-    MlpBarriers* bars = reinterpret_cast<MlpBarriers*>(s_adj_stat + (p.fuse_adj ? 256 : 0));
+    uint8_t* adj_stage = wadj_s + (p.fuse_adj ? p.ks1 * kAdjSlabBytes : 0);   // folded adjust: output boxes of the aux warps
+    float* s_bias1 = reinterpret_cast<float*>(adj_stage + (p.fuse_adj ? kAdjStageBytes : 0));
+    float* s_colsum1 = s_bias1 + p.nc * p.hc;                         // multiples of 16 floats: float4 reads stay aligned
+    float* s_bias2 = s_colsum1 + p.nc * p.hc;
+    float2* s_rowstat = reinterpret_cast<float2*>(s_bias2 + p.n2);  // [2 tile parities][128 rows]: (rstd, -mean * rstd)
+    MlpBarriers* bars = reinterpret_cast<MlpBarriers*>(s_rowstat + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -108,7 +113,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         s_bias1[i] = p.bias1[i];
         s_colsum1[i] = p.colsum1[i];
     }
-    for (int i = threadIdx.x; i < p.n2; i += kThreads) s_bias2[i] = p.bias2[i];
+    // folded adjust: the accumulator's bias is the adjust conv's (with W_adj b2 folded in on the host)
+    for (int i = threadIdx.x; i < p.n2; i += kThreads) s_bias2[i] = p.fuse_adj ? p.bias_adj[i] : p.bias2[i];
 
     if (warp == kFc1Warp && lane == 0) {
         for (int s = 0; s < 8; ++s) {
@@ -124,14 +130,15 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             mbar_init(&bars->acc1_free[b], 1);
             mbar_init(&bars->h_ready[b][0], kEpiWarps);
             mbar_init(&bars->h_ready[b][1], kEpiWarps);
+            mbar_init(&bars->rs_full[b], 4);
+            mbar_init(&bars->rs_free[b], kEpiWarps);
         }
         mbar_init(&bars->acc2_full, 1);
-        mbar_init(&bars->acc2_free, kEpiWarps);
+        mbar_init(&bars->acc2_free, p.fuse_adj ? 4 : kEpiWarps);      // folded adjust: its own four warps read the accumulator
         mbar_init(&bars->adj_w_full, 1);
-        mbar_init(&bars->adj_full, 1);
         // folded adjust: the tile buffer is free once BOTH its fc1 MMAs and its y W_adj^T MMAs (two issuing warps) have completed
-        mbar_init(&bars->adj_done[0], p.fuse_adj == 2 ? 2 : 1);
-        mbar_init(&bars->adj_done[1], p.fuse_adj == 2 ? 2 : 1);
+        mbar_init(&bars->adj_done[0], 2);
+        mbar_init(&bars->adj_done[1], 2);
         fence_barrier_init();
     }
     if (warp == kTileWarp) tmem_alloc<512>(&bars->tmem_base);
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     // programmatic dependent launch: set-up and weight loaders overlap the predecessor's tail; the warps that touch activations or
     // row statistics (tile loads / stores, epilogues) wait for it to complete
     pdl_launch_dependents();
-    if (warp < kEpiWarps || warp == kTileWarp) pdl_wait();
+    if (warp < kEpiWarps || warp >= kTileWarp) pdl_wait();
 
     // The control warps below stay CONVERGED (uniform control flow, one elected lane issues): descriptors then live in
     // uniform registers and no tcgen05 / bulk-copy instruction gets wrapped in a lane-serialising loop.
@@ -224,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                         umma_commit(&bars->w1_empty[slot]);
                         if (s == p.ks1 - 1) {
                             umma_commit(&bars->acc1_full[b]);
-                            if (p.fuse_adj == 2 && j == p.nc - 1) umma_commit(&bars->adj_done[it & 1]);   // last read of the y tile by fc1
+                            if (p.fuse_adj && j == p.nc - 1) umma_commit(&bars->adj_done[it & 1]);   // last read of the y tile by fc1
                         }
                     }
                     __syncwarp();
@@ -239,30 +246,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         uint32_t phase = 0;
         const uint32_t slot_units = static_cast<uint32_t>(p.w2_slot_bytes >> 4);
         const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring2));
-        // fused adjust: D_adj[128 x 32] = z_tile W_adj^T, issued once the last epilogue has turned the y tile into z in place
-        // (i.e. right when the fc2 accumulator is free again); its completion releases the tile buffer for the next load
         const uint64_t adj_a_desc0 = umma_desc_k_sw128(smem_u32(a_buf));
         const uint64_t adj_b_desc = umma_desc_k_sw128(smem_u32(wadj_s));
         const uint32_t adj_idesc = umma_idesc_bf16_m128(32u);
-        auto issue_adj = [&](int it) {
-            if (it == 0) mbar_wait(&bars->adj_w_full, 0);
-            mbar_wait(&bars->z_ready[it & 1], static_cast<uint32_t>(it >> 1) & 1);
-            tc_fence_after_sync();
-            if (elect_one_sync()) {
-                const uint64_t a_desc = adj_a_desc0 + static_cast<uint64_t>((it & 1) * static_cast<uint32_t>(p.a_buf_bytes >> 4));
-                const uint32_t d = tmem + static_cast<uint32_t>(p.adj_tcol);
-                for (int s = 0; s < p.ks1; ++s) {
-                    const int ksteps = min(4, p.k1steps - 4 * s);
-                    for (int j = 0; j < ksteps; ++j)
-                        umma_bf16(d, a_desc + static_cast<uint64_t>(s * (kPanelBytes >> 4)) + 2 * j,
-                                  adj_b_desc + static_cast<uint64_t>(s * (kAdjSlabBytes >> 4)) + 2 * j, adj_idesc, (s > 0 || j > 0) ? 1u : 0u);
-                }
-                umma_commit(&bars->adj_full);
-                umma_commit(&bars->adj_done[it & 1]);
-            }
-            __syncwarp();
-        };
-        // folded adjust (fuse_adj == 2): W_adj (y + fc2(g)) = y W_adj^T + g (W_adj W2)^T -- the fc2 ring carries the 32 rows of
+        // folded adjust: W_adj (y + fc2(g)) = y W_adj^T + g (W_adj W2)^T -- the fc2 ring carries the 32 rows of
         // W_adj W2, the accumulator is 32 columns wide, and the y term goes in first, straight from the tile buffer
         auto issue_adj_y = [&](int it) {
             if (it == 0) mbar_wait(&bars->adj_w_full, 0);
@@ -293,12 +280,11 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                     mbar_wait(&bars->h_ready[b][s], static_cast<uint32_t>(cg >> 1) & 1);
                     if (j == 0 && s == 0) {
                         mbar_wait(&bars->acc2_free, (static_cast<uint32_t>(it) & 1) ^ 1);
-                        if (p.fuse_adj == 1 && it > 0) issue_adj(it - 1);      // the previous tile's z is complete: adjust goes first
-                        if (p.fuse_adj == 2) issue_adj_y(it);                  // folded adjust: the accumulator starts as y W_adj^T
+                        if (p.fuse_adj) issue_adj_y(it);                       // folded adjust: the accumulator starts as y W_adj^T
                     }
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 1);
                     const uint32_t at = acc1 + static_cast<uint32_t>(64 * s);     // K=16 step u of the chunk lives at column 16 u
-                    const uint32_t first_acc = (j == 0 && s == 0 && p.fuse_adj != 2) ? 0u : 1u;
+                    const uint32_t first_acc = (j == 0 && s == 0 && !p.fuse_adj) ? 0u : 1u;
                     for (int pc = 0; pc < p.n_pieces; ++pc) {
                         const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.piece_rows[pc]));
                         const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[pc]);
@@ -323,7 +309,6 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                 }
             }
         }
-        if (p.fuse_adj == 1 && my_tiles > 0) issue_adj(my_tiles - 1);
     } else if (warp == kTileWarp) {
         // ============================================================ y-tile loads / z-tile stores (same buffers)
         auto load_a = [&](int it) {
@@ -348,7 +333,9 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             const int m0 = tile_of(it) * 128;
             if (p.fuse_adj) {
                 // z only feeds the fused adjust conv: nothing is stored; the buffer is free once the adjust MMAs have read it
+                trace_ev<TRACE>(p.trace, 0, it, 0, 0);
                 mbar_wait(&bars->adj_done[ab], static_cast<uint32_t>(it >> 1) & 1);
+                trace_ev<TRACE>(p.trace, 0, it, 0, 2);
             } else {
                 trace_ev<TRACE>(p.trace, 0, it, 0, 0);
                 mbar_wait(&bars->z_ready[ab], static_cast<uint32_t>(it >> 1) & 1);
@@ -377,23 +364,15 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         const int rsw = r_in_tile & 7;
         const bool tr = TRACE && warp == 0;
 
+        // (rstd, -mean * rstd) of the tile's rows, produced two tiles ahead by the aux warps (the (sum, sumsq) slots were written by
+        // the previous kernel: fetched cold here they cost ~2k cycles of exposed latency per tile on the clock64 timeline)
         auto row_stats = [&](int it, float& rstd, float& nrm) {
-            const int row = tile_of(it) * 128 + r_in_tile;
-            rstd = 1.f;
-            nrm = 0.f;                                                // nrm = -mean * rstd
-            if (row < p.M) {
-                const float2* sp = p.stats_in + static_cast<long long>(row) * p.stats_in_stride;
-                float s1 = 0.f, s2 = 0.f;
-                for (int k = 0; k < p.stats_in_slots; ++k) {
-                    const float2 v = __ldg(sp + k);
-                    s1 += v.x;
-                    s2 += v.y;
-                }
-                const float inv_c = 1.0f / static_cast<float>(p.C);
-                const float mean = s1 * inv_c;
-                rstd = rsqrtf(fmaxf(s2 * inv_c - mean * mean, 0.f) + p.ln_eps);
-                nrm = -mean * rstd;
-            }
+            mbar_wait(&bars->rs_full[it & 1], static_cast<uint32_t>(it >> 1) & 1);
+            const float2 v = s_rowstat[(it & 1) * 128 + r_in_tile];
+            rstd = v.x;
+            nrm = v.y;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->rs_free[it & 1]);
         };
 
         // ---- one hidden chunk: TMEM fp32 -> LN fold + bias + GELU -> bf16 into the first 8 columns of each 16-column unit
@@ -412,8 +391,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                 const int u = grp + 4 * h;
                 if (u < units) {
                     uint32_t raw[16];
+                    if (tr) trace_ev<TRACE>(p.trace, 2, it, 32 + j, 4 * h);
                     tmem_ld16(taddr + static_cast<uint32_t>(16 * u), raw);
                     tmem_ld_wait();
+                    if (tr) trace_ev<TRACE>(p.trace, 2, it, 32 + j, 4 * h + 1);
                     const float* bp = s_bias1 + j * p.hc + 16 * u;
                     const float* cp = s_colsum1 + j * p.hc + 16 * u;
                     uint32_t pk[8];
@@ -429,8 +410,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                         pk[2 * q4] = pack_bf16x2(g0.x, g0.y);
                         pk[2 * q4 + 1] = pack_bf16x2(g1.x, g1.y);
                     }
+                    if (tr) trace_ev<TRACE>(p.trace, 2, it, 32 + j, 4 * h + 2);
                     tmem_st8(taddr + static_cast<uint32_t>(16 * u), pk);
                     tmem_st_wait();
+                    if (tr) trace_ev<TRACE>(p.trace, 2, it, 32 + j, 4 * h + 3);
                 }
                 tc_fence_before_sync();
                 __syncwarp();
@@ -494,83 +477,119 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             if (tr) trace_ev<TRACE>(p.trace, 2, it, 16, 2);
         };
 
-        // ---- fused adjust: 32 new slab columns = LReLU(acc + bias), stored at the tile's token rows, + their row statistics
-        auto epi3 = [&](int it) {
-            const int row = tile_of(it) * 128 + r_in_tile;
-            const bool fold = p.fuse_adj == 2;                        // folded adjust: the 32 columns ARE the fc2 accumulator
-            mbar_wait(fold ? &bars->acc2_full : &bars->adj_full, static_cast<uint32_t>(it) & 1);
-            tc_fence_after_sync();
-            uint32_t raw[16];
-            if (grp < 2) {
-                tmem_ld16(tmem + lane_off + static_cast<uint32_t>(p.adj_tcol + 16 * grp), raw);
-                tmem_ld_wait();
-            }
-            if (fold) {                                               // the next tile's MMAs may overwrite the accumulator
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->acc2_free);
-            }
-            if (grp < 2) {
-                float st = 0.f, sq = 0.f;
-                uint32_t pk[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float v0 = __uint_as_float(raw[2 * e]) + __ldg(p.bias_adj + 16 * grp + 2 * e);
-                    float v1 = __uint_as_float(raw[2 * e + 1]) + __ldg(p.bias_adj + 16 * grp + 2 * e + 1);
-                    v0 = v0 > 0.f ? v0 : v0 * p.adj_slope;
-                    v1 = v1 > 0.f ? v1 : v1 * p.adj_slope;
-                    st += v0 + v1;
-                    sq = fmaf(v0, v0, fmaf(v1, v1, sq));
-                    pk[e] = pack_bf16x2(v0, v1);
-                }
-                s_adj_stat[grp * 128 + r_in_tile] = f2(st, sq);
-                if (row < p.M) {
-                    // the slab slice starts at an 8-byte aligned column (C_k * 2 bytes): four 8-byte stores per 16 columns
-                    uint2* dst = reinterpret_cast<uint2*>(p.adj_out + static_cast<long long>(row) * p.ld_adj + p.adj_col0 + 16 * grp);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) dst[e] = make_uint2(pk[2 * e], pk[2 * e + 1]);
-                }
-            }
-            tc_fence_before_sync();
-            named_bar_sync(1 + quad, 128);
-            if (grp == 0 && row < p.M && p.adj_stats != nullptr) {
-                const float2 a = s_adj_stat[r_in_tile], b = s_adj_stat[128 + r_in_tile];
-                float2* so = p.adj_stats + static_cast<long long>(row) * p.adj_stats_stride + p.adj_stats_slot0;
-                so[0] = f2(a.x + b.x, a.y + b.y);
-                so[1] = f2(0.f, 0.f);
-            }
-            named_bar_sync(1 + quad, 128);                            // s_adj_stat is reused by the next tile
-        };
-
         // task order mirrors the MMA streams: chunk 0 of tile it+1 is turned around BEFORE the last epilogue of tile it
         // (fc1 runs ahead of fc2, so that chunk is ready while the last fc2 MMAs of tile it are still in flight)
-        // the (sum, sumsq) slots of a row were written by the previous kernel: fetched cold they cost ~2k cycles of exposed latency per
-        // tile (clock64 timeline), so the lines of tile it + 1 are pulled into L1 while the chunks of tile it are converted
-        auto prefetch_stats = [&](int it) {
-            const int row = tile_of(it) * 128 + r_in_tile;
-            if (grp == 0 && row < p.M) {
-                const char* sp = reinterpret_cast<const char*>(p.stats_in + static_cast<long long>(row) * p.stats_in_stride);
-                for (int o = 0; o < p.stats_in_slots * 8; o += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + o));
-            }
-        };
         float rstd = 1.f, nrm = 0.f;
         if (my_tiles > 0) {
-            if (my_tiles > 1) prefetch_stats(1);
             row_stats(0, rstd, nrm);
             epi1(0, 0, rstd, nrm);
         }
         for (int it = 0; it < my_tiles; ++it) {
-            if (it > 0 && it + 1 < my_tiles) prefetch_stats(it + 1);
             for (int j = 1; j < p.nc; ++j) epi1(it, j, rstd, nrm);
-            if (p.fuse_adj == 1 && it > 0) epi3(it - 1);              // its MMAs were issued right after epi2(it - 1)
             if (it + 1 < my_tiles) {
                 row_stats(it + 1, rstd, nrm);
                 epi1(it + 1, 0, rstd, nrm);
             }
-            if (p.fuse_adj == 2) epi3(it);                            // folded adjust: no z, no residual pass
-            else epi2(it);
+            if (!p.fuse_adj) epi2(it);                                // folded adjust: no z, no residual pass (the aux warps finish the tile)
         }
-        if (p.fuse_adj == 1 && my_tiles > 0) epi3(my_tiles - 1);
+    } else if (warp >= kAuxWarp0) {
+        // ============================================================ aux warps, one per TMEM lane quadrant (thread = row of the tile):
+        //  * LayerNorm row statistics: (sum, sumsq) slots -> (rstd, -mean * rstd) in shared memory, up to two tiles ahead;
+        //  * folded adjust: 32 new slab columns = LReLU(acc + bias), stored at the tile's token rows, + their row statistics.  A
+        //    thread holds a whole row (32 columns), so its (sum, sumsq) never leaves the thread; the 16 conversion warps never
+        //    stop for this.
+        const int quad = warp & 3;
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const int r_in_tile = quad * 32 + lane;
+        auto produce_stats = [&](int it) {
+            const int row = tile_of(it) * 128 + r_in_tile;
+            float rstd = 1.f, nrm = 0.f;                              // nrm = -mean * rstd
+            if (row < p.M) {
+                const float2* sp = p.stats_in + static_cast<long long>(row) * p.stats_in_stride;
+                float s1 = 0.f, s2 = 0.f;
+                for (int k = 0; k < p.stats_in_slots; ++k) {
+                    const float2 v = __ldg(sp + k);
+                    s1 += v.x;
+                    s2 += v.y;
+                }
+                const float mean = s1 * p.inv_c;
+                rstd = rsqrtf(fmaxf(s2 * p.inv_c - mean * mean, 0.f) + p.ln_eps);
+                nrm = -mean * rstd;
+            }
+            mbar_wait(&bars->rs_free[it & 1], (static_cast<uint32_t>(it >> 1) & 1) ^ 1);
+            s_rowstat[(it & 1) * 128 + r_in_tile] = f2(rstd, nrm);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->rs_full[it & 1]);
+        };
+        if (my_tiles > 0) produce_stats(0);
+        if (my_tiles > 1) produce_stats(1);
+        for (int it = 0; it < my_tiles; ++it) {
+            if (it + 2 < my_tiles) produce_stats(it + 2);             // its buffer was released when tile it started
+            if (!p.fuse_adj) continue;
+            const int row = tile_of(it) * 128 + r_in_tile;
+            mbar_wait(&bars->acc2_full, static_cast<uint32_t>(it) & 1);
+            tc_fence_after_sync();
+            uint32_t raw[32];
+            tmem_ld16(tmem + lane_off + static_cast<uint32_t>(p.piece_col[0]), *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+            tmem_ld16(tmem + lane_off + static_cast<uint32_t>(p.piece_col[0] + 16), *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+            tmem_ld_wait();
+            tc_fence_before_sync();                                   // the next tile's MMAs may overwrite the accumulator
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc2_free);
+            float st = 0.f, sq = 0.f;
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float2 bb = *reinterpret_cast<const float2*>(s_bias2 + 2 * e);
+                float v0 = __uint_as_float(raw[2 * e]) + bb.x;
+                float v1 = __uint_as_float(raw[2 * e + 1]) + bb.y;
+                v0 = v0 > 0.f ? v0 : v0 * p.adj_slope;
+                v1 = v1 > 0.f ? v1 : v1 * p.adj_slope;
+                st += v0 + v1;
+                sq = fmaf(v0, v0, fmaf(v1, v1, sq));
+                pk[e] = pack_bf16x2(v0, v1);
+            }
+            // Row-per-thread stores of the slice (8-byte pieces at a 640-byte pitch: 32 sectors per instruction) cost the conversion
+            // warps ~10 % -- they share the load/store path (A/B with the stores removed).  The slice starts at column C_k, which
+            // is 8 but not 16 bytes aligned, so a TMA box cannot take it; the rows are transposed through a (swizzled) staging box
+            // instead and leave as 64 contiguous bytes per 8 lanes.
+            __syncwarp();                                             // the previous tile's box has been read out
+            const uint32_t sbox = smem_u32(adj_stage + quad * 2048);
+            {
+                const uint32_t srow = sbox + static_cast<uint32_t>(lane * 64);
+                const uint32_t sw = static_cast<uint32_t>(lane >> 1) & 3u;
+#pragma unroll
+                for (uint32_t c = 0; c < 4; ++c)
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((c ^ sw) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                                 "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                                 : "memory");
+            }
+            __syncwarp();
+            {
+                const uint32_t q = static_cast<uint32_t>(lane) & 7u;  // 8-byte piece of the row
+                const int row0 = tile_of(it) * 128 + quad * 32;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t r = static_cast<uint32_t>(4 * k + (lane >> 3));
+                    uint32_t v0, v1;
+                    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];"
+                                 : "=r"(v0), "=r"(v1)
+                                 : "r"(sbox + r * 64u + (((q >> 1) ^ ((r >> 1) & 3u)) << 4) + ((q & 1u) << 3)));
+                    if (row0 + static_cast<int>(r) < p.M)
+                        *reinterpret_cast<uint2*>(p.adj_out + static_cast<long long>(row0 + static_cast<int>(r)) * p.ld_adj + p.adj_col0 + 4 * q) =
+                            make_uint2(v0, v1);
+                }
+            }
+            if (row < p.M && p.adj_stats != nullptr) {
+                float2* so = p.adj_stats + static_cast<long long>(row) * p.adj_stats_stride + p.adj_stats_slot0;
+                if (p.adj_stats_vec4) {
+                    *reinterpret_cast<float4*>(so) = make_float4(st, sq, 0.f, 0.f);
+                } else {
+                    so[0] = f2(st, sq);
+                    so[1] = f2(0.f, 0.f);
+                }
+            }
+        }
     }
 
     tc_fence_before_sync();
@@ -604,15 +623,17 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
         if (p.hcw[j] <= 0 || p.hcw[j] > p.hc || p.hcw[j] > 128 || (p.hcw[j] % 16) != 0 || p.hcw[j] * 128 > p.w1_slot_bytes)
             return ADSR_ERR_BAD_SHAPE;
     p.a_buf_bytes = p.ks1 * kPanelBytes;
+    p.inv_c = 1.0f / static_cast<float>(p.C);
     if (p.fuse_adj) {
-        if (p.wadj == nullptr || p.bias_adj == nullptr || p.adj_out == nullptr || (p.adj_col0 % 4) || (p.ld_adj % 4) || p.adj_tcol % 16 ||
-            p.adj_tcol + 32 > 512 || (reinterpret_cast<uintptr_t>(p.wadj) & 15) || (reinterpret_cast<uintptr_t>(p.adj_out) & 7))
+        if (p.wadj == nullptr || p.bias_adj == nullptr || p.adj_out == nullptr || (p.adj_col0 % 4) || (p.ld_adj % 4) ||
+            (reinterpret_cast<uintptr_t>(p.wadj) & 15) || (reinterpret_cast<uintptr_t>(p.adj_out) & 7))
             return ADSR_ERR_BAD_SHAPE;
-        if (p.fuse_adj == 2 ? (p.n2 != 32 || p.n_pieces != 1 || p.adj_tcol != 0) : (p.adj_tcol < p.acc1_col[1] + p.hc)) return ADSR_ERR_BAD_SHAPE;
+        if (p.n2 != 32 || p.n_pieces != 1) return ADSR_ERR_BAD_SHAPE;       // the accumulator IS the 32 adjust columns
         if (p.adj_stats != nullptr && p.adj_stats_slot0 + 2 > p.adj_stats_stride) return ADSR_ERR_BAD_SHAPE;
+        p.adj_stats_vec4 = ((p.adj_stats_slot0 | p.adj_stats_stride) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.adj_stats) & 15) == 0;
     }
-    const int smem_bytes = 2 * p.a_buf_bytes + p.w1_slots * p.w1_slot_bytes + p.w2_slots * p.w2_slot_bytes + kConstBytes +
-                           (p.fuse_adj ? p.ks1 * kAdjSlabBytes + 2 * 128 * 8 : 0) + static_cast<int>(sizeof(MlpBarriers));
+    const int smem_bytes = 2 * p.a_buf_bytes + p.w1_slots * p.w1_slot_bytes + p.w2_slots * p.w2_slot_bytes + const_bytes(p.nc * p.hc, p.n2) +
+                           (p.fuse_adj ? p.ks1 * kAdjSlabBytes + kAdjStageBytes : 0) + static_cast<int>(sizeof(MlpBarriers));
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
     if ((reinterpret_cast<uintptr_t>(y) & 15) || (!p.fuse_adj && ((reinterpret_cast<uintptr_t>(z) & 15) || (ldz % 8))) || (ldy % 8) ||
         (reinterpret_cast<uintptr_t>(p.w1p) & 15) || (reinterpret_cast<uintptr_t>(p.w2p) & 15))
@@ -632,6 +653,6 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
     return p.trace != nullptr ? launch(swin_mlp_kernel<true>) : launch(swin_mlp_kernel<false>);
 }
 
-int swin_mlp_fixed_smem_bytes() { return kConstBytes + static_cast<int>(sizeof(MlpBarriers)); }
+int swin_mlp_fixed_smem_bytes(int hidden_padded, int n2) { return const_bytes(hidden_padded, n2) + static_cast<int>(sizeof(MlpBarriers)); }
 
 }  // namespace adsr

@@ -186,7 +186,9 @@ def pack_proj_weight(weight: torch.Tensor, bias: Optional[torch.Tensor], heads: 
 
 # ------------------------------------------------------------------------------------------------ fused Swin MLP
 _SMEM_LIMIT = 232448            # 227 KB of shared memory per CTA
-_MLP_FIXED_BYTES = (2 * 640 + 320) * 4 + 512   # bias1 / colsum1 / bias2 caches + barriers (swin_mlp.cu)
+def _mlp_fixed_bytes(hidden_padded: int, n2: int) -> int:
+    """bias1 / colsum1 / bias2 caches + row statistics of two tiles + barriers (swin_mlp.cu)."""
+    return (2 * hidden_padded + n2) * 4 + 2048 + 512
 
 
 @dataclass
@@ -207,33 +209,39 @@ class PackedMlp:
 _ADJ_N = 32                     # output channels of the fusable adjust convs (gc of the RDG)
 
 
-def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False, fold_adj: bool = False) -> dict:
+def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
     """Static tiling of one fused MLP (swin_mlp.cu): hidden chunks of <= 128 columns (two fp32 chunk accumulators plus the
     fc2 accumulator must fit the 512 TMEM columns), the fc2 output issued in two pieces of >= 128 rows when it is wider
     than 255, and the shared memory left after the two y-tile buffers split between the fc1 and fc2 weight rings."""
-    # fold_adj: the adjust conv is folded INTO fc2 (W_adj W2, 32 rows), so the "fc2" accumulator is the 32 adjust columns
-    n2 = _ADJ_N if fold_adj else round_up(c, 16)
+    # fuse_adj: the adjust conv is folded INTO fc2 (W_adj W2, 32 rows), so the "fc2" accumulator is the 32 adjust columns
+    n2 = _ADJ_N if fuse_adj else round_up(c, 16)
     k1steps = (c + 15) // 16
     ks1 = (c + 63) // 64
-    # TMEM: fc2 accumulator (n2) + two fc1 chunk accumulators (2 hc) [+ 32 columns of the fused adjust accumulator]
-    hc_max = min(128, ((512 - n2 - (_ADJ_N if fuse_adj and not fold_adj else 0)) // 2) // 16 * 16)
-    nc = (h + hc_max - 1) // hc_max
-    hc = round_up((h + nc - 1) // nc, 16)
-    widths = [hc] * (nc - 1) + [round_up(h - hc * (nc - 1), 16)]
-    s1 = round_up(hc * 128, 1024)
-    avail = _SMEM_LIMIT - 2 * ks1 * 16384 - _MLP_FIXED_BYTES - ((ks1 * _ADJ_N * 128 + 2048) if fuse_adj else 0)
-    # the fc2 N dimension goes out in one piece, or in two when it is wider than 255 -- or when one-piece ring slots would not
-    # leave room for two slots per ring (fused adjust takes shared memory for its resident weights)
-    if n2 >= 256 or avail < 2 * s1 + 2 * round_up(n2 * 128, 1024):
-        p0 = round_up(n2 // 2, 16)
-        pieces = [p0, n2 - p0]
-    else:
-        pieces = [n2]
-    s2 = round_up(max(pieces) * 128, 1024)
-    # bytes per tile through each ring decide how the slots are shared out (at least 2 each)
-    n1, n2s = 2, 2
-    if avail < n1 * s1 + n2s * s2 or nc > 8 or n2 > 320 or nc * hc > 640 or (fold_adj and not fuse_adj):
+    # TMEM: fc2 accumulator (n2) + two fc1 chunk accumulators (2 hc); narrower chunks when two fc1 ring slots would not fit
+    hc_max = min(128, ((512 - n2) // 2) // 16 * 16)
+    while True:
+        nc = (h + hc_max - 1) // hc_max
+        hc = round_up((h + nc - 1) // nc, 16)
+        widths = [hc] * (nc - 1) + [round_up(h - hc * (nc - 1), 16)]
+        s1 = round_up(hc * 128, 1024)
+        avail = _SMEM_LIMIT - 2 * ks1 * 16384 - _mlp_fixed_bytes(nc * hc, n2) - ((ks1 * _ADJ_N * 128 + 8192) if fuse_adj else 0)
+        # the fc2 N dimension goes out in one piece, or in two when it is wider than 255 -- or when one-piece ring slots would
+        # not leave room for two slots per ring
+        if n2 >= 256 or (avail < 2 * s1 + 2 * round_up(n2 * 128, 1024) and n2 >= 64):
+            p0 = round_up(n2 // 2, 16)
+            pieces = [p0, n2 - p0]
+        else:
+            pieces = [n2]
+        s2 = round_up(max(pieces) * 128, 1024)
+        n1, n2s = 2, 2
+        if avail >= n1 * s1 + n2s * s2 or hc_max <= 48:
+            break
+        hc_max -= 16
+    if avail < n1 * s1 + n2s * s2 or nc > 8 or n2 > 320 or nc * hc > 640:
         raise ValueError(f"fused MLP does not fit: C={c} H={h}")
+    # bytes per tile through each ring decide how the slots are shared out (at least 2 each); the 4 KB slabs of a folded adjust
+    # need no more than one chunk's worth in flight
+    n2s_max = 4 if fuse_adj else 8
     while True:
         grew = False
         for which in ((1, 2) if n1 * s1 <= n2s * s2 else (2, 1)):
@@ -241,14 +249,14 @@ def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False, fold_adj: bool = False
                 n1 += 1
                 grew = True
                 break
-            if which == 2 and n2s < 8 and avail >= n1 * s1 + (n2s + 1) * s2:
+            if which == 2 and n2s < n2s_max and avail >= n1 * s1 + (n2s + 1) * s2:
                 n2s += 1
                 grew = True
                 break
         if not grew:
             break
     return dict(ks1=ks1, k1steps=k1steps, nc=nc, hc=hc, n2=n2, widths=widths, pieces=pieces, w1_slots=n1, w1_slot_bytes=s1,
-                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(n2, n2 + hc), adj_tcol=0 if fold_adj else n2 + 2 * hc, fold=int(fold_adj))
+                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(n2, n2 + hc), adj_tcol=0, fold=int(fuse_adj))
 
 
 def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
@@ -269,10 +277,7 @@ def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
 
 # W_adj (y + fc2(g)) = y W_adj^T + g (W_adj W2)^T: fc2 and the adjust conv have nothing non-linear between them, and z itself is
 # never needed when the adjust conv is fused -- so its 32 rows replace fc2's C rows (6-10x fewer fc2 MMAs, no residual epilogue).
-_FOLD_ADJUST = os.environ.get("ADSR_FOLD_ADJUST", "1") != "0"
-
-
-def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, adjust_w=None, adjust_b=None, fold_adjust=None) -> PackedMlp:
+def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, adjust_w=None, adjust_b=None) -> PackedMlp:
     """norm2 + fc1 + GELU + fc2 of one Swin block (src/drct.py:438-441, 173-190) for adsr_swin_mlp_bf16: gamma folded into
     fc1 (pack_ln_gemm_weight's algebra), the 0.5 of GELU folded into fc2 (exact in bf16).  With adjust_w [32, C(,1,1)] the
     RDG's adjust 1x1 conv is packed along for adsr_swin_mlp_adjust_bf16 (raises ValueError if the tiling does not fit)."""
@@ -283,11 +288,9 @@ def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, adjust_w=None, a
     fuse_adj = adjust_w is not None
     if fuse_adj and adjust_w.shape[0] != _ADJ_N:
         raise ValueError("only 32-channel adjust convs can be fused")
-    fold = fuse_adj and (_FOLD_ADJUST if fold_adjust is None else bool(fold_adjust))
+    fold = fuse_adj
     wa32 = adjust_w.detach().float().reshape(_ADJ_N, -1) if fuse_adj else None
-    pl = swin_mlp_plan(c, h, fuse_adj, fold)
-    if fuse_adj and pl["adj_tcol"] + _ADJ_N > 512:
-        raise ValueError(f"fused adjust does not fit the tensor memory: C={c} H={h}")
+    pl = swin_mlp_plan(c, h, fuse_adj)
     hc, nc, n2, ks1 = pl["hc"], pl["nc"], pl["n2"], pl["ks1"]
     w1g = torch.zeros(nc * hc, ks1 * 64, device=dev)
     w1g[:h, :c] = w1 * gamma.detach().float()[None, :]

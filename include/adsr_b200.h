@@ -80,13 +80,15 @@ int adsr_swin_mlp_bf16(const void* y, int64_t ldy, int M, int C,
                        const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
                        void* z, int64_t ldz, int reverse_tiles, int num_sms, void* stream);
 
-/* Same kernel with the adjust 1x1 conv of the RDG fused in (src/drct.py:389-393: x_k = LReLU_0.2(adjust_k(swin_k(...))) appended to
+/* Same kernel with the adjust 1x1 conv of the RDG folded in (src/drct.py:389-393: x_k = LReLU_0.2(adjust_k(swin_k(...))) appended to
  * the dense feature slab): out[:, ocol0 + n] = LReLU(z W_adj^T + b_adj)[n] for the 32 new channels, where z is the MLP result above.
- * z itself is NOT written (nothing else reads it).  wadj_packed / bias_adj and the extended plan (..., adj_tmem_col, fold) come
- * from pack.pack_swin_mlp(..., adjust_w, adjust_b).  With fold != 0 the pack carries the adjust conv folded INTO fc2 --
- * W_adj (y + W2 g + b2) = y W_adj^T + g (W_adj W2)^T + (b_adj + W_adj b2): w2_packed holds the 32 rows of W_adj W2, n2 = 32,
- * the accumulator starts as y W_adj^T and there is no residual pass at all.  stats_out receives the per-row (sum, sumsq) of the 32 new columns in slot
- * stats_out_slot0 (slot0 + 1 is zeroed), for the LayerNorm folds of the following blocks. */
+ * fc2 and the conv have nothing non-linear between them and nothing else reads z, so the conv is folded INTO fc2:
+ *   W_adj (y + W2 g + b2) = y W_adj^T + g (W_adj W2)^T + (b_adj + W_adj b2)
+ * -- w2_packed holds the 32 rows of W_adj W2 (n2 = 32), the accumulator starts as y W_adj^T (wadj_packed, resident in shared
+ * memory), bias_adj is the combined bias, and there is no z and no residual pass.  All of it comes from
+ * pack.pack_swin_mlp(..., adjust_w, adjust_b), whose plan is extended by (0, 1): plan[23] != 0 marks the folded layout (plan_len
+ * >= 24 is required here, and adsr_swin_mlp_bf16 rejects such a pack).  stats_out receives the per-row (sum, sumsq) of the 32 new
+ * columns in slot stats_out_slot0 (slot0 + 1 is zeroed), for the LayerNorm folds of the following blocks. */
 int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int C,
                               const void* w1_packed, const void* w2_packed,
                               const float* bias1, const float* colsum1, const float* bias2,

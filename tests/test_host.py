@@ -132,45 +132,33 @@ def test_pack_swin_attn_layout():
 
 
 def test_swin_mlp_plans_fit_the_sm():
-    """Static tilings of the fused MLP (with and without the fused adjust conv) for the DRCT-L widths: TMEM columns, shared
-    memory and chunk widths stay inside the limits the kernel checks."""
+    """Static tilings of the fused MLP (plain, and with the adjust conv folded into fc2) for the DRCT-L widths: TMEM columns,
+    shared memory and chunk widths stay inside the limits the kernel checks."""
     pack = importlib.import_module(PKG + ".pack")
-    for c, h, fuse_ok in [(180, 360, True), (212, 424, True), (244, 488, True), (276, 276, False), (308, 308, False)]:
+    for c, h in [(180, 360), (212, 424), (244, 488), (276, 276), (308, 308)]:
         for fuse in (False, True):
-            try:
-                pl = pack.swin_mlp_plan(c, h, fuse)
-            except ValueError:
-                assert fuse and not fuse_ok, (c, h, fuse)
-                continue
-            assert not fuse or fuse_ok
+            pl = pack.swin_mlp_plan(c, h, fuse)
             n2, hc, nc = pl["n2"], pl["hc"], pl["nc"]
-            assert n2 == (c + 15) // 16 * 16 and sum(pl["widths"]) >= h and all(w % 16 == 0 and w <= hc for w in pl["widths"])
-            assert n2 + 2 * hc + (32 if fuse else 0) <= 512 and pl["adj_tcol"] == n2 + 2 * hc
+            assert n2 == (32 if fuse else (c + 15) // 16 * 16) and pl["fold"] == int(fuse) and pl["acc1_col"] == (n2, n2 + hc)
+            assert sum(pl["widths"]) >= h and all(w % 16 == 0 and w <= hc for w in pl["widths"]) and n2 + 2 * hc <= 512
             assert sum(pl["pieces"]) == n2 and all(16 <= r <= 256 and r % 16 == 0 for r in pl["pieces"])
+            assert not fuse or (pl["pieces"] == [32] and pl["w2_slot_bytes"] == 4096)
             smem = 2 * pl["ks1"] * 16384 + pl["w1_slots"] * pl["w1_slot_bytes"] + pl["w2_slots"] * pl["w2_slot_bytes"] + \
-                pack._MLP_FIXED_BYTES + ((pl["ks1"] * 4096 + 2048) if fuse else 0)
+                pack._mlp_fixed_bytes(nc * hc, n2) + ((pl["ks1"] * 4096 + 8192) if fuse else 0)
             assert smem <= 232448 and pl["w1_slots"] >= 2 and pl["w2_slots"] >= 2 and nc * hc <= 640
-    pm = pack.pack_swin_mlp(torch.randn(360, 180), torch.randn(360), torch.ones(180), torch.zeros(180), 1e-5, torch.randn(180, 360),
-                            torch.randn(180), torch.randn(32, 180, 1, 1), torch.randn(32))
-    assert pm.wadj.numel() == 3 * 32 * 128 and pm.bias_adj.numel() == 32 and pm.plan.numel() == 24
 
 
 def test_swin_mlp_folded_adjust_pack():
-    """Folded adjust (W_adj W2 as the fc2 weights): fits every DRCT-L width with a 32-column accumulator, and the packed slabs and
-    bias are the products they should be."""
+    """Adjust conv folded into fc2 (W_adj W2 as the fc2 weights): the packed slabs and the bias are the products they should be."""
     pack = importlib.import_module(PKG + ".pack")
-    for c, h in [(180, 360), (212, 424), (244, 488), (276, 276), (308, 308)]:
-        pl = pack.swin_mlp_plan(c, h, True, True)
-        assert pl["n2"] == 32 and pl["pieces"] == [32] and pl["adj_tcol"] == 0 and pl["fold"] == 1 and pl["acc1_col"][0] == 32
-        assert 32 + 2 * pl["hc"] <= 512 and pl["w2_slot_bytes"] == 4096
-        smem = 2 * pl["ks1"] * 16384 + pl["w1_slots"] * pl["w1_slot_bytes"] + pl["w2_slots"] * 4096 + pack._MLP_FIXED_BYTES + pl["ks1"] * 4096 + 2048
-        assert smem <= 232448
     torch.manual_seed(3)
     w2, b2, wa, ba = torch.randn(180, 360), torch.randn(180), torch.randn(32, 180, 1, 1), torch.randn(32)
-    args = (torch.randn(360, 180), torch.randn(360), torch.ones(180), torch.zeros(180), 1e-5, w2, b2, wa, ba)
-    pm, pm0 = pack.pack_swin_mlp(*args, fold_adjust=True), pack.pack_swin_mlp(*args, fold_adjust=False)
-    assert pm.plan.tolist()[4] == 32 and pm.plan.tolist()[23] == 1 and pm0.plan.tolist()[23] == 0 and pm0.plan.tolist()[4] == 192
-    assert torch.allclose(pm.bias_adj, ba + wa.view(32, 180) @ b2, atol=1e-4) and torch.equal(pm0.bias_adj, ba)
+    args = (torch.randn(360, 180), torch.randn(360), torch.ones(180), torch.zeros(180), 1e-5, w2, b2)
+    pm, pm0 = pack.pack_swin_mlp(*args, wa, ba), pack.pack_swin_mlp(*args)
+    assert pm.plan.numel() == 24 and pm.plan.tolist()[4] == 32 and pm.plan.tolist()[23] == 1
+    assert pm0.plan.tolist()[23] == 0 and pm0.plan.tolist()[4] == 192 and pm0.wadj is None
+    assert pm.wadj.numel() == 3 * 32 * 128 and pm.bias_adj.numel() == 32
+    assert torch.allclose(pm.bias_adj, ba + wa.view(32, 180) @ b2, atol=1e-4)
     wf = (wa.view(32, 180).double() @ (0.5 * w2).double()).float().to(torch.bfloat16)
     img = pm.w2.view(torch.bfloat16).view(-1, 32, 8, 8)           # slabs of [32 rows x 64 hidden columns], (chunk, K slab) order
     nc, hc = pm.plan.tolist()[2], pm.plan.tolist()[3]

@@ -36,18 +36,11 @@ for (C, H) in shapes:
     margs = (torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
              torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev), wa, ba)
     slab = torch.zeros(M, 320, device=dev, dtype=torch.bfloat16); st_s = torch.zeros(M, 12, 2, device=dev)
-    if hasattr(pack, "_FOLD_ADJUST"):
-        pmf = pack.pack_swin_mlp(*margs, fold_adjust=True)
-        bfo, afo = timeit(lambda: ops.swin_mlp_adjust(y, C, pmf, slab, C, stats_in=(stats, 2), stats_out=(st_s, 2)))
-        print(f"   + adjust FOLDED into fc2: {bfo*1e3:8.1f} us (avg {afo*1e3:8.1f})   plan {pmf.plan.tolist()[:14]}")
-    try:
-        pma = pack.pack_swin_mlp(*margs, fold_adjust=False) if hasattr(pack, "_FOLD_ADJUST") else pack.pack_swin_mlp(*margs)
-    except ValueError:
-        continue
+    pma = pack.pack_swin_mlp(*margs)
     padj = pack.pack_gemm_weight(wa, ba)
     bf, af = timeit(lambda: ops.swin_mlp_adjust(y, C, pma, slab, C, stats_in=(stats, 2), stats_out=(st_s, 2)))
     def sep():
         ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2))
         ops.tc_gemm(z, C, padj, slab, act=ops.ACT_LRELU, slope=0.2, ocol0=C, n_store=32, stats_out=(st_s, 2))
     bs, _ = timeit(sep)
-    print(f"   + adjust: fused {bf*1e3:8.1f} us (avg {af*1e3:8.1f})   separate MLP + adjust GEMM {bs*1e3:8.1f} us   plan {pma.plan.tolist()[:14]}")
+    print(f"   + adjust folded into fc2: {bf*1e3:8.1f} us (avg {af*1e3:8.1f})   separate MLP + adjust GEMM {bs*1e3:8.1f} us   plan {pma.plan.tolist()[:14]}")

@@ -9,13 +9,21 @@ M = int(os.environ.get("M", 262144)); C = int(os.environ.get("C", 180)); H = int
 y = torch.randn(M, 320, device=dev).to(torch.bfloat16); z = torch.empty_like(y)
 pm = pack.pack_swin_mlp(torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
                         torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev))
+FOLD = os.environ.get("FOLD")            # FOLD=1: the folded-adjust variant (swin_mlp_adjust), unset: plain MLP
+if FOLD is not None:
+    pm = pack.pack_swin_mlp(torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
+                            torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev),
+                            torch.randn(32, C, device=dev) * 0.05, torch.randn(32, device=dev))
+    slab = torch.zeros(M, 320, device=dev, dtype=torch.bfloat16); st_s = torch.zeros(M, 12, 2, device=dev)
 stats = torch.zeros(M, 2, 2, device=dev)
 yf = y[:, :C].float(); stats[:, 0, 0] = yf.sum(1); stats[:, 0, 1] = (yf * yf).sum(1)
-ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2)); torch.cuda.synchronize()
+run = (lambda: ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2))) if FOLD is None else \
+    (lambda: ops.swin_mlp_adjust(y, C, pm, slab, C, stats_in=(stats, 2), stats_out=(st_s, 2)))
+run(); torch.cuda.synchronize()
 trace = torch.zeros(4, 8, 64, 8, dtype=torch.int64, device=dev)
 fn = abi.lib().adsr_debug_set_mlp_trace; fn.restype = None; fn.argtypes = [ctypes.c_void_p]
 fn(trace.data_ptr())
-ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2)); torch.cuda.synchronize()
+run(); torch.cuda.synchronize()
 fn(None)
 t = trace.cpu()
 t0 = int(t[t > 0].min())
@@ -28,6 +36,8 @@ for it in range(1, 5):
     for j in range(nc):
         print(f" fc1 ch{j}: start {rel(t[1,it,j,0]):7d} acc1_free {rel(t[1,it,j,1]):7d} issued {rel(t[1,it,j,2]):7d}"
               f" | epi1: wait {rel(t[2,it,j,0]):7d} acc_ok {rel(t[2,it,j,1]):7d} slab0 {rel(t[2,it,j,2]):7d} slab1 {rel(t[2,it,j,3]):7d}")
+        print("   epi1 detail (ld issue, ld done, math done, st done) x 2 slabs: " + " ".join(f"{rel(t[2,it,32+j,k]):7d}" for k in range(8)))
         for s in range(2):
             print(f"   fc2 ch{j} slab{s}: start {rel(t[3,it,2*j+s,0]):7d} h_ok {rel(t[3,it,2*j+s,1]):7d} issued {rel(t[3,it,2*j+s,2]):7d}")
+    print(f" epi3 (adjust columns): wait {rel(t[2,it,17,0]):7d} acc_ok {rel(t[2,it,17,1]):7d} done {rel(t[2,it,17,2]):7d}")
     print(f" epi2: wait {rel(t[2,it,16,0]):7d} acc2_ok {rel(t[2,it,16,1]):7d} done {rel(t[2,it,16,2]):7d}")
