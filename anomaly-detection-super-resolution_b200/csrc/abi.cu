@@ -233,6 +233,8 @@ extern "C" int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int 
 static long long* g_attn_trace = nullptr;
 extern "C" void adsr_debug_set_attn_trace(void* device_buffer) { g_attn_trace = static_cast<long long*>(device_buffer); }
 
+extern "C" void adsr_debug_set_mlp_acc1(int max_buffers) { g_mlp_acc1_max = max_buffers; }
+
 static int g_swin_attn2 = 1;
 extern "C" void adsr_debug_set_swin_attn2(int enabled) { g_swin_attn2 = enabled; }
 

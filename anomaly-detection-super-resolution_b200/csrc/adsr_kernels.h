@@ -115,7 +115,8 @@ struct SwinMlpParams {
     int n2;               // fc2 accumulator columns (C rounded up to 16)
     int n_pieces;         // the fc2 N dimension is issued in 1 or 2 pieces (each <= 256 rows)
     int piece_rows[2], piece_col[2];
-    int acc1_col[2];
+    int acc1_col[3];      // TMEM columns of the fc1 chunk accumulators ([2] = [1] + hc, used when n_acc1 == 3)
+    int n_acc1;           // 2 or 3 (set by the launcher)
     int w1_slots, w1_slot_bytes, w2_slots, w2_slot_bytes, a_buf_bytes;
     long long* trace;     // optional [4 roles][8 tiles][64][8] clock64 timeline of CTA 0 (tools/mlp_trace.py), else nullptr
     // optional adjust 1x1 conv (src/drct.py:389-393) FOLDED into fc2: adj_out[:, adj_col0 + n] = LReLU(z W_adj^T + b)[n], n < 32, computed
@@ -133,6 +134,7 @@ struct SwinMlpParams {
     int adj_stats_vec4;   // the two slots of a row form one aligned 16-byte store (set by the launcher)
 };
 int swin_mlp_fixed_smem_bytes(int hidden_padded, int n2);
+extern int g_mlp_acc1_max;
 int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, long long ldz, int num_sms, cudaStream_t stream);
 
 // ---- fused attention half of a Swin block (swin_attn.cu)

@@ -21,6 +21,8 @@
 
 namespace adsr {
 
+int g_mlp_acc1_max = 3;                        // debug switch (adsr_debug_set_mlp_acc1): 2 = never use a third chunk accumulator
+
 namespace {
 
 constexpr int kEpiWarps = 16;                 // warps 0..15: epilogue (TMEM lane quadrant = warp % 4)
@@ -28,9 +30,9 @@ constexpr int kW1LoaderWarp = 16;             // fc1 weight slabs
 constexpr int kFc1Warp = 17;                  // fc1 MMA issuer
 constexpr int kFc2Warp = 18;                  // fc2 MMA issuer
 constexpr int kW2LoaderWarp = 19;             // fc2 weight slabs
-constexpr int kTileWarp = 20;                 // TMEM alloc, y-tile loads, z-tile stores
-constexpr int kAuxWarp0 = 21;                 // warps 21..24 (TMEM lane quadrant = warp % 4): row mean / rstd two tiles ahead, folded-adjust epilogue
-constexpr int kThreads = 25 * 32;
+constexpr int kTileWarp = 20;                 // the first aux warp also does: TMEM alloc, y-tile loads, z-tile stores
+constexpr int kAuxWarp0 = 20;                 // warps 20..23 (TMEM lane quadrant = warp % 4): row mean / rstd two tiles ahead, folded-adjust epilogue
+constexpr int kThreads = 24 * 32;             // 24 warps: 80 registers per thread (a 25th warp costs 8 of them to the allocation granularity)
 constexpr int kPanelBytes = 128 * 128;        // 128 rows x 64 bf16
 constexpr int kMaxHidden = 640;               // padded hidden columns (sum of chunk strides)
 constexpr int kMaxN2 = 320;
@@ -46,11 +48,11 @@ struct __align__(16) MlpBarriers {
     uint64_t w2_full[8], w2_empty[8];
     uint64_t a_full[2];
     uint64_t z_ready[2];
-    uint64_t acc1_full[2];
-    uint64_t acc1_free[2];
-    uint64_t h_ready[2][2];                   // [accumulator buffer][64-column slab of the chunk]
-    uint64_t acc2_full;
-    uint64_t acc2_free;
+    uint64_t acc1_full[3];
+    uint64_t acc1_free[3];
+    uint64_t h_ready[3][2];                   // [accumulator buffer][64-column slab of the chunk]
+    uint64_t acc2_full[2];                    // [1] only with the folded adjust, whose 32-column accumulator is double-buffered
+    uint64_t acc2_free[2];
     uint64_t adj_w_full;                      // folded adjust: the resident W_adj slabs have landed
     uint64_t adj_done[2];                     // folded adjust: fc1 and the y W_adj^T MMAs have finished reading the y tile in buffer b
     uint64_t rs_full[2], rs_free[2];          // (rstd, -mean * rstd) of a tile's rows in s_rowstat[tile parity]
@@ -101,6 +103,13 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // fc1 chunk accumulators: two, or three where the TMEM columns allow (folded adjust: fc1 then runs two chunks ahead of the
+    // conversion, so a chunk never waits for the fc2 of the chunk two before it)
+    // fc2 accumulator of tile it: one, or (folded adjust: 32 columns) two so that the next tile's MMAs never wait for the aux warps
+    auto acc2_buf = [&](int it) -> int { return p.fuse_adj ? it & 1 : 0; };
+    auto acc2_phase = [&](int it) -> uint32_t { return static_cast<uint32_t>(p.fuse_adj ? it >> 1 : it) & 1u; };
+    auto acc1_buf = [&](int cg) -> int { return p.n_acc1 == 3 ? cg % 3 : cg & 1; };
+    auto acc1_phase = [&](int cg) -> uint32_t { return static_cast<uint32_t>(p.n_acc1 == 3 ? cg / 3 : cg >> 1) & 1u; };
     const int my_tiles = static_cast<int>(blockIdx.x) < p.m_tiles ? (p.m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto tile_of = [&](int it) -> int {                                // forward, or from the last tile down (p.rev)
         const int t = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
@@ -126,15 +135,19 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->a_full[b], 1);
             mbar_init(&bars->z_ready[b], kEpiWarps);
+            mbar_init(&bars->rs_full[b], 4);
+            mbar_init(&bars->rs_free[b], kEpiWarps);
+        }
+        for (int b = 0; b < 3; ++b) {
             mbar_init(&bars->acc1_full[b], 1);
             mbar_init(&bars->acc1_free[b], 1);
             mbar_init(&bars->h_ready[b][0], kEpiWarps);
             mbar_init(&bars->h_ready[b][1], kEpiWarps);
-            mbar_init(&bars->rs_full[b], 4);
-            mbar_init(&bars->rs_free[b], kEpiWarps);
         }
-        mbar_init(&bars->acc2_full, 1);
-        mbar_init(&bars->acc2_free, p.fuse_adj ? 4 : kEpiWarps);      // folded adjust: its own four warps read the accumulator
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->acc2_full[b], 1);
+            mbar_init(&bars->acc2_free[b], p.fuse_adj ? 4 : kEpiWarps);   // folded adjust: its own four warps read the accumulator
+        }
         mbar_init(&bars->adj_w_full, 1);
         // folded adjust: the tile buffer is free once BOTH its fc1 MMAs and its y W_adj^T MMAs (two issuing warps) have completed
         mbar_init(&bars->adj_done[0], 2);
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             }
         }
     } else if (warp == kFc1Warp) {
-        // ============================================================ fc1 MMA issuer: acc1[cg & 1] = y_tile . W1_chunk^T
+        // ============================================================ fc1 MMA issuer: acc1[cg % n_acc1] = y_tile . W1_chunk^T
         int slot = 0;
         uint32_t phase = 0;
         const uint32_t slot_units = static_cast<uint32_t>(p.w1_slot_bytes >> 4);
@@ -210,12 +223,12 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             trace_ev<TRACE>(p.trace, 0, it, 1, 1);
             const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((it & 1) * a_units);
             for (int j = 0; j < p.nc; ++j) {
-                const int cg = it * p.nc + j;                         // running chunk counter: buffer = cg & 1, use = cg >> 1
-                const int b = cg & 1;
+                const int cg = it * p.nc + j;                         // running chunk counter: buffer = cg % n_acc1, use = cg / n_acc1
+                const int b = acc1_buf(cg);
                 const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.hcw[j]));
                 const uint32_t acc1 = tmem + static_cast<uint32_t>(p.acc1_col[b]);
                 trace_ev<TRACE>(p.trace, 1, it, j, 0);
-                mbar_wait(&bars->acc1_free[b], (static_cast<uint32_t>(cg >> 1) & 1) ^ 1);   // fc2 of chunk cg-2 has consumed it
+                mbar_wait(&bars->acc1_free[b], acc1_phase(cg) ^ 1);   // fc2 of chunk cg - n_acc1 has consumed it
                 trace_ev<TRACE>(p.trace, 1, it, j, 1);
                 for (int s = 0; s < p.ks1; ++s) {
                     const int ksteps = min(4, p.k1steps - 4 * s);
@@ -257,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             tc_fence_after_sync();
             if (elect_one_sync()) {
                 const uint64_t a_desc = adj_a_desc0 + static_cast<uint64_t>((it & 1) * static_cast<uint32_t>(p.a_buf_bytes >> 4));
-                const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[0]);
+                const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[0] + 32 * acc2_buf(it));
                 for (int s = 0; s < p.ks1; ++s) {
                     const int ksteps = min(4, p.k1steps - 4 * s);
                     for (int j = 0; j < ksteps; ++j)
@@ -271,15 +284,17 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         for (int it = 0; it < my_tiles; ++it) {
             for (int j = 0; j < p.nc; ++j) {
                 const int cg = it * p.nc + j;
-                const int b = cg & 1;
+                const int b = acc1_buf(cg);
                 const int nslab = (p.hcw[j] + 63) >> 6;
                 const uint32_t acc1 = tmem + static_cast<uint32_t>(p.acc1_col[b]);
                 for (int s = 0; s < nslab; ++s) {
                     const int ksteps = min(4, (p.hcw[j] >> 4) - 4 * s);
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 0);
-                    mbar_wait(&bars->h_ready[b][s], static_cast<uint32_t>(cg >> 1) & 1);
+                    mbar_wait(&bars->h_ready[b][s], acc1_phase(cg));
                     if (j == 0 && s == 0) {
-                        mbar_wait(&bars->acc2_free, (static_cast<uint32_t>(it) & 1) ^ 1);
+                        trace_ev<TRACE>(p.trace, 3, it, 0, 3);
+                        mbar_wait(&bars->acc2_free[acc2_buf(it)], acc2_phase(it) ^ 1);
+                        trace_ev<TRACE>(p.trace, 3, it, 0, 4);
                         if (p.fuse_adj) issue_adj_y(it);                       // folded adjust: the accumulator starts as y W_adj^T
                     }
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 1);
@@ -287,8 +302,9 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                     const uint32_t first_acc = (j == 0 && s == 0 && !p.fuse_adj) ? 0u : 1u;
                     for (int pc = 0; pc < p.n_pieces; ++pc) {
                         const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.piece_rows[pc]));
-                        const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[pc]);
+                        const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[pc] + 32 * acc2_buf(it));
                         mbar_wait(&bars->w2_full[slot], phase);
+                        trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 5);
                         tc_fence_after_sync();
                         if (elect_one_sync()) {
                             const uint64_t bdesc = ring_desc + static_cast<uint64_t>(static_cast<uint32_t>(slot) * slot_units);
@@ -299,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                             umma_commit(&bars->w2_empty[slot]);
                             if (s == nslab - 1 && pc == p.n_pieces - 1) {
                                 umma_commit(&bars->acc1_free[b]);                  // chunk accumulator may be overwritten
-                                if (j == p.nc - 1) umma_commit(&bars->acc2_full);  // tile complete -> last epilogue
+                                if (j == p.nc - 1) umma_commit(&bars->acc2_full[acc2_buf(it)]);  // tile complete -> last epilogue
                             }
                         }
                         __syncwarp();
@@ -309,51 +325,6 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                 }
             }
         }
-    } else if (warp == kTileWarp) {
-        // ============================================================ y-tile loads / z-tile stores (same buffers)
-        auto load_a = [&](int it) {
-            const int ab = it & 1;
-            const int m0 = tile_of(it) * 128;
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&bars->a_full[ab], static_cast<uint32_t>(p.a_buf_bytes));
-                for (int pn = 0; pn < p.ks1; ++pn)
-                    tma_load_2d(a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, &p.tmap_y, pn * 64, m0, &bars->a_full[ab]);
-            }
-            __syncwarp();
-        };
-        if (lane == 0) tma_prefetch_desc(&p.tmap_y);
-        if (p.fuse_adj && lane == 0) {
-            mbar_arrive_expect_tx(&bars->adj_w_full, static_cast<uint32_t>(p.ks1 * kAdjSlabBytes));
-            bulk_g2s(wadj_s, p.wadj, static_cast<uint32_t>(p.ks1 * kAdjSlabBytes), &bars->adj_w_full);
-        }
-        if (my_tiles > 0) load_a(0);
-        if (my_tiles > 1) load_a(1);
-        for (int it = 0; it < my_tiles; ++it) {
-            const int ab = it & 1;
-            const int m0 = tile_of(it) * 128;
-            if (p.fuse_adj) {
-                // z only feeds the fused adjust conv: nothing is stored; the buffer is free once the adjust MMAs have read it
-                trace_ev<TRACE>(p.trace, 0, it, 0, 0);
-                mbar_wait(&bars->adj_done[ab], static_cast<uint32_t>(it >> 1) & 1);
-                trace_ev<TRACE>(p.trace, 0, it, 0, 2);
-            } else {
-                trace_ev<TRACE>(p.trace, 0, it, 0, 0);
-                mbar_wait(&bars->z_ready[ab], static_cast<uint32_t>(it >> 1) & 1);
-                trace_ev<TRACE>(p.trace, 0, it, 0, 1);
-                if (lane == 0) {        // bulk-group bookkeeping is per thread: the same lane stores and waits
-                    for (int pn = 0; pn < p.ks1; ++pn)
-                        tma_store_2d_box(&p.tmap_z, a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, pn * 64, m0);
-                    bulk_commit_group();
-                    bulk_wait_group_read0();
-                }
-                __syncwarp();
-                trace_ev<TRACE>(p.trace, 0, it, 0, 2);
-            }
-            if (it + 2 < my_tiles) load_a(it + 2);                    // the buffer is free again: fetch the tile after next
-            trace_ev<TRACE>(p.trace, 0, it, 0, 3);
-        }
-        if (lane == 0) bulk_wait_group0();
-        __syncwarp();
     } else if (warp < kEpiWarps) {
         // ============================================================ epilogue: 4 quadrants (TMEM lanes) x 4 column groups
         const int quad = warp & 3;
@@ -378,42 +349,41 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         // ---- one hidden chunk: TMEM fp32 -> LN fold + bias + GELU -> bf16 into the first 8 columns of each 16-column unit
         auto epi1 = [&](int it, int j, float rstd, float nrm) {
             const int cg = it * p.nc + j;
-            const int b = cg & 1;
+            const int b = acc1_buf(cg);
             const int units = p.hcw[j] >> 4;                          // K=16 steps of fc2 in this chunk
             const uint32_t taddr = tmem + static_cast<uint32_t>(p.acc1_col[b]) + lane_off;
             const float2 rstd2 = f2(rstd, rstd), nrm2 = f2(nrm, nrm);
             if (tr) trace_ev<TRACE>(p.trace, 2, it, j, 0);
-            mbar_wait(&bars->acc1_full[b], static_cast<uint32_t>(cg >> 1) & 1);
+            mbar_wait(&bars->acc1_full[b], acc1_phase(cg));
             tc_fence_after_sync();
             if (tr) trace_ev<TRACE>(p.trace, 2, it, j, 1);
+            // 16 accumulator columns -> 8 packed bf16x2 GELU activations
+            auto convert16 = [&](const uint32_t (&raw)[16], int u, uint32_t (&pk)[8]) {
+                const float* bp = s_bias1 + j * p.hc + 16 * u;
+                const float* cp = s_colsum1 + j * p.hc + 16 * u;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(bp + 4 * q4);
+                    const float4 cs = *reinterpret_cast<const float4*>(cp + 4 * q4);
+                    const float2 x0 = __ffma2_rn(rstd2, f2(__uint_as_float(raw[4 * q4]), __uint_as_float(raw[4 * q4 + 1])),
+                                                 __ffma2_rn(nrm2, f2(cs.x, cs.y), f2(bb.x, bb.y)));
+                    const float2 x1 = __ffma2_rn(rstd2, f2(__uint_as_float(raw[4 * q4 + 2]), __uint_as_float(raw[4 * q4 + 3])),
+                                                 __ffma2_rn(nrm2, f2(cs.z, cs.w), f2(bb.z, bb.w)));
+                    const float2 g0 = gelu2_pair(x0), g1 = gelu2_pair(x1);
+                    pk[2 * q4] = pack_bf16x2(g0.x, g0.y);
+                    pk[2 * q4 + 1] = pack_bf16x2(g1.x, g1.y);
+                }
+            };
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {                             // h = 64-column slab of the chunk
                 const int u = grp + 4 * h;
                 if (u < units) {
-                    uint32_t raw[16];
-                    if (tr) trace_ev<TRACE>(p.trace, 2, it, 32 + j, 4 * h);
+                    uint32_t raw[16], pk[8];
                     tmem_ld16(taddr + static_cast<uint32_t>(16 * u), raw);
                     tmem_ld_wait();
-                    if (tr) trace_ev<TRACE>(p.trace, 2, it, 32 + j, 4 * h + 1);
-                    const float* bp = s_bias1 + j * p.hc + 16 * u;
-                    const float* cp = s_colsum1 + j * p.hc + 16 * u;
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const float4 bb = *reinterpret_cast<const float4*>(bp + 4 * q4);
-                        const float4 cs = *reinterpret_cast<const float4*>(cp + 4 * q4);
-                        const float2 x0 = __ffma2_rn(rstd2, f2(__uint_as_float(raw[4 * q4]), __uint_as_float(raw[4 * q4 + 1])),
-                                                     __ffma2_rn(nrm2, f2(cs.x, cs.y), f2(bb.x, bb.y)));
-                        const float2 x1 = __ffma2_rn(rstd2, f2(__uint_as_float(raw[4 * q4 + 2]), __uint_as_float(raw[4 * q4 + 3])),
-                                                     __ffma2_rn(nrm2, f2(cs.z, cs.w), f2(bb.z, bb.w)));
-                        const float2 g0 = gelu2_pair(x0), g1 = gelu2_pair(x1);
-                        pk[2 * q4] = pack_bf16x2(g0.x, g0.y);
-                        pk[2 * q4 + 1] = pack_bf16x2(g1.x, g1.y);
-                    }
-                    if (tr) trace_ev<TRACE>(p.trace, 2, it, 32 + j, 4 * h + 2);
+                    convert16(raw, u, pk);
                     tmem_st8(taddr + static_cast<uint32_t>(16 * u), pk);
                     tmem_st_wait();
-                    if (tr) trace_ev<TRACE>(p.trace, 2, it, 32 + j, 4 * h + 3);
                 }
                 tc_fence_before_sync();
                 __syncwarp();
@@ -430,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             const uint32_t taddr = tmem + lane_off;
             if (tr) trace_ev<TRACE>(p.trace, 2, it, 16, 0);
             mbar_wait(&bars->a_full[ab], static_cast<uint32_t>(it >> 1) & 1);    // TMA-written tile visible to me
-            mbar_wait(&bars->acc2_full, static_cast<uint32_t>(it) & 1);
+            mbar_wait(&bars->acc2_full[0], static_cast<uint32_t>(it) & 1);
             tc_fence_after_sync();
             if (tr) trace_ev<TRACE>(p.trace, 2, it, 16, 1);
 #pragma unroll 1
@@ -471,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             fence_proxy_async_smem();                                  // my st.shared -> visible to the TMA store
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&bars->acc2_free);
+                mbar_arrive(&bars->acc2_free[0]);
                 mbar_arrive(&bars->z_ready[ab]);
             }
             if (tr) trace_ev<TRACE>(p.trace, 2, it, 16, 2);
@@ -521,21 +491,65 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->rs_full[it & 1]);
         };
+        // ---- warp 20 only: y-tile loads / z-tile stores (same buffers)
+        const bool tile_warp = warp == kTileWarp;
+        auto load_a = [&](int it) {
+            const int ab = it & 1;
+            const int m0 = tile_of(it) * 128;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars->a_full[ab], static_cast<uint32_t>(p.a_buf_bytes));
+                for (int pn = 0; pn < p.ks1; ++pn)
+                    tma_load_2d(a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, &p.tmap_y, pn * 64, m0, &bars->a_full[ab]);
+            }
+            __syncwarp();
+        };
+        if (tile_warp) {
+            if (lane == 0) tma_prefetch_desc(&p.tmap_y);
+            if (p.fuse_adj && lane == 0) {
+                mbar_arrive_expect_tx(&bars->adj_w_full, static_cast<uint32_t>(p.ks1 * kAdjSlabBytes));
+                bulk_g2s(wadj_s, p.wadj, static_cast<uint32_t>(p.ks1 * kAdjSlabBytes), &bars->adj_w_full);
+            }
+            if (my_tiles > 0) load_a(0);
+            if (my_tiles > 1) load_a(1);
+        }
         if (my_tiles > 0) produce_stats(0);
         if (my_tiles > 1) produce_stats(1);
         for (int it = 0; it < my_tiles; ++it) {
             if (it + 2 < my_tiles) produce_stats(it + 2);             // its buffer was released when tile it started
+            if (tile_warp) {
+                // the tile buffer is free again -- folded adjust: fc1 and the y W_adj^T MMAs have read it (nothing is stored);
+                // plain: the last epilogue has turned it into z, which leaves by TMA -- fetch the tile after next
+                const int ab = it & 1;
+                trace_ev<TRACE>(p.trace, 0, it, 0, 0);
+                if (p.fuse_adj) {
+                    mbar_wait(&bars->adj_done[ab], static_cast<uint32_t>(it >> 1) & 1);
+                } else {
+                    mbar_wait(&bars->z_ready[ab], static_cast<uint32_t>(it >> 1) & 1);
+                    trace_ev<TRACE>(p.trace, 0, it, 0, 1);
+                    if (lane == 0) {    // bulk-group bookkeeping is per thread: the same lane stores and waits
+                        for (int pn = 0; pn < p.ks1; ++pn)
+                            tma_store_2d_box(&p.tmap_z, a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, pn * 64, tile_of(it) * 128);
+                        bulk_commit_group();
+                        bulk_wait_group_read0();
+                    }
+                    __syncwarp();
+                }
+                trace_ev<TRACE>(p.trace, 0, it, 0, 2);
+                if (it + 2 < my_tiles) load_a(it + 2);
+                trace_ev<TRACE>(p.trace, 0, it, 0, 3);
+            }
             if (!p.fuse_adj) continue;
             const int row = tile_of(it) * 128 + r_in_tile;
-            mbar_wait(&bars->acc2_full, static_cast<uint32_t>(it) & 1);
+            mbar_wait(&bars->acc2_full[it & 1], acc2_phase(it));
             tc_fence_after_sync();
             uint32_t raw[32];
-            tmem_ld16(tmem + lane_off + static_cast<uint32_t>(p.piece_col[0]), *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
-            tmem_ld16(tmem + lane_off + static_cast<uint32_t>(p.piece_col[0] + 16), *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+            const uint32_t acc2 = tmem + lane_off + static_cast<uint32_t>(p.piece_col[0] + 32 * (it & 1));
+            tmem_ld16(acc2, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+            tmem_ld16(acc2 + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
             tmem_ld_wait();
             tc_fence_before_sync();                                   // the next tile's MMAs may overwrite the accumulator
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->acc2_free);
+            if (lane == 0) mbar_arrive(&bars->acc2_free[it & 1]);
             float st = 0.f, sq = 0.f;
             uint32_t pk[16];
 #pragma unroll
@@ -590,6 +604,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                 }
             }
         }
+        if (tile_warp && lane == 0) bulk_wait_group0();
+        __syncwarp();
     }
 
     tc_fence_before_sync();
@@ -606,8 +622,10 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
     if (p.M <= 0) return ADSR_OK;
     if (p.nc <= 0 || p.nc > 8 || p.n_pieces < 1 || p.n_pieces > 2) return ADSR_ERR_BAD_SHAPE;
     if (p.n2 > kMaxN2 || (p.n2 % 16) != 0 || p.nc * p.hc > kMaxHidden || (p.hc % 16) != 0) return ADSR_ERR_BAD_SHAPE;
-    if (p.n2 + 2 * p.hc > 512 || p.acc1_col[0] < p.n2 || p.acc1_col[1] < p.acc1_col[0] + p.hc || p.acc1_col[1] + p.hc > 512)
+    if (p.n2 + 2 * p.hc > 512 || p.acc1_col[0] < (p.fuse_adj ? 2 : 1) * p.n2 || p.acc1_col[1] < p.acc1_col[0] + p.hc || p.acc1_col[1] + p.hc > 512)
         return ADSR_ERR_BAD_SHAPE;
+    p.acc1_col[2] = p.acc1_col[1] + p.hc;
+    p.n_acc1 = (p.acc1_col[2] + p.hc <= 512 && g_mlp_acc1_max >= 3) ? 3 : 2;
     if (p.ks1 <= 0 || p.ks1 > 5 || p.k1steps <= 4 * (p.ks1 - 1) || p.k1steps > 4 * p.ks1) return ADSR_ERR_BAD_SHAPE;
     if (p.w1_slots < 2 || p.w1_slots > 8 || p.w2_slots < 2 || p.w2_slots > 8 || (p.w1_slot_bytes % 1024) || (p.w2_slot_bytes % 1024))
         return ADSR_ERR_BAD_SHAPE;

@@ -218,7 +218,8 @@ def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
     k1steps = (c + 15) // 16
     ks1 = (c + 63) // 64
     # TMEM: fc2 accumulator (n2) + two fc1 chunk accumulators (2 hc); narrower chunks when two fc1 ring slots would not fit
-    hc_max = min(128, ((512 - n2) // 2) // 16 * 16)
+    a2 = 2 * n2 if fuse_adj else n2              # folded adjust: the 32-column accumulator is double-buffered
+    hc_max = min(128, ((512 - a2) // 2) // 16 * 16)
     while True:
         nc = (h + hc_max - 1) // hc_max
         hc = round_up((h + nc - 1) // nc, 16)
@@ -239,9 +240,8 @@ def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
         hc_max -= 16
     if avail < n1 * s1 + n2s * s2 or nc > 8 or n2 > 320 or nc * hc > 640:
         raise ValueError(f"fused MLP does not fit: C={c} H={h}")
-    # bytes per tile through each ring decide how the slots are shared out (at least 2 each); the 4 KB slabs of a folded adjust
-    # need no more than one chunk's worth in flight
-    n2s_max = 4 if fuse_adj else 8
+    # bytes per tile through each ring decide how the slots are shared out (at least 2 each)
+    n2s_max = 4 if fuse_adj else 8               # the 4 KB slabs of a folded adjust: more slots only take ring space from fc1
     while True:
         grew = False
         for which in ((1, 2) if n1 * s1 <= n2s * s2 else (2, 1)):
@@ -256,7 +256,7 @@ def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
         if not grew:
             break
     return dict(ks1=ks1, k1steps=k1steps, nc=nc, hc=hc, n2=n2, widths=widths, pieces=pieces, w1_slots=n1, w1_slot_bytes=s1,
-                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(n2, n2 + hc), adj_tcol=0, fold=int(fuse_adj))
+                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(a2, a2 + hc), adj_tcol=0, fold=int(fuse_adj))
 
 
 def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:

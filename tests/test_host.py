@@ -139,8 +139,8 @@ def test_swin_mlp_plans_fit_the_sm():
         for fuse in (False, True):
             pl = pack.swin_mlp_plan(c, h, fuse)
             n2, hc, nc = pl["n2"], pl["hc"], pl["nc"]
-            assert n2 == (32 if fuse else (c + 15) // 16 * 16) and pl["fold"] == int(fuse) and pl["acc1_col"] == (n2, n2 + hc)
-            assert sum(pl["widths"]) >= h and all(w % 16 == 0 and w <= hc for w in pl["widths"]) and n2 + 2 * hc <= 512
+            assert n2 == (32 if fuse else (c + 15) // 16 * 16) and pl["fold"] == int(fuse) and pl["acc1_col"] == ((2 if fuse else 1) * n2, (2 if fuse else 1) * n2 + hc)
+            assert sum(pl["widths"]) >= h and all(w % 16 == 0 and w <= hc for w in pl["widths"]) and pl["acc1_col"][1] + hc <= 512
             assert sum(pl["pieces"]) == n2 and all(16 <= r <= 256 and r % 16 == 0 for r in pl["pieces"])
             assert not fuse or (pl["pieces"] == [32] and pl["w2_slot_bytes"] == 4096)
             smem = 2 * pl["ks1"] * 16384 + pl["w1_slots"] * pl["w1_slot_bytes"] + pl["w2_slots"] * pl["w2_slot_bytes"] + \

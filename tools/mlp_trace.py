@@ -36,8 +36,8 @@ for it in range(1, 5):
     for j in range(nc):
         print(f" fc1 ch{j}: start {rel(t[1,it,j,0]):7d} acc1_free {rel(t[1,it,j,1]):7d} issued {rel(t[1,it,j,2]):7d}"
               f" | epi1: wait {rel(t[2,it,j,0]):7d} acc_ok {rel(t[2,it,j,1]):7d} slab0 {rel(t[2,it,j,2]):7d} slab1 {rel(t[2,it,j,3]):7d}")
-        print("   epi1 detail (ld issue, ld done, math done, st done) x 2 slabs: " + " ".join(f"{rel(t[2,it,32+j,k]):7d}" for k in range(8)))
         for s in range(2):
-            print(f"   fc2 ch{j} slab{s}: start {rel(t[3,it,2*j+s,0]):7d} h_ok {rel(t[3,it,2*j+s,1]):7d} issued {rel(t[3,it,2*j+s,2]):7d}")
+            print(f"   fc2 ch{j} slab{s}: start {rel(t[3,it,2*j+s,0]):7d} h_ok {rel(t[3,it,2*j+s,1]):7d} w2_full {rel(t[3,it,2*j+s,5]):7d} issued {rel(t[3,it,2*j+s,2]):7d}"
+                  + (f"   (h_ready {rel(t[3,it,0,3]):7d} acc2_free {rel(t[3,it,0,4]):7d})" if j == 0 and s == 0 else ""))
     print(f" epi3 (adjust columns): wait {rel(t[2,it,17,0]):7d} acc_ok {rel(t[2,it,17,1]):7d} done {rel(t[2,it,17,2]):7d}")
     print(f" epi2: wait {rel(t[2,it,16,0]):7d} acc2_ok {rel(t[2,it,16,1]):7d} done {rel(t[2,it,16,2]):7d}")
