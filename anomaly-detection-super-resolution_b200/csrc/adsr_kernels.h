@@ -117,6 +117,7 @@ struct SwinMlpParams {
     int piece_rows[2], piece_col[2];
     int acc1_col[3];      // TMEM columns of the fc1 chunk accumulators ([2] = [1] + hc, used when n_acc1 == 3)
     int n_acc1;           // 2 or 3 (set by the launcher)
+    int adjy_fc1;         // folded adjust: the fc1 (1) or the fc2 (0) issuer starts the accumulator with y W_adj^T (set by the launcher)
     int w1_slots, w1_slot_bytes, w2_slots, w2_slot_bytes, a_buf_bytes;
     long long* trace;     // optional [4 roles][8 tiles][64][8] clock64 timeline of CTA 0 (tools/mlp_trace.py), else nullptr
     // optional adjust 1x1 conv (src/drct.py:389-393) FOLDED into fc2: adj_out[:, adj_col0 + n] = LReLU(z W_adj^T + b)[n], n < 32, computed

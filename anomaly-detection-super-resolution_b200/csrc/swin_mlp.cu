@@ -149,9 +149,9 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             mbar_init(&bars->acc2_free[b], p.fuse_adj ? 4 : kEpiWarps);   // folded adjust: its own four warps read the accumulator
         }
         mbar_init(&bars->adj_w_full, 1);
-        // folded adjust: the tile buffer is free once BOTH its fc1 MMAs and its y W_adj^T MMAs (two issuing warps) have completed
-        mbar_init(&bars->adj_done[0], 2);
-        mbar_init(&bars->adj_done[1], 2);
+        // folded adjust: the tile buffer is free once its fc1 and y W_adj^T MMAs (one or two issuing warps) have completed
+        mbar_init(&bars->adj_done[0], p.adjy_fc1 ? 1 : 2);
+        mbar_init(&bars->adj_done[1], p.adjy_fc1 ? 1 : 2);
         fence_barrier_init();
     }
     if (warp == kTileWarp) tmem_alloc<512>(&bars->tmem_base);
@@ -163,6 +163,27 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
     // row statistics (tile loads / stores, epilogues) wait for it to complete
     pdl_launch_dependents();
     if (warp < kEpiWarps || warp >= kTileWarp) pdl_wait();
+
+    // folded adjust: W_adj (y + fc2(g)) = y W_adj^T + g (W_adj W2)^T -- the fc2 ring carries the 32 rows of W_adj W2, the accumulator is
+    // 32 columns wide, and the y term goes in first, straight from the tile buffer (the caller has waited for a_full / acc2_free).
+    // Either MMA issuer can take it (p.adjy_fc1): the fc2 issuer's 4-MMA batches cost ~350 cycles each (profiles/r02_mma_bench.txt),
+    // so for narrow blocks (3 K slabs) it is better off without these 12 MMAs; for the wide ones the fc1 issuer is the busier warp.
+    auto issue_adj_y = [&](int it) {
+        tc_fence_after_sync();
+        if (elect_one_sync()) {
+            const uint64_t a_desc = umma_desc_k_sw128(smem_u32(a_buf)) + static_cast<uint64_t>((it & 1) * static_cast<uint32_t>(p.a_buf_bytes >> 4));
+            const uint64_t b_desc = umma_desc_k_sw128(smem_u32(wadj_s));
+            const uint32_t idesc = umma_idesc_bf16_m128(32u);
+            const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[0] + 32 * acc2_buf(it));
+            for (int s = 0; s < p.ks1; ++s) {
+                const int ksteps = min(4, p.k1steps - 4 * s);
+                for (int j = 0; j < ksteps; ++j)
+                    umma_bf16(d, a_desc + static_cast<uint64_t>(s * (kPanelBytes >> 4)) + 2 * j,
+                              b_desc + static_cast<uint64_t>(s * (kAdjSlabBytes >> 4)) + 2 * j, idesc, (s > 0 || j > 0) ? 1u : 0u);
+            }
+        }
+        __syncwarp();
+    };
 
     // The control warps below stay CONVERGED (uniform control flow, one elected lane issues): descriptors then live in
     // uniform registers and no tcgen05 / bulk-copy instruction gets wrapped in a lane-serialising loop.
@@ -222,6 +243,13 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             mbar_wait(&bars->a_full[it & 1], static_cast<uint32_t>(it >> 1) & 1);
             trace_ev<TRACE>(p.trace, 0, it, 1, 1);
             const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((it & 1) * a_units);
+            if (p.fuse_adj && p.adjy_fc1) {
+                // issued in front of the tile's fc1 chunks: the fc2 MMAs that accumulate on top are only issued after the conversion
+                // of a chunk whose completion this thread commits later, so the tensor pipe sees them in the right order
+                if (it == 0) mbar_wait(&bars->adj_w_full, 0);
+                mbar_wait(&bars->acc2_free[acc2_buf(it)], acc2_phase(it) ^ 1);     // the aux warps have read tile it - 2
+                issue_adj_y(it);
+            }
             for (int j = 0; j < p.nc; ++j) {
                 const int cg = it * p.nc + j;                         // running chunk counter: buffer = cg % n_acc1, use = cg / n_acc1
                 const int b = acc1_buf(cg);
@@ -259,28 +287,6 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         uint32_t phase = 0;
         const uint32_t slot_units = static_cast<uint32_t>(p.w2_slot_bytes >> 4);
         const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring2));
-        const uint64_t adj_a_desc0 = umma_desc_k_sw128(smem_u32(a_buf));
-        const uint64_t adj_b_desc = umma_desc_k_sw128(smem_u32(wadj_s));
-        const uint32_t adj_idesc = umma_idesc_bf16_m128(32u);
-        // folded adjust: W_adj (y + fc2(g)) = y W_adj^T + g (W_adj W2)^T -- the fc2 ring carries the 32 rows of
-        // W_adj W2, the accumulator is 32 columns wide, and the y term goes in first, straight from the tile buffer
-        auto issue_adj_y = [&](int it) {
-            if (it == 0) mbar_wait(&bars->adj_w_full, 0);
-            mbar_wait(&bars->a_full[it & 1], static_cast<uint32_t>(it >> 1) & 1);
-            tc_fence_after_sync();
-            if (elect_one_sync()) {
-                const uint64_t a_desc = adj_a_desc0 + static_cast<uint64_t>((it & 1) * static_cast<uint32_t>(p.a_buf_bytes >> 4));
-                const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[0] + 32 * acc2_buf(it));
-                for (int s = 0; s < p.ks1; ++s) {
-                    const int ksteps = min(4, p.k1steps - 4 * s);
-                    for (int j = 0; j < ksteps; ++j)
-                        umma_bf16(d, a_desc + static_cast<uint64_t>(s * (kPanelBytes >> 4)) + 2 * j,
-                                  adj_b_desc + static_cast<uint64_t>(s * (kAdjSlabBytes >> 4)) + 2 * j, adj_idesc, (s > 0 || j > 0) ? 1u : 0u);
-                }
-                umma_commit(&bars->adj_done[it & 1]);
-            }
-            __syncwarp();
-        };
         for (int it = 0; it < my_tiles; ++it) {
             for (int j = 0; j < p.nc; ++j) {
                 const int cg = it * p.nc + j;
@@ -291,11 +297,17 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                     const int ksteps = min(4, (p.hcw[j] >> 4) - 4 * s);
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 0);
                     mbar_wait(&bars->h_ready[b][s], acc1_phase(cg));
-                    if (j == 0 && s == 0) {
-                        trace_ev<TRACE>(p.trace, 3, it, 0, 3);
+                    // the accumulator is free: plain -- the last epilogue has read the previous tile's; folded adjust -- the aux warps
+                    // have read tile it - 2 (if the fc1 issuer takes the y term, it has waited for that and issued it already)
+                    if (j == 0 && s == 0 && !(p.fuse_adj && p.adjy_fc1)) {
                         mbar_wait(&bars->acc2_free[acc2_buf(it)], acc2_phase(it) ^ 1);
-                        trace_ev<TRACE>(p.trace, 3, it, 0, 4);
-                        if (p.fuse_adj) issue_adj_y(it);                       // folded adjust: the accumulator starts as y W_adj^T
+                        if (p.fuse_adj) {
+                            if (it == 0) mbar_wait(&bars->adj_w_full, 0);
+                            mbar_wait(&bars->a_full[it & 1], static_cast<uint32_t>(it >> 1) & 1);
+                            issue_adj_y(it);
+                            if (elect_one_sync()) umma_commit(&bars->adj_done[it & 1]);
+                            __syncwarp();
+                        }
                     }
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 1);
                     const uint32_t at = acc1 + static_cast<uint32_t>(64 * s);     // K=16 step u of the chunk lives at column 16 u
@@ -642,6 +654,7 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
             return ADSR_ERR_BAD_SHAPE;
     p.a_buf_bytes = p.ks1 * kPanelBytes;
     p.inv_c = 1.0f / static_cast<float>(p.C);
+    p.adjy_fc1 = p.ks1 <= 3 ? 1 : 0;
     if (p.fuse_adj) {
         if (p.wadj == nullptr || p.bias_adj == nullptr || p.adj_out == nullptr || (p.adj_col0 % 4) || (p.ld_adj % 4) ||
             (reinterpret_cast<uintptr_t>(p.wadj) & 15) || (reinterpret_cast<uintptr_t>(p.adj_out) & 7))
