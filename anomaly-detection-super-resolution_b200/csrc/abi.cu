@@ -177,9 +177,11 @@ static int swin_mlp_common(SwinMlpParams& p, const void* y, int64_t ldy, int M, 
     p.piece_col[0] = 0; p.piece_col[1] = plan[8];
     p.w1_slots = plan[10]; p.w1_slot_bytes = plan[11]; p.w2_slots = plan[12]; p.w2_slot_bytes = plan[13];
     for (int j = 0; j < 8; ++j) p.hcw[j] = plan[14 + j];
-    // plan[23] != 0: folded adjust -- the fc2 ring carries W_adj W2 (32 rows), so the accumulator is 32 columns, not C
-    const bool fold = plan_len >= 24 && plan[23] != 0;
-    if (p.ks1 != (C + 63) / 64 || p.k1steps != (C + 15) / 16 || p.n2 != (fold ? 32 : (C + 15) / 16 * 16)) return ADSR_ERR_BAD_SHAPE;
+    // plan[23] = 1: folded adjust -- the fc2 ring carries W_adj W2 (32 rows), so the accumulator is 32 columns, not C;
+    // plan[23] = 2: wide folded conv with residual -- n2 = the conv's output channels rounded up to 16 (checked by the launcher)
+    const int fold = plan_len >= 24 ? plan[23] : 0;
+    if (p.ks1 != (C + 63) / 64 || p.k1steps != (C + 15) / 16 || (fold == 0 && p.n2 != (C + 15) / 16 * 16) || (fold == 1 && p.n2 != 32))
+        return ADSR_ERR_BAD_SHAPE;
     p.w1p = static_cast<const uint8_t*>(w1_packed);
     p.w2p = static_cast<const uint8_t*>(w2_packed);
     p.bias1 = bias1; p.colsum1 = colsum1; p.bias2 = bias2;
@@ -211,7 +213,7 @@ extern "C" int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int 
                                          void* out, int64_t ldo, int ocol0, float* stats_out, int stats_out_slot0,
                                          int stats_out_stride, int reverse_tiles, int num_sms, void* stream) {
     if (M <= 0) return ADSR_OK;
-    if (plan_len < 24 || plan[23] == 0 || wadj_packed == nullptr || bias_adj == nullptr || out == nullptr || ldo < ocol0 + 32) return ADSR_ERR_BAD_SHAPE;
+    if (plan_len < 24 || plan[23] != 1 || wadj_packed == nullptr || bias_adj == nullptr || out == nullptr || ldo < ocol0 + 32) return ADSR_ERR_BAD_SHAPE;
     SwinMlpParams p{};
     p.rev = reverse_tiles != 0;
     const int st = swin_mlp_common(p, y, ldy, M, C, w1_packed, w2_packed, bias1, colsum1, bias2, plan, plan_len, ln_eps, ln_stats_in,
@@ -228,6 +230,29 @@ extern "C" int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int 
     p.adj_stats_slot0 = stats_out_slot0;
     p.adj_stats_stride = stats_out_stride;
     return launch_swin_mlp(p, y, ldy, nullptr, 0, num_sms, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int adsr_swin_mlp_conv_res_bf16(const void* y, int64_t ldy, int M, int C, const void* w1_packed, const void* w2_packed,
+                                           const float* bias1, const float* colsum1, const float* bias2, const int32_t* plan,
+                                           int plan_len, float ln_eps, const float* ln_stats_in, int stats_in_slots,
+                                           int stats_in_stride, const void* res, int64_t ldres, void* out, int64_t ldo, int c_out,
+                                           float* stats_out, int stats_out_slot0, int stats_out_stride, int reverse_tiles, int num_sms,
+                                           void* stream) {
+    if (M <= 0) return ADSR_OK;
+    if (plan_len < 24 || plan[23] != 2 || res == nullptr || out == nullptr) return ADSR_ERR_BAD_SHAPE;
+    SwinMlpParams p{};
+    p.rev = reverse_tiles != 0;
+    const int st = swin_mlp_common(p, y, ldy, M, C, w1_packed, w2_packed, bias1, colsum1, bias2, plan, plan_len, ln_eps, ln_stats_in,
+                                   stats_in_slots, stats_in_stride);
+    if (st != ADSR_OK) return st;
+    p.fold_res = 1;
+    p.c_out = c_out;
+    p.res = static_cast<const __nv_bfloat16*>(res);
+    p.ld_res = ldres;
+    p.adj_stats = reinterpret_cast<float2*>(stats_out);
+    p.adj_stats_slot0 = stats_out_slot0;
+    p.adj_stats_stride = stats_out_stride;
+    return launch_swin_mlp(p, y, ldy, out, ldo, num_sms, static_cast<cudaStream_t>(stream));
 }
 
 static long long* g_attn_trace = nullptr;

@@ -117,6 +117,16 @@ struct SwinMlpParams {
     int piece_rows[2], piece_col[2];
     int acc1_col[3];      // TMEM columns of the fc1 chunk accumulators ([2] = [1] + hc, used when n_acc1 == 3)
     int n_acc1;           // 2 or 3 (set by the launcher)
+    // wide folded 1x1 conv WITH residual (adjust5 of the RDG, src/drct.py:394-396: x + 0.2 adjust5(z)):
+    //   out[:, :c_out] = res[:, :c_out] + y W_a^T + g (W_a W2)^T + bias2   (the conv's scale and both biases folded in on the host);
+    // W_a leads the fc2 ring of every tile as (K slab, N piece) slabs, the residual tile replaces the consumed y tile in shared memory,
+    // the last epilogue adds it in place and also leaves the row's (sum, sumsq) in adj_stats (optional).  z itself never exists.
+    int fold_res;
+    int ypre[8];          // W_a slabs issued in front of chunk j (set by the launcher)
+    int c_out;
+    const __nv_bfloat16* res;
+    long long ld_res;
+    CUtensorMap tmap_res;
     int adjy_fc1;         // folded adjust: the fc1 (1) or the fc2 (0) issuer starts the accumulator with y W_adj^T (set by the launcher)
     int w1_slots, w1_slot_bytes, w2_slots, w2_slot_bytes, a_buf_bytes;
     long long* trace;     // optional [4 roles][8 tiles][64][8] clock64 timeline of CTA 0 (tools/mlp_trace.py), else nullptr

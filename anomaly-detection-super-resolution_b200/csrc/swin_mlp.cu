@@ -56,6 +56,7 @@ struct __align__(16) MlpBarriers {
     uint64_t adj_w_full;                      // folded adjust: the resident W_adj slabs have landed
     uint64_t adj_done[2];                     // folded adjust: fc1 and the y W_adj^T MMAs have finished reading the y tile in buffer b
     uint64_t rs_full[2], rs_free[2];          // (rstd, -mean * rstd) of a tile's rows in s_rowstat[tile parity]
+    uint64_t res_full[2];                     // fold_res: the residual tile has replaced the (consumed) y tile in buffer b
     uint32_t tmem_base;
 };
 
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             mbar_init(&bars->z_ready[b], kEpiWarps);
             mbar_init(&bars->rs_full[b], 4);
             mbar_init(&bars->rs_free[b], kEpiWarps);
+            mbar_init(&bars->res_full[b], 1);
         }
         for (int b = 0; b < 3; ++b) {
             mbar_init(&bars->acc1_full[b], 1);
@@ -150,8 +152,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         }
         mbar_init(&bars->adj_w_full, 1);
         // folded adjust: the tile buffer is free once its fc1 and y W_adj^T MMAs (one or two issuing warps) have completed
-        mbar_init(&bars->adj_done[0], p.adjy_fc1 ? 1 : 2);
-        mbar_init(&bars->adj_done[1], p.adjy_fc1 ? 1 : 2);
+        mbar_init(&bars->adj_done[0], (p.fuse_adj && p.adjy_fc1) ? 1 : 2);
+        mbar_init(&bars->adj_done[1], (p.fuse_adj && p.adjy_fc1) ? 1 : 2);
         fence_barrier_init();
     }
     if (warp == kTileWarp) tmem_alloc<512>(&bars->tmem_base);
@@ -213,8 +215,22 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         uint32_t phase = 0;
         for (int it = 0; it < my_tiles; ++it) {
             uint32_t goff = 0;
+            int yq = 0;
             for (int j = 0; j < p.nc; ++j) {
                 const int nslab = (p.hcw[j] + 63) >> 6;
+                if (p.fold_res) {                                    // wide folded conv: p.ypre[j] slabs of W_a go in front of chunk j
+                    for (int q = 0; q < p.ypre[j]; ++q, ++yq) {
+                        const uint32_t bytes = static_cast<uint32_t>(p.piece_rows[yq % p.n_pieces]) * 128u;
+                        mbar_wait(&bars->w2_empty[slot], phase ^ 1);
+                        if (elect_one_sync()) {
+                            mbar_arrive_expect_tx(&bars->w2_full[slot], bytes);
+                            bulk_g2s(ring2 + slot * p.w2_slot_bytes, p.w2p + goff, bytes, &bars->w2_full[slot]);
+                        }
+                        __syncwarp();
+                        goff += bytes;
+                        if (++slot == p.w2_slots) { slot = 0; phase ^= 1; }
+                    }
+                }
                 for (int s = 0; s < nslab; ++s) {
                     for (int pc = 0; pc < p.n_pieces; ++pc) {
                         const uint32_t bytes = static_cast<uint32_t>(p.piece_rows[pc]) * 128u;
@@ -272,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                         umma_commit(&bars->w1_empty[slot]);
                         if (s == p.ks1 - 1) {
                             umma_commit(&bars->acc1_full[b]);
-                            if (p.fuse_adj && j == p.nc - 1) umma_commit(&bars->adj_done[it & 1]);   // last read of the y tile by fc1
+                            if ((p.fuse_adj || p.fold_res) && j == p.nc - 1) umma_commit(&bars->adj_done[it & 1]);   // last read of the y tile by fc1
                         }
                     }
                     __syncwarp();
@@ -288,6 +304,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
         const uint32_t slot_units = static_cast<uint32_t>(p.w2_slot_bytes >> 4);
         const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring2));
         for (int it = 0; it < my_tiles; ++it) {
+            uint32_t acc2_started = 0u;                                // fold_res: bit pc = this N piece of acc2 has been written in this tile
+            int yq = 0;                                                // fold_res: next (K slab, N piece) slab of W_a
             for (int j = 0; j < p.nc; ++j) {
                 const int cg = it * p.nc + j;
                 const int b = acc1_buf(cg);
@@ -308,10 +326,37 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                             if (elect_one_sync()) umma_commit(&bars->adj_done[it & 1]);
                             __syncwarp();
                         }
+                        if (p.fold_res) mbar_wait(&bars->a_full[it & 1], static_cast<uint32_t>(it >> 1) & 1);
+                    }
+                    if (p.fold_res && s == 0) {
+                        // wide folded conv: acc2 also takes y W_a^T -- the ring brings W_a as (K slab, N piece) slabs, the y panels are
+                        // the (shared-memory) A operand; p.ypre[j] of them are issued in front of chunk j (see the launcher)
+                        const uint64_t ya_desc = umma_desc_k_sw128(smem_u32(a_buf)) + static_cast<uint64_t>((it & 1) * static_cast<uint32_t>(p.a_buf_bytes >> 4));
+                        for (int q = 0; q < p.ypre[j]; ++q, ++yq) {
+                            const int ys = yq / p.n_pieces, pc = yq - ys * p.n_pieces;
+                            const int yk = min(4, p.k1steps - 4 * ys);
+                            const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.piece_rows[pc]));
+                            const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[pc]);
+                            mbar_wait(&bars->w2_full[slot], phase);
+                            tc_fence_after_sync();
+                            if (elect_one_sync()) {
+                                const uint64_t adesc = ya_desc + static_cast<uint64_t>(ys * (kPanelBytes >> 4));
+                                const uint64_t bdesc = ring_desc + static_cast<uint64_t>(static_cast<uint32_t>(slot) * slot_units);
+                                umma_bf16(d, adesc, bdesc, idesc, (acc2_started >> pc) & 1u);
+                                if (yk > 1) umma_bf16(d, adesc + 2, bdesc + 2, idesc, 1u);
+                                if (yk > 2) umma_bf16(d, adesc + 4, bdesc + 4, idesc, 1u);
+                                if (yk > 3) umma_bf16(d, adesc + 6, bdesc + 6, idesc, 1u);
+                                umma_commit(&bars->w2_empty[slot]);
+                                if (yq == p.ks1 * p.n_pieces - 1) umma_commit(&bars->adj_done[it & 1]);   // my last read of the y tile
+                            }
+                            __syncwarp();
+                            acc2_started |= 1u << pc;
+                            if (++slot == p.w2_slots) { slot = 0; phase ^= 1; }
+                        }
                     }
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 1);
                     const uint32_t at = acc1 + static_cast<uint32_t>(64 * s);     // K=16 step u of the chunk lives at column 16 u
-                    const uint32_t first_acc = (j == 0 && s == 0 && !p.fuse_adj) ? 0u : 1u;
+                    const uint32_t first_acc = (j == 0 && s == 0 && !p.fuse_adj) ? 0u : 1u;   // (fold_res: per N piece, acc2_started)
                     for (int pc = 0; pc < p.n_pieces; ++pc) {
                         const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(p.piece_rows[pc]));
                         const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[pc] + 32 * acc2_buf(it));
@@ -320,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                         tc_fence_after_sync();
                         if (elect_one_sync()) {
                             const uint64_t bdesc = ring_desc + static_cast<uint64_t>(static_cast<uint32_t>(slot) * slot_units);
-                            umma_bf16_ts(d, at, bdesc, idesc, first_acc);
+                            umma_bf16_ts(d, at, bdesc, idesc, p.fold_res ? ((acc2_started >> pc) & 1u) : first_acc);
                             if (ksteps > 1) umma_bf16_ts(d, at + 16, bdesc + 2, idesc, 1u);
                             if (ksteps > 2) umma_bf16_ts(d, at + 32, bdesc + 4, idesc, 1u);
                             if (ksteps > 3) umma_bf16_ts(d, at + 48, bdesc + 6, idesc, 1u);
@@ -331,6 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                             }
                         }
                         __syncwarp();
+                        acc2_started |= 1u << pc;
                         if (++slot == p.w2_slots) { slot = 0; phase ^= 1; }
                     }
                     trace_ev<TRACE>(p.trace, 3, it, 2 * j + s, 2);
@@ -411,8 +457,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             const uint32_t a_row = smem_u32(a_buf + ab * p.a_buf_bytes) + row_off;
             const uint32_t taddr = tmem + lane_off;
             if (tr) trace_ev<TRACE>(p.trace, 2, it, 16, 0);
-            mbar_wait(&bars->a_full[ab], static_cast<uint32_t>(it >> 1) & 1);    // TMA-written tile visible to me
+            // the residual: the y tile itself, or (fold_res) the tile of the residual tensor that replaced it -- TMA-written, visible to me
+            mbar_wait(p.fold_res ? &bars->res_full[ab] : &bars->a_full[ab], static_cast<uint32_t>(it >> 1) & 1);
             mbar_wait(&bars->acc2_full[0], static_cast<uint32_t>(it) & 1);
+            float2 ost = f2(0.f, 0.f), osq = f2(0.f, 0.f);                       // fold_res: (sum, sumsq) of my columns of the output row
             tc_fence_after_sync();
             if (tr) trace_ev<TRACE>(p.trace, 2, it, 16, 1);
 #pragma unroll 1
@@ -447,7 +495,21 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr[o]), "r"(pack_bf16x2(v0.x, v0.y)),
                                  "r"(pack_bf16x2(v1.x, v1.y)), "r"(pack_bf16x2(v2.x, v2.y)), "r"(pack_bf16x2(v3.x, v3.y))
                                  : "memory");
+                    if (p.fold_res) {      // pad columns: zero weights, zero bias, zero-filled residual -> exact zeros, no effect on the sums
+                        ost = __fadd2_rn(ost, __fadd2_rn(__fadd2_rn(v0, v1), __fadd2_rn(v2, v3)));
+                        osq = __ffma2_rn(v0, v0, osq);
+                        osq = __ffma2_rn(v1, v1, osq);
+                        osq = __ffma2_rn(v2, v2, osq);
+                        osq = __ffma2_rn(v3, v3, osq);
+                    }
                 }
+            }
+            if (p.fold_res && p.adj_stats != nullptr) {
+                // the row's (sum, sumsq): each of the four column groups leaves its partial in a slot of its own (the LayerNorm fold
+                // of the consumer adds the slots up anyway) -- no exchange through shared memory, no barrier
+                const int row = tile_of(it) * 128 + r_in_tile;
+                if (row < p.M)
+                    p.adj_stats[static_cast<long long>(row) * p.adj_stats_stride + p.adj_stats_slot0 + grp] = f2(ost.x + ost.y, osq.x + osq.y);
             }
             tc_fence_before_sync();
             fence_proxy_async_smem();                                  // my st.shared -> visible to the TMA store
@@ -536,10 +598,22 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
                 if (p.fuse_adj) {
                     mbar_wait(&bars->adj_done[ab], static_cast<uint32_t>(it >> 1) & 1);
                 } else {
+                    const int zpan = p.fold_res ? (p.n2 + 63) >> 6 : p.ks1;     // 64-column panels of the output tile
+                    if (p.fold_res) {
+                        // fc1 and the y W_a^T MMAs have read the y tile: the residual tile takes its place (same panel layout; columns
+                        // >= c_out are zero-filled by the tensor map), the last epilogue adds it and leaves the output in place
+                        mbar_wait(&bars->adj_done[ab], static_cast<uint32_t>(it >> 1) & 1);
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(&bars->res_full[ab], static_cast<uint32_t>(zpan * kPanelBytes));
+                            for (int pn = 0; pn < zpan; ++pn)
+                                tma_load_2d(a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, &p.tmap_res, pn * 64, tile_of(it) * 128, &bars->res_full[ab]);
+                        }
+                        __syncwarp();
+                    }
                     mbar_wait(&bars->z_ready[ab], static_cast<uint32_t>(it >> 1) & 1);
                     trace_ev<TRACE>(p.trace, 0, it, 0, 1);
                     if (lane == 0) {    // bulk-group bookkeeping is per thread: the same lane stores and waits
-                        for (int pn = 0; pn < p.ks1; ++pn)
+                        for (int pn = 0; pn < zpan; ++pn)
                             tma_store_2d_box(&p.tmap_z, a_buf + ab * p.a_buf_bytes + pn * kPanelBytes, pn * 64, tile_of(it) * 128);
                         bulk_commit_group();
                         bulk_wait_group_read0();
@@ -663,8 +737,23 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
         if (p.adj_stats != nullptr && p.adj_stats_slot0 + 2 > p.adj_stats_stride) return ADSR_ERR_BAD_SHAPE;
         p.adj_stats_vec4 = ((p.adj_stats_slot0 | p.adj_stats_stride) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.adj_stats) & 15) == 0;
     }
+    if (p.fold_res) {
+        // wide folded conv with residual: out[:, :c_out] = res[:, :c_out] + y W_a^T + g (W_a W2)^T + bias; the output tile (n2 columns)
+        // takes the place of the y tile, so it must fit its panels
+        if (p.fuse_adj || p.res == nullptr || p.c_out <= 0 || p.n2 != (p.c_out + 15) / 16 * 16 || (p.n2 + 63) / 64 > p.ks1 ||
+            p.ld_res < p.c_out || ldz < p.c_out)
+            return ADSR_ERR_BAD_SHAPE;
+        if ((reinterpret_cast<uintptr_t>(p.res) & 15) || (p.ld_res % 8)) return ADSR_ERR_BAD_ALIGN;
+        if (p.adj_stats != nullptr && p.adj_stats_slot0 + 4 > p.adj_stats_stride) return ADSR_ERR_BAD_SHAPE;   // four partial slots
+        // where the ks1 * n_pieces slabs of W_a go in the fc2 stream (pack.pack_swin_mlp_conv_res lays it out by the same rule): all in
+        // front of chunk 0.  Spreading them evenly over the chunks was measured SLOWER (188 vs 177 us at C = 308): with ~56 KB of ring
+        // in flight next to two 80 KB tile buffers both rings are L2-latency bound, and the fc2 issuer then paces the whole tile
+        const int ytot = p.ks1 * p.n_pieces;
+        for (int j = 0; j < 8; ++j) p.ypre[j] = j == 0 ? ytot : 0;
+    }
     const int smem_bytes = 2 * p.a_buf_bytes + p.w1_slots * p.w1_slot_bytes + p.w2_slots * p.w2_slot_bytes + const_bytes(p.nc * p.hc, p.n2) +
-                           (p.fuse_adj ? p.ks1 * kAdjSlabBytes + kAdjStageBytes : 0) + static_cast<int>(sizeof(MlpBarriers));
+                           (p.fuse_adj ? p.ks1 * kAdjSlabBytes + kAdjStageBytes : 0) +
+                           static_cast<int>(sizeof(MlpBarriers));
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
     if ((reinterpret_cast<uintptr_t>(y) & 15) || (!p.fuse_adj && ((reinterpret_cast<uintptr_t>(z) & 15) || (ldz % 8))) || (ldy % 8) ||
         (reinterpret_cast<uintptr_t>(p.w1p) & 15) || (reinterpret_cast<uintptr_t>(p.w2p) & 15))
@@ -672,7 +761,11 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
     int st = encode_tmap_rows_bf16(&p.tmap_y, y, p.M, p.C, ldy);
     if (st != ADSR_OK) return st;
     if (!p.fuse_adj) {
-        st = encode_tmap_rows_bf16(&p.tmap_z, z, p.M, p.C, ldz);
+        st = encode_tmap_rows_bf16(&p.tmap_z, z, p.M, p.fold_res ? p.c_out : p.C, ldz);
+        if (st != ADSR_OK) return st;
+    }
+    if (p.fold_res) {
+        st = encode_tmap_rows_bf16(&p.tmap_res, p.res, p.M, p.c_out, p.ld_res);
         if (st != ADSR_OK) return st;
     }
     p.m_tiles = (p.M + 127) / 128;

@@ -29,6 +29,7 @@ from .pack import PackedWeight, round_up
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # src/drct.py:774
 _FUSED_ADJUST = os.environ.get("ADSR_FUSED_ADJUST", "1") != "0"  # A/B switch: 0 = adjust convs as separate GEMMs
+_FOLD_ADJUST5 = os.environ.get("ADSR_FOLD_ADJUST5", "1") != "0"  # A/B switch: 0 = adjust5 + the RDG residual as a row-tile GEMM
 _ALT_TILE_ORDER = os.environ.get("ADSR_ALT_TILE_ORDER", "1") != "0"  # A/B switch: 0 = every kernel walks its row tiles front to back
 _FUSED_ATTN = os.environ.get("ADSR_FUSED_ATTN", "1") != "0"
 _PREFER_ATTN2 = os.environ.get("ADSR_PREFER_ATTN2", "0") != "0"  # A/B switch: 1 = swin_attn2 (+ proj GEMM) wherever it covers the block shape    # A/B switch for profiling: 0 = separate qkv / attention / proj kernels
@@ -109,7 +110,7 @@ class _PatchNorm(nn.Module):
 class _Block:
     """Packed weights + geometry of one Swin block and its adjust conv."""
     __slots__ = ("dim", "heads", "hd", "hdp", "shift", "ws", "hidden", "adjust_out", "n1w", "n1b", "n2w", "n2b", "table",
-                 "qkv", "proj", "mlp", "adjust", "last", "attn", "attn_mode")
+                 "qkv", "proj", "mlp", "mlp_res", "adjust", "last", "attn", "attn_mode")
 
 
 class DRCT(nn.Module):
@@ -217,6 +218,13 @@ class DRCT(nn.Module):
                         b.mlp = None
                 if b.mlp is None:
                     b.mlp = up(pack.pack_swin_mlp(fc1_w, fc1_b, n2w, n2b, sw.norm2.eps, fc2_w, fc2_b))
+                # adjust5 and the group's residual (`x5 * 0.2 + x`, src/drct.py:394-396) fold into the last block's MLP kernel the same way
+                b.mlp_res = None
+                if k == 4 and _FOLD_ADJUST5:
+                    try:
+                        b.mlp_res = up(pack.pack_swin_mlp_conv_res(fc1_w, fc1_b, n2w, n2b, sw.norm2.eps, fc2_w, fc2_b, adj_w, adj_b, 0.2))
+                    except ValueError:
+                        b.mlp_res = None
                 b.adjust = up(pack.pack_gemm_weight(adj_w, adj_b, rows_kernel=(k == 4)))
                 blocks.append(b)
             P["blocks"].append(blocks)
@@ -308,7 +316,8 @@ class DRCT(nn.Module):
         rev = _ALT_TILE_ORDER
         slab_fwd = True                                   # direction in which the current slab contents were written
         for blocks in P["blocks"]:
-            xs = 2 * blocks[-1].adjust.n_tiles        # st_slab: x owns the first xs slots (written by adjust5), each x_j two more
+            # st_slab: x owns the first xs slots (written by adjust5: four partial slots from the folded kernel), each x_j two more
+            xs = 4 if blocks[-1].mlp_res is not None else 2 * blocks[-1].adjust.n_tiles
             for k, b in enumerate(blocks):
                 C = b.dim
                 # ---- W-MSA / SW-MSA half (src/drct.py:478-509); norm1 is folded into the qkv GEMM, its row statistics
@@ -334,6 +343,11 @@ class DRCT(nn.Module):
                 if b.mlp.wadj is not None:
                     # ... and the adjust 1x1 conv (+LeakyReLU 0.2) into the slab slice (src/drct.py:389-393) in the same kernel
                     ops.swin_mlp_adjust(y, C, b.mlp, slab, C, stats_in=(st_y, y_slots), stats_out=(st_slab, xs + 2 * k), reverse=mlp_rev)
+                    slab_fwd = not mlp_rev
+                    continue
+                if b.last and b.mlp_res is not None:
+                    # ... and adjust5 + the group's residual: slab[:, :D] = slab[:, :D] + 0.2 adjust5(z), in place, in the same kernel
+                    ops.swin_mlp_conv_res(y, C, b.mlp_res, slab, slab, stats_in=(st_y, y_slots), stats_out=(st_slab, 0), reverse=mlp_rev)
                     slab_fwd = not mlp_rev
                     continue
                 ops.swin_mlp(y, C, b.mlp, z, stats_in=(st_y, y_slots), reverse=mlp_rev)

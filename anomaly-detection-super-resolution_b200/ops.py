@@ -105,6 +105,28 @@ def swin_mlp_adjust(y: torch.Tensor, c: int, pm, out: torch.Tensor, ocol0: int, 
     _count("swin_mlp", 4.0 * m * pm.C * pm.H + 2.0 * m * pm.C * 32, _t)
 
 
+def swin_mlp_conv_res(y: torch.Tensor, c: int, pm, res: torch.Tensor, out: torch.Tensor, stats_in: tuple,
+                      stats_out: Optional[tuple] = None, m: Optional[int] = None, reverse: bool = False) -> None:
+    """out[:, :c_out] = res[:, :c_out] + alpha * conv(z),  z = y + fc2(GELU(fc1(LayerNorm(y[:, :c]))))  -- the fused MLP kernel with a
+    wide 1x1 conv (adjust5 of the RDG) and the residual folded in; z is never written, out may alias res.  `pm` from
+    pack.pack_swin_mlp_conv_res(...); stats_out receives the row's (sum, sumsq) of the c_out output columns as four partial slots."""
+    _cuda(y, "y")
+    _cuda(res, "res")
+    _cuda(out, "out")
+    if not getattr(pm, "conv_out", 0):
+        raise ValueError("swin_mlp_conv_res: weights were not packed by pack_swin_mlp_conv_res")
+    m = y.shape[0] if m is None else m
+    si_t, si_n = stats_in
+    so_t, so_0 = stats_out if stats_out is not None else (None, 0)
+    _t = _begin()
+    check(lib().adsr_swin_mlp_conv_res_bf16(ptr(y), y.stride(0), m, c, ptr(pm.w1), ptr(pm.w2), ptr(pm.bias1), ptr(pm.colsum1), ptr(pm.bias2),
+                                            pm.plan.data_ptr(), pm.plan.numel(), pm.ln_eps, ptr(si_t), si_n, si_t.shape[1],
+                                            ptr(res), res.stride(0), ptr(out), out.stride(0), pm.conv_out, ptr(so_t), so_0,
+                                            so_t.shape[1] if so_t is not None else 0, int(reverse), _abi.num_sms(), stream_ptr()),
+          "adsr_swin_mlp_conv_res_bf16")
+    _count("swin_mlp", 2.0 * m * pm.C * pm.H + 2.0 * m * pm.H * pm.conv_out + 2.0 * m * pm.C * pm.conv_out, _t)
+
+
 def swin_attn_mode(c: int, heads: int, hdp: int, allow_proj: bool = True) -> int:
     """What adsr_swin_attn_bf16 covers for this block shape: 2 = whole attention half, 1 = qkv + attention, 0 = nothing."""
     return int(lib().adsr_swin_attn_mode(c, heads, hdp, int(allow_proj)))

@@ -204,22 +204,28 @@ class PackedMlp:
     H: int
     wadj: Optional[torch.Tensor] = None      # fused adjust conv: uint8 slabs [32 rows x 64 bf16] per K slab, 128-byte swizzle
     bias_adj: Optional[torch.Tensor] = None  # fp32 [32]
+    conv_out: int = 0                        # pack_swin_mlp_conv_res: output channels of the folded conv (plan[23] = 2)
 
 
 _ADJ_N = 32                     # output channels of the fusable adjust convs (gc of the RDG)
 
 
-def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
+def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False, conv_out: int = 0) -> dict:
     """Static tiling of one fused MLP (swin_mlp.cu): hidden chunks of <= 128 columns (two fp32 chunk accumulators plus the
     fc2 accumulator must fit the 512 TMEM columns), the fc2 output issued in two pieces of >= 128 rows when it is wider
     than 255, and the shared memory left after the two y-tile buffers split between the fc1 and fc2 weight rings."""
-    # fuse_adj: the adjust conv is folded INTO fc2 (W_adj W2, 32 rows), so the "fc2" accumulator is the 32 adjust columns
-    n2 = _ADJ_N if fuse_adj else round_up(c, 16)
+    # fuse_adj: the adjust conv is folded INTO fc2 (W_adj W2, 32 rows), so the "fc2" accumulator is the 32 adjust columns;
+    # conv_out > 0: a wide 1x1 conv with residual folded in the same way (adsr_swin_mlp_conv_res_bf16): its output channels
+    n2 = _ADJ_N if fuse_adj else round_up(conv_out if conv_out else c, 16)
+    if conv_out and (fuse_adj or (n2 + 63) // 64 > (c + 63) // 64):
+        raise ValueError(f"folded conv does not fit: C={c} -> {conv_out}")
     k1steps = (c + 15) // 16
     ks1 = (c + 63) // 64
     # TMEM: fc2 accumulator (n2) + two fc1 chunk accumulators (2 hc); narrower chunks when two fc1 ring slots would not fit
     a2 = 2 * n2 if fuse_adj else n2              # folded adjust: the 32-column accumulator is double-buffered
     hc_max = min(128, ((512 - a2) // 2) // 16 * 16)
+    if conv_out:        # chunks narrow enough for THREE fc1 accumulators next to the wide one: smaller ring slots, a deeper fc2 ring
+        hc_max = min(hc_max, ((512 - a2) // 3) // 16 * 16)
     while True:
         nc = (h + hc_max - 1) // hc_max
         hc = round_up((h + nc - 1) // nc, 16)
@@ -244,7 +250,8 @@ def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
     n2s_max = 4 if fuse_adj else 8               # the 4 KB slabs of a folded adjust: more slots only take ring space from fc1
     while True:
         grew = False
-        for which in ((1, 2) if n1 * s1 <= n2s * s2 else (2, 1)):
+        # (a folded wide conv streams ks1 * pieces extra slabs through the fc2 ring at every tile start: that ring grows first)
+        for which in ((2, 1) if conv_out and n2s < 4 else (1, 2) if n1 * s1 <= n2s * s2 else (2, 1)):
             if which == 1 and n1 < 8 and avail >= (n1 + 1) * s1 + n2s * s2:
                 n1 += 1
                 grew = True
@@ -256,7 +263,7 @@ def swin_mlp_plan(c: int, h: int, fuse_adj: bool = False) -> dict:
         if not grew:
             break
     return dict(ks1=ks1, k1steps=k1steps, nc=nc, hc=hc, n2=n2, widths=widths, pieces=pieces, w1_slots=n1, w1_slot_bytes=s1,
-                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(a2, a2 + hc), adj_tcol=0, fold=int(fuse_adj))
+                w2_slots=n2s, w2_slot_bytes=s2, acc1_col=(a2, a2 + hc), adj_tcol=0, fold=2 if conv_out else int(fuse_adj))
 
 
 def _swizzle_slab(block: torch.Tensor) -> torch.Tensor:
@@ -333,6 +340,65 @@ def pack_swin_mlp(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, adjust_w=None, a
         bias_adj = bias_adj.contiguous()
     return PackedMlp(torch.cat(slabs1).contiguous(), torch.cat(slabs2).contiguous(), bias1, colsum1, bias2,
                      torch.tensor(plan, dtype=torch.int32), float(eps), c, h, wadj, bias_adj)
+
+
+def pack_swin_mlp_conv_res(fc1_w, fc1_b, gamma, beta, eps, fc2_w, fc2_b, conv_w, conv_b, alpha: float) -> PackedMlp:
+    """norm2 + fc1 + GELU + fc2 of the RDG's LAST Swin block with adjust5 and the group's residual folded in
+    (src/drct.py:394-396: `x5 = adjust5(swin5(...)); return x5 * 0.2 + x`) for adsr_swin_mlp_conv_res_bf16:
+        out = res + alpha * (W_a z + b_a),  z = y + W2 g + b2   =>   out = res + y (alpha W_a)^T + g (alpha W_a W2)^T + alpha (b_a + W_a b2)
+    The fc2 ring carries the c_out rows of alpha W_a W2 (with GELU's 0.5), led every tile by the (K slab, N piece) slabs of alpha W_a."""
+    w1 = fc1_w.detach().float()
+    h, c = w1.shape
+    dev = w1.device
+    wa = conv_w.detach().float().reshape(conv_w.shape[0], -1) * float(alpha)
+    co = wa.shape[0]
+    pl = swin_mlp_plan(c, h, False, co)
+    hc, nc, n2, ks1 = pl["hc"], pl["nc"], pl["n2"], pl["ks1"]
+    w1g = torch.zeros(nc * hc, ks1 * 64, device=dev)
+    w1g[:h, :c] = w1 * gamma.detach().float()[None, :]
+    w2p = torch.zeros(n2, nc * hc + 64, device=dev)
+    w2p[:co, :h] = (wa.double() @ (fc2_w.detach().double() * 0.5)).float()
+    wap = torch.zeros(n2, ks1 * 64, device=dev)
+    wap[:co, :c] = wa
+    bias1 = torch.zeros(nc * hc, device=dev)
+    bias1[:h] = w1 @ beta.detach().float() + (fc1_b.detach().float() if fc1_b is not None else 0.0)
+    colsum1 = w1g.to(torch.bfloat16).float().sum(dim=1)
+    bias2 = torch.zeros(n2, device=dev)
+    b = (conv_b.detach().double() * float(alpha)) if conv_b is not None else torch.zeros(co, device=dev, dtype=torch.float64)
+    if fc2_b is not None:
+        b = b + wa.double() @ fc2_b.detach().double()
+    bias2[:co] = b.float()
+    slabs1, slabs2 = [], []
+    yslabs = []                                          # the y term: alpha W_a, (K slab, N piece)
+    for s in range(ks1):
+        dcol = 0
+        for rows in pl["pieces"]:
+            yslabs.append(_swizzle_slab(wap[dcol:dcol + rows, 64 * s:64 * s + 64].contiguous()))
+            dcol += rows
+    # ... ypre[j] of them lead chunk j's own slabs in the fc2 stream (the launcher derives the same schedule: all in front of chunk 0)
+    ypre = [len(yslabs) if j == 0 else 0 for j in range(nc)]
+    for j, wj in enumerate(pl["widths"]):
+        for s in range(ks1):
+            slabs1.append(_swizzle_slab(w1g[j * hc:j * hc + wj, 64 * s:64 * s + 64].contiguous()))
+        for _ in range(ypre[j]):
+            slabs2.append(yslabs.pop(0))
+        for s in range((wj + 63) // 64):
+            k0 = j * hc + 64 * s
+            valid = wj - 64 * s
+            dcol = 0
+            for rows in pl["pieces"]:
+                blk = w2p[dcol:dcol + rows, k0:k0 + 64].clone()
+                if valid < 64:
+                    blk[:, valid:] = 0.0
+                slabs2.append(_swizzle_slab(blk))
+                dcol += rows
+    pieces = pl["pieces"] + [0] * (2 - len(pl["pieces"]))
+    plan = [ks1, pl["k1steps"], nc, hc, n2, pl["acc1_col"][0], pl["acc1_col"][1], len(pl["pieces"]), pieces[0], pieces[1],
+            pl["w1_slots"], pl["w1_slot_bytes"], pl["w2_slots"], pl["w2_slot_bytes"]] + pl["widths"] + [0] * (8 - nc) + [0, 2]
+    pm = PackedMlp(torch.cat(slabs1).contiguous(), torch.cat(slabs2).contiguous(), bias1, colsum1, bias2,
+                   torch.tensor(plan, dtype=torch.int32), float(eps), c, h)
+    pm.conv_out = co
+    return pm
 
 
 # ------------------------------------------------------------------------------------------------ fused attention half

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ADSR_ABI_VERSION 12
+#define ADSR_ABI_VERSION 13
 
 #define ADSR_OK 0
 #define ADSR_ERR_BAD_SHAPE 1   /* unsupported dimensions (e.g. window size whose N does not tile 64) */
@@ -97,6 +97,23 @@ int adsr_swin_mlp_adjust_bf16(const void* y, int64_t ldy, int M, int C,
                               const void* wadj_packed, const float* bias_adj, float slope,
                               void* out, int64_t ldo, int ocol0,
                               float* stats_out, int stats_out_slot0, int stats_out_stride, int reverse_tiles, int num_sms, void* stream);
+
+/* Same kernel with a WIDE 1x1 conv and its residual folded in -- adjust5 of the RDG (src/drct.py:394-396: `x5 = adjust5(swin5(...));
+ * return x5 * 0.2 + x`):   out[:, :c_out] = res[:, :c_out] + alpha (W_a z + b_a),  z = the MLP result above, computed as
+ *   res + y (alpha W_a)^T + g (alpha W_a W2)^T + alpha (b_a + W_a b2)
+ * -- w2_packed holds, per tile, the (K slab, N piece) slabs of alpha W_a followed by the chunk slabs of alpha W_a W2; bias2 is the
+ * combined bias (n2 = c_out rounded up to 16 entries); the plan ends in (0, 2).  All of it comes from
+ * pack.pack_swin_mlp_conv_res().  The residual tile replaces the consumed y tile in shared memory and the result leaves by TMA, so
+ * res and out need 16-byte aligned rows (ld % 8 == 0) and MAY alias (the in-place update of the dense-feature slab).  stats_out
+ * (optional) receives the row's (sum, sumsq) over the c_out output columns as FOUR partial slots stats_out_slot0 .. +3 (one per
+ * column group of the epilogue; a consumer's LayerNorm fold adds its slots up).  z is never written. */
+int adsr_swin_mlp_conv_res_bf16(const void* y, int64_t ldy, int M, int C,
+                                const void* w1_packed, const void* w2_packed,
+                                const float* bias1, const float* colsum1, const float* bias2,
+                                const int32_t* plan, int plan_len, float ln_eps,
+                                const float* ln_stats_in, int stats_in_slots, int stats_in_stride,
+                                const void* res, int64_t ldres, void* out, int64_t ldo, int c_out,
+                                float* stats_out, int stats_out_slot0, int stats_out_stride, int reverse_tiles, int num_sms, void* stream);
 
 /* ---- fused attention half of a Swin block for 8 x 8 windows ------------------------------------------------------
  *   y = x + proj( WindowAttention( LayerNorm(x) ) )

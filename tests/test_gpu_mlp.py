@@ -102,3 +102,50 @@ def test_mlp_fused_adjust(C, H, M):
     assert float((st_out[:, 2, 1] - s2).abs().max()) < 5e-3 * float(s2.abs().max()) + 1e-3
     assert float(st_out[:, 3].abs().max()) == 0.0
     assert float((st_out[:, :2] - 1e9).abs().max()) == 0.0 and float((st_out[:, 4:] - 1e9).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("C,H,Co,M,inplace", [(308, 308, 180, 677, True), (308, 308, 180, 128 * 148 * 2 + 9, True), (244, 488, 180, 677, False),
+                                              (128, 256, 60, 300, True)])
+def test_mlp_folded_conv_with_residual(C, H, Co, M, inplace):
+    """adjust5 + the RDG residual folded into the MLP kernel (src/drct.py:394-396): out[:, :Co] = res[:, :Co] + 0.2 (W_a z + b_a), z never
+    written; in place on the slab (out is res) or into another tensor; row statistics of the Co output columns in the given slot."""
+    ops, pack = mod("ops"), mod("pack")
+    torch.manual_seed(C + Co)
+    ld = 320
+    y = torch.full((M, ld), 5.0, device=DEV, dtype=torch.bfloat16)
+    y[:, :C] = (torch.randn(M, C, device=DEV) * 1.5 + 0.3).to(torch.bfloat16)
+    res = torch.full((M, ld), -7.0, device=DEV, dtype=torch.bfloat16)
+    res[:, :Co] = (torch.randn(M, Co, device=DEV) * 2.0).to(torch.bfloat16)
+    w1, b1 = torch.randn(H, C, device=DEV) * 0.08, torch.randn(H, device=DEV) * 0.2
+    w2, b2 = torch.randn(C, H, device=DEV) * 0.08, torch.randn(C, device=DEV) * 0.2
+    wa, ba = torch.randn(Co, C, 1, 1, device=DEV) * 0.1, torch.randn(Co, device=DEV) * 0.2
+    gamma, beta = 1.0 + 0.2 * torch.randn(C, device=DEV), 0.1 * torch.randn(C, device=DEV)
+    pm = pack.pack_swin_mlp_conv_res(w1, b1, gamma, beta, 1e-5, w2, b2, wa, ba, 0.2)
+    assert pm.plan.tolist()[23] == 2 and pm.plan.tolist()[4] == (Co + 15) // 16 * 16
+    yf, rf = y[:, :C].float(), res[:, :Co].float()
+    stats = torch.zeros(M, 2, 2, device=DEV)
+    stats[:, 0, 0], stats[:, 0, 1] = yf.sum(1), (yf ** 2).sum(1)
+    st_out = torch.full((M, 6, 2), 1e9, device=DEV)
+    out = res if inplace else torch.full((M, ld), -3.0, device=DEV, dtype=torch.bfloat16)
+    ops.swin_mlp_conv_res(y, C, pm, res, out, stats_in=(stats, 1), stats_out=(st_out, 2))
+    torch.cuda.synchronize()
+    z = yf + F.linear(F.gelu(F.linear(F.layer_norm(yf, (C,), gamma, beta, 1e-5), w1, b1)), w2, b2)
+    want = rf + 0.2 * F.linear(z, wa.view(Co, C), ba)
+    got = out[:, :Co].float()
+    err = float((got - want).abs().max() / want.abs().max())
+    assert err < 0.012, f"C={C} Co={Co}: rel err {err}"
+    fill = -7.0 if inplace else -3.0
+    c8 = (Co + 7) // 8 * 8              # the TMA store clips at Co rounded up to a 16-byte chunk; pad columns there receive exact zeros
+    tail = out[:, Co:c8].float()
+    assert bool(((tail == 0.0) | (tail == fill)).all()) and float((out[:, c8:].float() - fill).abs().max()) == 0.0, "wrote outside the output columns"
+    if not inplace:
+        assert float((res[:, :Co].float() - rf).abs().max()) == 0.0 and float((res[:, Co:].float() + 7.0).abs().max()) == 0.0
+    s1, s2 = got.sum(1), (got ** 2).sum(1)
+    assert float((st_out[:, 2:6, 0].sum(1) - s1).abs().max()) < 5e-3 * float(s1.abs().max()) + 1e-2      # four partial slots
+    assert float((st_out[:, 2:6, 1].sum(1) - s2).abs().max()) < 5e-3 * float(s2.abs().max()) + 1e-2
+    assert float((st_out[:, :2] - 1e9).abs().max()) == 0.0
+    out2 = res.clone() if inplace else torch.full((M, ld), -3.0, device=DEV, dtype=torch.bfloat16)     # reverse tile order: same bits
+    if not inplace:
+        ops.swin_mlp_conv_res(y, C, pm, res, out2, stats_in=(stats, 1), reverse=True)
+        torch.cuda.synchronize()
+        assert torch.equal(out, out2)

@@ -35,6 +35,18 @@ for (C, H) in shapes:
     fl = 4.0 * M * C * H
     print(f"swin_mlp C={C} H={H}: {best*1e3:8.1f} us (avg {avg*1e3:8.1f})  {fl/best/1e9:7.1f} TFLOP/s  {4.0*M*C/best/1e6:7.1f} GB/s(y+z)")
     # the same with the RDG's adjust 1x1 conv fused in (z never written) next to MLP + separate adjust GEMM
+    if C == 308:                    # adjust5 (308 -> 180) + the RDG residual folded in, next to plain MLP + the row-tile GEMM it replaces
+        wa5, ba5 = torch.randn(180, C, device=dev) * 0.05, torch.randn(180, device=dev)
+        pm5 = pack.pack_swin_mlp_conv_res(torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
+                                          torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev), wa5, ba5, 0.2)
+        slab5 = torch.randn(M, 320, device=dev).to(torch.bfloat16); st5 = torch.zeros(M, 12, 2, device=dev)
+        b5, a5 = timeit(lambda: ops.swin_mlp_conv_res(y, C, pm5, slab5, slab5, stats_in=(stats, 2), stats_out=(st5, 0)))
+        padj5 = pack.pack_gemm_weight(wa5, ba5, rows_kernel=True)
+        def sep5():
+            ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2))
+            ops.tc_gemm(z, C, padj5, slab5, alpha=0.2, res=slab5, stats_out=(st5, 0))
+        bs5, _ = timeit(sep5)
+        print(f"   + adjust5 and residual folded in: {b5*1e3:8.1f} us (avg {a5*1e3:8.1f})   separate MLP + adjust5 GEMM {bs5*1e3:8.1f} us   plan {pm5.plan.tolist()[:14]}")
     if C + 32 > 320: continue      # adjust5 is not a 32-channel conv
     wa, ba = torch.randn(32, C, device=dev) * 0.05, torch.randn(32, device=dev)
     margs = (torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),

@@ -10,7 +10,12 @@ y = torch.randn(M, 320, device=dev).to(torch.bfloat16); z = torch.empty_like(y)
 pm = pack.pack_swin_mlp(torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
                         torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev))
 FOLD = os.environ.get("FOLD")            # FOLD=1: the folded-adjust variant (swin_mlp_adjust), unset: plain MLP
-if FOLD is not None:
+if FOLD == "res":                     # FOLD=res: adjust5 + residual folded in (swin_mlp_conv_res), C=308 H=308
+    pm = pack.pack_swin_mlp_conv_res(torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
+                                     torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev),
+                                     torch.randn(180, C, device=dev) * 0.05, torch.randn(180, device=dev), 0.2)
+    slab = torch.randn(M, 320, device=dev).to(torch.bfloat16); st_s = torch.zeros(M, 12, 2, device=dev)
+elif FOLD is not None:
     pm = pack.pack_swin_mlp(torch.randn(H, C, device=dev) * 0.05, torch.randn(H, device=dev), torch.ones(C, device=dev),
                             torch.zeros(C, device=dev), 1e-5, torch.randn(C, H, device=dev) * 0.05, torch.randn(C, device=dev),
                             torch.randn(32, C, device=dev) * 0.05, torch.randn(32, device=dev))
@@ -18,6 +23,7 @@ if FOLD is not None:
 stats = torch.zeros(M, 2, 2, device=dev)
 yf = y[:, :C].float(); stats[:, 0, 0] = yf.sum(1); stats[:, 0, 1] = (yf * yf).sum(1)
 run = (lambda: ops.swin_mlp(y, C, pm, z, stats_in=(stats, 2))) if FOLD is None else \
+    (lambda: ops.swin_mlp_conv_res(y, C, pm, slab, slab, stats_in=(stats, 2), stats_out=(st_s, 0))) if FOLD == "res" else \
     (lambda: ops.swin_mlp_adjust(y, C, pm, slab, C, stats_in=(stats, 2), stats_out=(st_s, 2)))
 run(); torch.cuda.synchronize()
 trace = torch.zeros(4, 8, 64, 8, dtype=torch.int64, device=dev)
