@@ -9,6 +9,19 @@
 
 namespace adsr {
 
+// Opt-in dynamic shared memory of a kernel: only ever RAISED.  The limit is per-function state, not part of a launch: a launcher that
+// sets it to each launch's own size leaves the LAST size behind, and a tool that re-launches the kernel nodes of a captured CUDA graph
+// one by one (ncu) then fails the nodes that need more than the last captured launch did.
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes) {
+    cudaFuncAttributes attr;
+    const cudaError_t e = cudaFuncGetAttributes(&attr, kernel);
+    if (e != cudaSuccess) return e;
+    if (attr.maxDynamicSharedSizeBytes >= bytes) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+
 // Programmatic dependent launch (PDL): the kernel may become resident while the previous kernel of the stream is still draining; it
 // must execute pdl_wait() before touching anything the previous kernel wrote (or still reads).  Used by the three kernels of DRN's
 // RCAB chain (320 of the 333 launches of a DRN-L step), whose prologues (barrier init, TMEM allocation, resident weights) then

@@ -415,7 +415,7 @@ int launch_attn64(const AttnParams& p, cudaStream_t stream) {
     const int nbias = (2 * p.ws - 1) * (2 * p.ws - 1);
     const size_t smem = static_cast<size_t>(64) * (3 * HPC * HDP + 8) * 2 + 2 * 64 * 4 + static_cast<size_t>(HPC) * nbias * 4;
     if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(window_attn64_kernel<KD, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        if (ensure_dynamic_smem(window_attn64_kernel<KD, HPC>, static_cast<int>(smem)) != cudaSuccess)
             return ADSR_ERR_CUDA;
     }
     dim3 grid((p.total_slots + 63) / 64, p.nH / HPC);
@@ -438,7 +438,7 @@ int launch_attn(const AttnParams& p, cudaStream_t stream) {
     const size_t smem = 3 * 64 * (HDP + 8) * 2 + 6 * 64 * 4 + static_cast<size_t>(nbias) * 4;
     if (smem > 200 * 1024) return ADSR_ERR_BAD_SHAPE;
     if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(window_attn_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        if (ensure_dynamic_smem(window_attn_kernel<KD>, static_cast<int>(smem)) != cudaSuccess)
             return ADSR_ERR_CUDA;
     }
     dim3 grid((p.total_slots + 63) / 64, p.nH);

@@ -512,7 +512,7 @@ int launch_window_attention_tc(const void* qkv, long long ldq, void* out, long l
     if (p.nbuf < 2) return ADSR_ERR_BAD_SHAPE;
     const int smem_bytes = p.nbuf * 3 * p.pan * kPanelBytes + fixed;
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-    if (cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
+    if (ensure_dynamic_smem(window_attn_tc_kernel, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
     window_attn_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
 }

@@ -510,7 +510,7 @@ int launch_window_attention_tc16(const void* qkv, long long ldq, void* out, long
     const int smem_bytes = p.nbuf * (2 * p.pan * 256 * 128 + 2 * p.pan * 128 * 128) + 2 * kStageBytes + 4 * kTabCopy * 4 + 2 * 512 * 4 +
                            static_cast<int>(sizeof(Bars16)) + 128 + 64;
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
-    if (cudaFuncSetAttribute(window_attn16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
+    if (ensure_dynamic_smem(window_attn16_tc_kernel, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
     window_attn16_tc_kernel<<<p.n_slots * nH, kThreads, smem_bytes, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
 }

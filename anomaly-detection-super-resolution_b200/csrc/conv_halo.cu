@@ -297,7 +297,7 @@ int launch_conv_halo(ConvHaloParams& p, const void* in, long long ld_in, int num
     if (encode_tmap_nhwc_box3_bf16(&p.tmap_in, in, p.B, p.H, p.W, k8, ld_in, 64, p.Wh, p.box_rows) != ADSR_OK) return ADSR_ERR_CUDA;
     if (p.tail && encode_tmap_nhwc_box3_bf16(&p.tmap_tail, in, p.B, p.H, p.W, k8, ld_in, 16, p.Wh, p.box_rows) != ADSR_OK) return ADSR_ERR_CUDA;
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-    if (cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
+    if (ensure_dynamic_smem(conv_halo_kernel, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
     // every global access that depends on (or could disturb) the previous kernel sits behind the loader's pdl_wait(): the A tiles,
     // hence the MMAs, hence the epilogue's stores
     return launch_pdl(conv_halo_kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem_bytes), stream, p) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;

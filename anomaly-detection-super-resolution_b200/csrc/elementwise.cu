@@ -587,7 +587,7 @@ extern "C" int adsr_conv_last_quant(const void* in, int64_t ld_in, int B, int H,
     if (Cin == kClCin && (W % 4) == 0) {
         static bool attr_set = false;
         if (!attr_set) {
-            if (cudaFuncSetAttribute(conv_last_quant_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClSmemBytes) != cudaSuccess)
+            if (ensure_dynamic_smem(conv_last_quant_tiled_kernel, kClSmemBytes) != cudaSuccess)
                 return ADSR_ERR_CUDA;
             attr_set = true;
         }

@@ -354,7 +354,7 @@ int launch_score(adsr::ScoreParams& p, int B, const int32_t* host_ws_list, int n
     const size_t fast_smem = (32 + kFastWorkers * (2 * 5 * 4 + 2 * 5 * static_cast<size_t>(p.W + 1))) * sizeof(double) +
                              2 * static_cast<size_t>(p.H) * p.W * sizeof(float);
     if (p.W <= 128 && fast_smem <= 227 * 1024 && n_ws > 0) {
-        if (cudaFuncSetAttribute(score_images_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fast_smem)) != cudaSuccess)
+        if (ensure_dynamic_smem(score_images_fast_kernel, static_cast<int>(fast_smem)) != cudaSuccess)
             return ADSR_ERR_CUDA;
         // a CTA costs ~0.3 units (gray planes + MSE) + one unit per window size of its busiest worker; with few images (DRN-L's
         // batch of 64 fills 64 of 148 SMs) two CTAs per image halve the sweep, with many (256) the extra waves would cost more
@@ -376,7 +376,7 @@ int launch_score(adsr::ScoreParams& p, int B, const int32_t* host_ws_list, int n
     const int threads = ((p.W + 31) / 32) * 32;
     const size_t smem = (32 + 2 * 5 * 32 + 2 * 5 * static_cast<size_t>(p.W + 1)) * sizeof(double);
     if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(score_images_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+        if (ensure_dynamic_smem(score_images_kernel, static_cast<int>(smem)) != cudaSuccess)
             return ADSR_ERR_CUDA;
     }
     dim3 grid(n_ws + 1, B);

@@ -908,7 +908,7 @@ int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream) {
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     auto launch = [&](auto kernel) -> int {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
+        if (ensure_dynamic_smem(kernel, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
         return launch_pdl(kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem_bytes), stream, p) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };
     if (p.trace != nullptr) return p.fuse_proj ? launch(swin_attn_kernel<true, true>) : launch(swin_attn_kernel<true, false>);

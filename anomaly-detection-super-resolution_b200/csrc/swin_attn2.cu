@@ -578,7 +578,7 @@ int launch_swin_attn2(SwinAttnParams& p, int num_sms, cudaStream_t stream) {
     const int smem_bytes = p.ks * kPanelBytes + 4 * p.pan * kPanelBytes + p.w_slots * p.w_slot_bytes + fixed_smem_bytes2(p.nH, p.hdp);
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-    if (cudaFuncSetAttribute(swin_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
+    if (ensure_dynamic_smem(swin_attn2_kernel, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
     return launch_pdl(swin_attn2_kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem_bytes), stream, p) == cudaSuccess ? ADSR_OK
                                                                                                                                  : ADSR_ERR_LAUNCH;
 }

@@ -771,7 +771,7 @@ int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, lon
     p.m_tiles = (p.M + 127) / 128;
     const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
     auto launch = [&](auto kernel) -> int {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
+        if (ensure_dynamic_smem(kernel, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
         return launch_pdl(kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem_bytes), stream, p) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };
     return p.trace != nullptr ? launch(swin_mlp_kernel<true>) : launch(swin_mlp_kernel<false>);

@@ -648,7 +648,7 @@ int launch_tc_gemm(TcGemmParams& p, int num_sms, cudaStream_t stream) {
         }
     }
     auto launch = [&](auto kernel) -> int {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return ADSR_ERR_CUDA;
+        if (ensure_dynamic_smem(kernel, kSmemBytes) != cudaSuccess) return ADSR_ERR_CUDA;
         kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(p);
         return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };

@@ -461,7 +461,7 @@ tc_gemm_manual_kernel(const __grid_constant__ TcGemmParams p) {
 
 int launch_tc_gemm_manual(const TcGemmParams& p, int grid, cudaStream_t stream) {
     auto launch = [&](auto kernel, int threads) -> int {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return ADSR_ERR_CUDA;
+        if (ensure_dynamic_smem(kernel, kSmemBytes) != cudaSuccess) return ADSR_ERR_CUDA;
         kernel<<<grid, threads, kSmemBytes, stream>>>(p);
         return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };

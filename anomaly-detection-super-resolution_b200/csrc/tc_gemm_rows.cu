@@ -375,7 +375,7 @@ int launch_tc_gemm_rows(TcGemmParams& g, int num_sms, cudaStream_t stream) {
     const int smem_bytes = rp.n_abuf * a_bytes + 2 * rp.n_slots * kPanelBytes + fixed;
     const int grid = g.m_tiles < num_sms ? g.m_tiles : num_sms;
     auto launch = [&](auto kernel) -> int {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
+        if (ensure_dynamic_smem(kernel, smem_bytes) != cudaSuccess) return ADSR_ERR_CUDA;
         return launch_pdl(kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem_bytes), stream, rp) == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     };
     switch (g.act) {
