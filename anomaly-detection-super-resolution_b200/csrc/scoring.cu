@@ -205,13 +205,19 @@ __global__ void __launch_bounds__(1024) score_images_kernel(const ScoreParams p)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Fast path (images up to 128 columns whose two gray planes fit shared memory: the evaluator's 128 x 128 crops):
-// ONE CTA per image.  The 1024 threads first turn the pair into fp32 gray planes in shared memory (and reduce the MSE on
-// the way), then split into 8 workers of 128 threads; worker k runs the running-sum / prefix-sum SSIM of window sizes
-// k, k + 8, ... on the shared planes, synchronising only inside the worker (named barriers).  Same arithmetic, in the same
-// order, as score_images_kernel -- but the image is fetched and converted once instead of once per window size.
-constexpr int kFastWorkers = 8;
+// ONE CTA of 512 threads per image.  The threads first turn the pair into fp32 gray planes in shared memory (and reduce the
+// MSE on the way), then every WARP runs the running-sum / prefix-sum SSIM of one window size (w, w + 16, ...) on the shared
+// planes: a lane owns 4 adjacent columns, so the row's prefix sums are a local 4-element prefix + ONE warp scan per quantity
+// and the warp never leaves itself (no barriers; the round-1 layout -- 8 workers of 128 threads, one column per thread -- spent
+// 73 % of the issue slots on 4x as many scan steps, two named barriers per row and the cross-warp bases, and 14 window sizes
+// on 8 workers meant two rounds: 1.6 ms per 256 images).  The prefix rows carry one pad slot per 16 so that the stride-4 accesses
+// of a warp are bank-conflict free.  Sums are fp64 in a fixed order (deterministic; same formulas as score_images_kernel).
+constexpr int kFastWarps = 16;
+constexpr int kFastThreads = kFastWarps * 32;
 
-__global__ void __launch_bounds__(1024, 1) score_images_fast_kernel(const ScoreParams p) {
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }      // prefix-array slot of logical index i
+
+__global__ void __launch_bounds__(kFastThreads, 1) score_images_fast_kernel(const ScoreParams p) {
     const int H = p.H, W = p.W, C = p.C, n_ws = p.n_ws;
     extern __shared__ double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -219,14 +225,14 @@ __global__ void __launch_bounds__(1024, 1) score_images_fast_kernel(const ScoreP
     const int part = blockIdx.y, nparts = gridDim.y;                    // small batches: the window sizes of an image split over CTAs
     const long long srb = static_cast<long long>(b) * p.sr.sb, hrb = static_cast<long long>(b) * p.hr.sb;
     double* red = sm;                                                   // [32]
-    double* wbase = sm + 32;                                            // per worker: wtot [2][5][4], pref [2][5][W+1]
-    const int wstride = 2 * 5 * 4 + 2 * 5 * (W + 1);
-    float* gx = reinterpret_cast<float*>(wbase + kFastWorkers * wstride);   // HR gray plane
+    const int prow = pidx(W) + 1;                                       // slots of one prefix row (logical indices 0 .. W)
+    double* pref = sm + 32 + warp * 5 * prow;                           // per warp: [5][prow]
+    float* gx = reinterpret_cast<float*>(sm + 32 + kFastWarps * 5 * prow);   // HR gray plane
     float* gy = gx + H * W;                                             // SR gray plane
 
     // ---- gray planes + MSE
     double acc_mse = 0.0;
-    for (int idx = tid; idx < H * W; idx += 1024) {
+    for (int idx = tid; idx < H * W; idx += kFastThreads) {
         const int r = idx / W, c = idx - r * W;
         const long long oh = hrb + r * p.hr.sr + c * p.hr.sc, os = srb + r * p.sr.sr + c * p.sr.sc;
         gx[idx] = gray_at(p.hr, oh, C);
@@ -241,41 +247,60 @@ __global__ void __launch_bounds__(1024, 1) score_images_fast_kernel(const ScoreP
     __syncthreads();
     if (tid == 0 && part == 0) {
         double t = 0;
-        for (int w = 0; w < 32; ++w) t += red[w];
+        for (int w = 0; w < kFastWarps; ++w) t += red[w];
         const double mse = t / (static_cast<double>(H) * W * C);
         p.scores[static_cast<long long>(b) * (n_ws + 2) + n_ws] = mse;
         p.scores[static_cast<long long>(b) * (n_ws + 2) + n_ws + 1] =
             mse == 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : 10.0 * log10(p.psnr_peak2 / mse);
     }
 
-    // ---- SSIM sweep: worker = 4 warps, thread = column
-    const int worker = tid >> 7, col = tid & 127, wwarp = warp & 3;
-    const bool active = col < W;
-    double* wtot = wbase + worker * wstride;                            // [2][5][4]
-    double* pref = wtot + 2 * 5 * 4;                                    // [2][5][W + 1]
+    // ---- SSIM sweep: warp = window size, lane = 4 adjacent columns
+    const int c0 = 4 * lane;
+    const bool w4 = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(gx) | reinterpret_cast<uintptr_t>(gy)) & 15) == 0;
     const bool zp = p.zero_pad != 0;
     const double C1 = p.C1, C2 = p.C2;
-    for (int j = worker + kFastWorkers * part; j < n_ws; j += kFastWorkers * nparts) {
+    for (int j = warp + kFastWarps * part; j < n_ws; j += kFastWarps * nparts) {
         const int ws = p.wl.ws[j], pad = ws / 2;
         const double inv_n = 1.0 / (static_cast<double>(ws) * ws);
-        double v[5] = {0, 0, 0, 0, 0};
-        auto add_row = [&](int r, double sign) {
-            const float x = gx[r * W + col], y = gy[r * W + col];
-            v[0] += sign * static_cast<double>(x);
-            v[1] += sign * static_cast<double>(y);
-            v[2] += sign * static_cast<double>(x * x);
-            v[3] += sign * static_cast<double>(y * y);
-            v[4] += sign * static_cast<double>(x * y);
-        };
-        if (active)
-            for (int r = -pad; r <= pad; ++r) {
-                if (zp) { if (r >= 0 && r < H) add_row(r, 1.0); }
-                else add_row(reflect_idx(r, H), 1.0);
+        double v[4][5];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) v[k][q] = 0.0;
+        auto add_row = [&](int r, double sign) {                       // columns >= W contribute nothing
+            float xs[4] = {0.f, 0.f, 0.f, 0.f}, ys[4] = {0.f, 0.f, 0.f, 0.f};
+            if (w4) {                                                  // one 16-byte load per plane (4 scalar loads at a 16-byte lane pitch are 4-way bank conflicted)
+                if (c0 < W) {
+                    const float4 a = *reinterpret_cast<const float4*>(gx + r * W + c0), c = *reinterpret_cast<const float4*>(gy + r * W + c0);
+                    xs[0] = a.x; xs[1] = a.y; xs[2] = a.z; xs[3] = a.w;
+                    ys[0] = c.x; ys[1] = c.y; ys[2] = c.z; ys[3] = c.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c0 + k < W) { xs[k] = gx[r * W + c0 + k]; ys[k] = gy[r * W + c0 + k]; }
             }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (c0 + k < W) {
+                    const float x = xs[k], y = ys[k];
+                    v[k][0] += sign * static_cast<double>(x);
+                    v[k][1] += sign * static_cast<double>(y);
+                    v[k][2] += sign * static_cast<double>(x * x);
+                    v[k][3] += sign * static_cast<double>(y * y);
+                    v[k][4] += sign * static_cast<double>(x * y);
+                }
+            }
+        };
+        for (int r = -pad; r <= pad; ++r) {
+            if (zp) { if (r >= 0 && r < H) add_row(r, 1.0); }
+            else add_row(reflect_idx(r, H), 1.0);
+        }
+        if (lane == 0)
+            for (int q = 0; q < 5; ++q) pref[q * prow] = 0.0;          // P[0] = 0 (never overwritten)
         double acc = 0.0;
         for (int i = 0; i < H; ++i) {
-            const int bufi = i & 1;
-            if (i > 0 && active) {
+            if (i > 0) {
                 if (zp) {
                     if (i + pad < H) add_row(i + pad, 1.0);
                     if (i - pad - 1 >= 0) add_row(i - pad - 1, -1.0);
@@ -284,54 +309,50 @@ __global__ void __launch_bounds__(1024, 1) score_images_fast_kernel(const ScoreP
                     add_row(reflect_idx(i - pad - 1, H), -1.0);
                 }
             }
-            double s5[5];
+            // inclusive prefix sums of the 5 column-sum rows: local over my 4 columns, one warp scan of the lane totals
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
-                double t = active ? v[q] : 0.0;
+                const double l0 = v[0][q], l1 = l0 + v[1][q], l2 = l1 + v[2][q], l3 = l2 + v[3][q];
+                double t = l3;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const double u = shfl_up_d(t, d);
                     if (lane >= d) t += u;
                 }
-                s5[q] = t;
-                if (lane == 31) wtot[(bufi * 5 + q) * 4 + wwarp] = t;
+                const double base = t - l3;                            // sum of the lanes to my left
+                double* Pq = pref + q * prow;
+                if (c0 + 0 < W) Pq[pidx(c0 + 1)] = base + l0;
+                if (c0 + 1 < W) Pq[pidx(c0 + 2)] = base + l1;
+                if (c0 + 2 < W) Pq[pidx(c0 + 3)] = base + l2;
+                if (c0 + 3 < W) Pq[pidx(c0 + 4)] = base + l3;
             }
-            named_bar_sync(1 + worker, 128);
-            double* P = pref + bufi * 5 * (W + 1);
+            __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                double base = 0.0;
-                for (int w = 0; w < wwarp; ++w) base += wtot[(bufi * 5 + q) * 4 + w];
-                if (active) P[q * (W + 1) + col + 1] = s5[q] + base;
-                if (col == 0) P[q * (W + 1)] = 0.0;
-            }
-            named_bar_sync(1 + worker, 128);
-            if (active) {
-                const int lo = col - pad, hi = col + pad;
-                const int a0 = lo < 0 ? 0 : lo, a1 = hi > W - 1 ? W - 1 : hi;
-                double box[5];
+            for (int k = 0; k < 4; ++k) {
+                const int col = c0 + k;
+                if (col < W) {
+                    const int lo = col - pad, hi = col + pad;
+                    const int a0 = lo < 0 ? 0 : lo, a1 = hi > W - 1 ? W - 1 : hi;
+                    double box[5];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const double* Pq = P + q * (W + 1);
-                    double t = Pq[a1 + 1] - Pq[a0];
-                    if (!zp) {
-                        if (lo < 0) t += Pq[-lo + 1] - Pq[1];
-                        if (hi > W - 1) t += Pq[W - 1] - Pq[2 * (W - 1) - hi];
+                    for (int q = 0; q < 5; ++q) {
+                        const double* Pq = pref + q * prow;
+                        double t = Pq[pidx(a1 + 1)] - Pq[pidx(a0)];
+                        if (!zp) {
+                            if (lo < 0) t += Pq[pidx(-lo + 1)] - Pq[pidx(1)];                       // reflected columns 1 .. -lo
+                            if (hi > W - 1) t += Pq[pidx(W - 1)] - Pq[pidx(2 * (W - 1) - hi)];      // reflected columns 2(W-1)-hi .. W-2
+                        }
+                        box[q] = t * inv_n;
                     }
-                    box[q] = t * inv_n;
+                    const double mu1 = box[0], mu2 = box[1];
+                    const double s1 = box[2] - mu1 * mu1, s2 = box[3] - mu2 * mu2, s12 = box[4] - mu1 * mu2;
+                    acc += ((2.0 * mu1 * mu2 + C1) * (2.0 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2));
                 }
-                const double mu1 = box[0], mu2 = box[1];
-                const double s1 = box[2] - mu1 * mu1, s2 = box[3] - mu2 * mu2, s12 = box[4] - mu1 * mu2;
-                acc += ((2.0 * mu1 * mu2 + C1) * (2.0 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2));
             }
+            __syncwarp();                                              // the next row overwrites the prefix rows
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        named_bar_sync(1 + worker, 128);                                // everyone is done with wtot of the last row
-        if (lane == 0) wtot[wwarp] = acc;
-        named_bar_sync(1 + worker, 128);
-        if (col == 0)
-            p.scores[static_cast<long long>(b) * (n_ws + 2) + j] = (wtot[0] + wtot[1] + wtot[2] + wtot[3]) / (static_cast<double>(H) * W);
-        named_bar_sync(1 + worker, 128);
+        if (lane == 0) p.scores[static_cast<long long>(b) * (n_ws + 2) + j] = acc / (static_cast<double>(H) * W);
     }
 }
 
@@ -351,13 +372,13 @@ int launch_score(adsr::ScoreParams& p, int B, const int32_t* host_ws_list, int n
     }
     p.n_ws = n_ws;
     // one CTA per image when the gray planes fit shared memory (the evaluator's 128 x 128 crops)
-    const size_t fast_smem = (32 + kFastWorkers * (2 * 5 * 4 + 2 * 5 * static_cast<size_t>(p.W + 1))) * sizeof(double) +
+    const size_t fast_smem = (32 + kFastWarps * 5 * static_cast<size_t>(p.W + (p.W >> 4) + 1)) * sizeof(double) +
                              2 * static_cast<size_t>(p.H) * p.W * sizeof(float);
     if (p.W <= 128 && fast_smem <= 227 * 1024 && n_ws > 0) {
         if (ensure_dynamic_smem(score_images_fast_kernel, static_cast<int>(fast_smem)) != cudaSuccess)
             return ADSR_ERR_CUDA;
-        // a CTA costs ~0.3 units (gray planes + MSE) + one unit per window size of its busiest worker; with few images (DRN-L's
-        // batch of 64 fills 64 of 148 SMs) two CTAs per image halve the sweep, with many (256) the extra waves would cost more
+        // a CTA costs ~0.3 units (gray planes + MSE) + one unit per window size of its busiest warp; with few images and more
+        // window sizes than warps two CTAs per image halve the sweep, with many images the extra waves would cost more
         static int sms = 0;
         if (sms == 0) {
             int dev = 0;
@@ -366,11 +387,11 @@ int launch_score(adsr::ScoreParams& p, int B, const int32_t* host_ws_list, int n
         }
         auto cost = [&](int parts) {
             const int waves = (B * parts + sms - 1) / sms;
-            const int per_worker = (n_ws + kFastWorkers * parts - 1) / (kFastWorkers * parts);
+            const int per_worker = (n_ws + kFastWarps * parts - 1) / (kFastWarps * parts);
             return waves * (0.3 + per_worker);
         };
-        const int parts = (n_ws > kFastWorkers && cost(2) < cost(1)) ? 2 : 1;
-        score_images_fast_kernel<<<dim3(B, parts), 1024, fast_smem, st>>>(p);
+        const int parts = (n_ws > kFastWarps && cost(2) < cost(1)) ? 2 : 1;
+        score_images_fast_kernel<<<dim3(B, parts), kFastThreads, fast_smem, st>>>(p);
         return cudaGetLastError() == cudaSuccess ? ADSR_OK : ADSR_ERR_LAUNCH;
     }
     const int threads = ((p.W + 31) / 32) * 32;
