@@ -259,6 +259,7 @@ static long long* g_attn_trace = nullptr;
 extern "C" void adsr_debug_set_attn_trace(void* device_buffer) { g_attn_trace = static_cast<long long*>(device_buffer); }
 
 extern "C" void adsr_debug_set_mlp_acc1(int max_buffers) { g_mlp_acc1_max = max_buffers; }
+extern "C" void adsr_debug_set_attn_pipe(int enabled) { g_attn_pipe = enabled; }
 
 static int g_swin_attn2 = 1;
 extern "C" void adsr_debug_set_swin_attn2(int enabled) { g_swin_attn2 = enabled; }

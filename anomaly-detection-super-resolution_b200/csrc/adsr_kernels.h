@@ -159,6 +159,7 @@ struct SwinMlpParams {
 };
 int swin_mlp_fixed_smem_bytes(int hidden_padded, int n2);
 extern int g_mlp_acc1_max;
+extern int g_attn_pipe;
 int launch_swin_mlp(SwinMlpParams& p, const void* y, long long ldy, void* z, long long ldz, int num_sms, cudaStream_t stream);
 
 // ---- fused attention half of a Swin block (swin_attn.cu)
@@ -191,6 +192,7 @@ struct SwinAttnParams {
     int rsz, nreg;            // TMEM: columns per head region, number of regions (2 = next head's q|k|v runs one head ahead)
     int col_o;                // TMEM column of O (fuse_proj: behind the region; else O overlays the region's q columns)
     int col_acc;              // fuse_proj with spare TMEM: separate q|k|v accumulator columns, else -1 (accumulators = the region)
+    int pipe;                 // heads pipelined: convert(h + 1) between softmax(h) and normalise(h) (needs col_acc >= 0; second v panel)
     int early_setup;          // per-row tile set-up (token, mask bits, LayerNorm statistics) one tile ahead, under the first S wait
     int w_slots, w_slot_bytes;   // qkv weight ring
     int p_slots, p_slot_bytes;   // proj weight ring (fuse_proj)

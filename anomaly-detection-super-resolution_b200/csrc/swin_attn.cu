@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
     uint8_t* x_buf = smem;                                             // [ks panels] raw x rows of the tile (A operand of qkv)
     uint8_t* k_buf = x_buf + x_bytes;                                  // [pan panels] k of the current head (K-major B operand of S)
     uint8_t* v_buf = k_buf + op_bytes;                                 // [pan panels] v of the current head (MN-major B operand of P V)
-    uint8_t* ring = v_buf + op_bytes;                                  // qkv slabs: w_slots x w_slot_bytes
+    uint8_t* ring = v_buf + op_bytes * (p.pipe ? 2 : 1);               // qkv slabs: w_slots x w_slot_bytes (pipe: the v panel alternates)
     uint8_t* pring = ring + p.w_slots * p.w_slot_bytes;                // proj slabs: p_slots x p_slot_bytes
     uint8_t* ident_s = pring + p.p_slots * p.p_slot_bytes;             // FUSE: [16 x 64] bf16 operand slab holding the 16 x 16 identity
     float* s_bq = reinterpret_cast<float*>(ident_s + (FUSE ? kIdentBytes : 0));     // [nqkv] folded qkv bias, per-head q|k|v order
@@ -113,9 +113,10 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
     float* s_bias = s_bp + p.cp;                                       // [nH][232] rel-pos table * log2(e)
     int* s_tok = reinterpret_cast<int*>(s_bias + p.nH * 232);          // [2][128] token row of each tile row
     float* s_max = reinterpret_cast<float*>(s_tok + 256);              // [4][128] partial row maxima
-    float* s_sum = s_max + 512;                                        // [4][128] partial row sums
-    float2* s_stat = reinterpret_cast<float2*>(s_max);                 // [4][128] (sum, sumsq) partials of y -- aliases s_max | s_sum
-    AttnBlockBarriers* bars = reinterpret_cast<AttnBlockBarriers*>(s_sum + 512);
+    float* s_sum = s_max + 512;                                        // [2][4][128] partial row sums, by head parity (pipe: a warp may be in
+                                                                       // the next head's softmax while another still normalises this one)
+    float2* s_stat = reinterpret_cast<float2*>(s_max);                 // [4][128] (sum, sumsq) partials of y -- aliases s_max | s_sum[0]
+    AttnBlockBarriers* bars = reinterpret_cast<AttnBlockBarriers*>(s_sum + 1024);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -184,6 +185,8 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         if (lane == 0) tma_prefetch_desc(&p.tmap_x);
         const int R = p.box_r, nb = 8 / R;
         const int combos = 2 * nb * nb;
+        int qslot = 0;                                                 // pipelined heads: consumer cursor of the qkv weight ring
+        uint32_t qph = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const int tile = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
             tr_ev<TRACE>(p.trace, 2, it, 8, 0);
@@ -203,6 +206,50 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
             }
             __syncwarp();
             tr_ev<TRACE>(p.trace, 2, it, 8, 2);
+            if (FUSE && p.pipe) {
+                // pipelined heads: this warp also issues the q|k|v MMAs of the tile it has just requested (accumulator columns of
+                // their own; head g may start once the conversion warps have read head g - 1 out of them)
+                mbar_wait(&bars->x_full, static_cast<uint32_t>(it) & 1);
+                const uint64_t x_desc = umma_desc_k_sw128(smem_u32(x_buf));
+                const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring));
+                const uint32_t slot_units = static_cast<uint32_t>(p.w_slot_bytes >> 4);
+                const uint32_t acc = tmem + static_cast<uint32_t>(p.col_acc);
+                for (int h = 0; h < p.nH; ++h) {
+                    const int g = it * p.nH + h;
+                    // head g may start once the conversion warps have read head g - 1 out of the accumulator columns.  (Gating on "S of head
+                    // g - 1 issued / completed" instead, so that these bulk MMAs queue behind the latency-critical S, was measured slower:
+                    // 221 / 218 vs 209 us -- they then sit in front of P V.)
+                    if (g > 0) mbar_wait(&bars->qkv_ready, static_cast<uint32_t>(g - 1) & 1);
+                    tr_ev<TRACE>(p.trace, 2, it, h, 4);
+                    // (K slab, N piece) steps of 4 MMAs: one batch of 12 in a single elected region was measured at ~280 cycles per MMA
+                    for (int qs = 0; qs < p.ks; ++qs) {
+                        const int ksteps = min(4, p.k16 - 4 * qs);
+                        uint32_t dcol = 0;
+                        for (int pc = 0; pc < p.qkv_pieces; ++pc) {
+                            mbar_wait(&bars->w_full[qslot], qph);
+                            tc_fence_after_sync();
+                            if (elect_one_sync()) {
+                                const uint64_t adesc = x_desc + static_cast<uint64_t>(qs * (kPanelBytes >> 4));
+                                const uint64_t bdesc = ring_desc + static_cast<uint64_t>(static_cast<uint32_t>(qslot) * slot_units);
+                                const uint32_t idesc = idesc_m128(static_cast<uint32_t>(p.qp_rows[pc]), 0);
+                                umma_bf16(acc + dcol, adesc, bdesc, idesc, qs > 0 ? 1u : 0u);
+                                if (ksteps > 1) umma_bf16(acc + dcol, adesc + 2, bdesc + 2, idesc, 1u);
+                                if (ksteps > 2) umma_bf16(acc + dcol, adesc + 4, bdesc + 4, idesc, 1u);
+                                if (ksteps > 3) umma_bf16(acc + dcol, adesc + 6, bdesc + 6, idesc, 1u);
+                                umma_commit(&bars->w_empty[qslot]);
+                                if (qs == p.ks - 1 && pc == p.qkv_pieces - 1) {
+                                    umma_commit(&bars->qkv_full[0]);
+                                    if (h == p.nH - 1) umma_commit(&bars->x_empty);      // the x tile is no longer an operand
+                                }
+                            }
+                            __syncwarp();
+                            dcol += static_cast<uint32_t>(p.qp_rows[pc]);
+                            if (++qslot == p.w_slots) { qslot = 0; qph ^= 1; }
+                        }
+                    }
+                    tr_ev<TRACE>(p.trace, 2, it, h, 5);
+                }
+            }
         }
     } else if (warp == kWLoaderWarp) {
         // ============================================================ qkv weight slabs: (head, K slab, N piece) in order, every tile
@@ -328,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
         };
         q_step = q_steps;                                              // nothing pending
 
-        if (my_tiles > 0) {
+        if (my_tiles > 0 && !(FUSE && p.pipe)) {
             mbar_wait(&bars->x_full, 0);
             qkv_begin(0, 0);
             qkv_finish();
@@ -363,14 +410,79 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
-                            umma_bf16_ts(t_o, t_s + static_cast<uint32_t>(8 * k), desc_mn_sw128(v_addr + static_cast<uint32_t>(k * 2048), kPanelBytes),
+                            umma_bf16_ts(t_o, t_s + static_cast<uint32_t>(8 * k), desc_mn_sw128(v_addr + (p.pipe ? static_cast<uint32_t>((g & 1) * op_bytes) : 0u) + static_cast<uint32_t>(k * 2048), kPanelBytes),
                                          idesc_pv, k == 0 ? 0u : 1u);
                         umma_commit(&bars->o_full);
                     }
                     __syncwarp();
                 };
                 tr_ev<TRACE>(p.trace, 0, it, h, 0);
-                if (FUSE) {
+                if (FUSE && p.pipe) {
+                    // pipelined heads (separate q|k|v accumulator columns): S of head h + 1 goes in front of the proj MMAs of head h, right
+                    // behind P V of head h -- the conversion warps have turned head h + 1 around by then.  The q|k|v MMAs are issued by
+                    // the x-loader warp: with them this warp's issue time per head (3.7 k cycles) was the bottleneck of the pipeline
+                    auto issue_proj_shortcut = [&]() {
+                        // the accumulator starts as the shortcut: Y[:, 16 g .. 16 g + 15] = x[:, same columns] * I (x tile still
+                        // resident; bf16 values enter the fp32 accumulator exactly), the proj MMAs of every head accumulate on top
+                        mbar_wait(&bars->proj_free, (static_cast<uint32_t>(it) & 1) ^ 1);
+                        tc_fence_after_sync();
+                        if (elect_one_sync()) {
+                            const uint64_t idesc_b = umma_desc_k_sw128(smem_u32(ident_s));
+                            const uint32_t idesc16 = idesc_m128(16u, 0);
+                            const int n16 = p.cp >> 4;
+#pragma unroll
+                            for (int gcol = 0; gcol < 20; ++gcol)             // cp <= 320
+                                if (gcol < n16)
+                                    umma_bf16(tmem + static_cast<uint32_t>(16 * gcol),
+                                              x_desc + static_cast<uint64_t>((gcol >> 2) * (kPanelBytes >> 4) + (gcol & 3) * 2), idesc_b, idesc16, 0u);
+                        }
+                        __syncwarp();
+                    };
+                    if (h == 0) {
+                        mbar_wait(&bars->qkv_ready, par);
+                        tr_ev<TRACE>(p.trace, 0, it, h, 2);
+                        issue_s();
+                        issue_proj_shortcut();
+                    }
+                    mbar_wait(&bars->p_ready, par);
+                    tr_ev<TRACE>(p.trace, 0, it, h, 3);
+                    issue_pv();
+                    tr_ev<TRACE>(p.trace, 0, it, h, 4);
+                    if (next_in_tile) {
+                        // S of the next head: same code as issue_s() with the next head's counters (its region is the same one)
+                        mbar_wait(&bars->qkv_ready, par ^ 1);
+                        tc_fence_after_sync();
+                        if (elect_one_sync()) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (u < uq)
+                                    umma_bf16_ts(t_s, t_r + static_cast<uint32_t>(16 * u),
+                                                 k_desc + static_cast<uint64_t>(((u >> 2) * kPanelBytes + (u & 3) * 32) >> 4), idesc_s, u == 0 ? 0u : 1u);
+                            umma_commit(&bars->s_full);
+                        }
+                        __syncwarp();
+                    }
+                    tr_ev<TRACE>(p.trace, 0, it, h, 1);
+                    ensure_o(g);
+                    uint32_t dcol = 0;
+                    for (int pc = 0; pc < p.n_pp; ++pc) {
+                        mbar_wait(&bars->p_full[pslot], pph);
+                        tc_fence_after_sync();
+                        if (elect_one_sync()) {
+                            const uint64_t bdesc = pring_desc + static_cast<uint64_t>(static_cast<uint32_t>(pslot) * pslot_units);
+                            const uint32_t idesc = idesc_m128(static_cast<uint32_t>(p.pp_rows[pc]), 0);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)                // fuse_proj: hdp <= 64
+                                if (u < uq) umma_bf16_ts(tmem + dcol, t_o + static_cast<uint32_t>(16 * u), bdesc + 2 * u, idesc, 1u);
+                            umma_commit(&bars->p_empty[pslot]);
+                            if (h == p.nH - 1 && pc == p.n_pp - 1) umma_commit(&bars->proj_full);
+                        }
+                        __syncwarp();
+                        dcol += static_cast<uint32_t>(p.pp_rows[pc]);
+                        if (++pslot == p.p_slots) { pslot = 0; pph ^= 1; }
+                    }
+                    tr_ev<TRACE>(p.trace, 0, it, h, 5);
+                } else if (FUSE) {
                     // one region: S / P overlay the k|v accumulators, so the next head's q|k|v follows P V in the pipe; it runs
                     // while the epilogue normalises O, whose bf16 copy then feeds  Y += O_h Wp_h^T  (persistent accumulator)
                     mbar_wait(&bars->qkv_ready, par);
@@ -564,7 +676,12 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
             if (grp == 0) s_tok[mb * 128 + r] = tok;
             const float2 rstd2 = f2_(rstd, rstd), nrm2 = f2_(nrm, nrm);
 
-            for (int h = 0; h < p.nH; ++h) {
+            // The three stages of a head.  Usual order: convert(h), softmax(h), normalise(h).  Pipelined order (p.pipe: blocks whose
+            // next q|k|v has accumulator columns of its own, so it is complete while the softmax runs): convert(h + 1) goes BETWEEN
+            // softmax(h) and normalise(h) -- it runs under P V of head h (q columns and the k panel are dead once S has completed,
+            // the v panel alternates), and normalise(h) then runs under S of head h + 1: on the clock64 timeline of block 1 the
+            // conversion warps waited 0.46 k cycles for S and 0.54 k for P V in every head of 4.0 k.
+            auto stage_convert = [&](int h) {
                 const int g = it * p.nH + h;
                 const uint32_t par = static_cast<uint32_t>(g) & 1;
                 const int reg = (!FUSE && p.nreg == 2) ? (g & 1) : 0;
@@ -572,6 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 const uint32_t t_s = t_r + static_cast<uint32_t>(p.hdp);
                 const uint32_t t_o = FUSE ? t_base + static_cast<uint32_t>(p.col_o) : t_r;
                 const uint32_t t_acc = (FUSE && p.col_acc >= 0) ? t_base + static_cast<uint32_t>(p.col_acc) : t_r;   // q|k|v accumulators
+                (void)par; (void)t_s; (void)t_o; (void)t_acc;
                 // ---- q | k | v of head h: folded LayerNorm + bias -> bf16; q in place (TMEM), k / v into the operand panels
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 0);
                 mbar_wait(&bars->qkv_full[reg], static_cast<uint32_t>((!FUSE && p.nreg == 2) ? (g >> 1) : g) & 1);
@@ -600,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     } else {
                         const bool is_k = u < 2 * uq;
                         const int cu = u - (is_k ? uq : 2 * uq);       // unit inside the operand: columns 16 cu .. 16 cu + 15
-                        const uint32_t rowa = (is_k ? k_row : v_row) + static_cast<uint32_t>((cu >> 2) * kPanelBytes);
+                        const uint32_t rowa = (is_k ? k_row : v_row + (p.pipe ? static_cast<uint32_t>((g & 1) * op_bytes) : 0u)) + static_cast<uint32_t>((cu >> 2) * kPanelBytes);
                         const int c0 = (2 * cu) & 7;
                         st_shared_v4(rowa + static_cast<uint32_t>(((c0 ^ rsw) << 4)), pk[0], pk[1], pk[2], pk[3]);
                         st_shared_v4(rowa + static_cast<uint32_t>((((c0 + 1) ^ rsw) << 4)), pk[4], pk[5], pk[6], pk[7]);
@@ -613,6 +731,16 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 if (lane == 0) mbar_arrive(&bars->qkv_ready);
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 2);
 
+            };
+            auto stage_softmax = [&](int h) {
+                const int g = it * p.nH + h;
+                const uint32_t par = static_cast<uint32_t>(g) & 1;
+                const int reg = (!FUSE && p.nreg == 2) ? (g & 1) : 0;
+                const uint32_t t_r = t_base + static_cast<uint32_t>(FUSE ? p.cp : reg * p.rsz);
+                const uint32_t t_s = t_r + static_cast<uint32_t>(p.hdp);
+                const uint32_t t_o = FUSE ? t_base + static_cast<uint32_t>(p.col_o) : t_r;
+                const uint32_t t_acc = (FUSE && p.col_acc >= 0) ? t_base + static_cast<uint32_t>(p.col_acc) : t_r;   // q|k|v accumulators
+                (void)par; (void)t_s; (void)t_o; (void)t_acc;
                 // ---- softmax over my window's 64 keys, 16 per thread
                 if (early && h == 0 && it + 1 < my_tiles) row_setup(tile + static_cast<int>(gridDim.x), tok_n, mbits_n, rstd_n, nrm_n);
                 mbar_wait(&bars->s_full, par);
@@ -676,7 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                             pk[k >> 1] = pack_bf16x2(e.x, e.y);
                         }
                     }
-                    s_sum[grp * 128 + r] = acc.x + acc.y;
+                    s_sum[(g & 1) * 512 + grp * 128 + r] = acc.x + acc.y;
                     // P in place: key j of the tile -> packed column j / 2; the same keys' slots of the OTHER window get zeros
                     tmem_st8_(t_s + ((kcol0 + static_cast<uint32_t>(16 * grp)) >> 1), pk);
                     tmem_st8_zero_(t_s + (((64u - kcol0) + static_cast<uint32_t>(16 * grp)) >> 1));
@@ -687,12 +815,23 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                 if (lane == 0) mbar_arrive(&bars->p_ready);
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 4);
 
+            };
+            auto stage_normalise = [&](int h) {
+                const int g = it * p.nH + h;
+                const uint32_t par = static_cast<uint32_t>(g) & 1;
+                const int reg = (!FUSE && p.nreg == 2) ? (g & 1) : 0;
+                const uint32_t t_r = t_base + static_cast<uint32_t>(FUSE ? p.cp : reg * p.rsz);
+                const uint32_t t_s = t_r + static_cast<uint32_t>(p.hdp);
+                const uint32_t t_o = FUSE ? t_base + static_cast<uint32_t>(p.col_o) : t_r;
+                const uint32_t t_acc = (FUSE && p.col_acc >= 0) ? t_base + static_cast<uint32_t>(p.col_acc) : t_r;   // q|k|v accumulators
+                (void)par; (void)t_s; (void)t_o; (void)t_acc;
                 // ---- O = P v done: normalise; fuse_proj: pack into the persistent bf16 operand, else store the rows
                 mbar_wait(&bars->o_full, par);
                 tc_fence_after_sync();
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 5);
                 {
-                    const float inv = 1.0f / ((s_sum[r] + s_sum[128 + r]) + (s_sum[256 + r] + s_sum[384 + r]));
+                    const float* ss = s_sum + (g & 1) * 512;
+                    const float inv = 1.0f / ((ss[r] + ss[128 + r]) + (ss[256 + r] + ss[384 + r]));
                     const float2 inv2 = f2_(inv, inv);
                     for (int u = grp; u < uq; u += 4) {
                         uint32_t raw[16];
@@ -737,6 +876,20 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
                     named_bar_sync(1 + quad, 128);                       // copied out: the next head may overwrite the k panel
                 }
                 if (warp == 0) tr_ev<TRACE>(p.trace, 1, it, h, 6);
+            };
+            if (FUSE && p.pipe) {
+                stage_convert(0);
+                for (int h = 0; h < p.nH; ++h) {
+                    stage_softmax(h);
+                    if (h + 1 < p.nH) stage_convert(h + 1);
+                    stage_normalise(h);
+                }
+            } else {
+                for (int h = 0; h < p.nH; ++h) {
+                    stage_convert(h);
+                    stage_softmax(h);
+                    stage_normalise(h);
+                }
             }
 
             if (FUSE) {
@@ -836,12 +989,14 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
 }
 
 int fixed_smem_bytes(int nH, int hdp, int cp) {       // kIdentBytes is only used with fuse_proj; reserving it always keeps this simple
-    return kIdentBytes + (2 * nH * 3 * hdp + cp + nH * 232) * 4 + 256 * 4 + 2 * 512 * 4 + static_cast<int>(sizeof(AttnBlockBarriers)) + 64;
+    return kIdentBytes + (2 * nH * 3 * hdp + cp + nH * 232) * 4 + 256 * 4 + 3 * 512 * 4 + static_cast<int>(sizeof(AttnBlockBarriers)) + 64;
 }
 
 int round16(int v) { return (v + 15) / 16 * 16; }
 
 }  // namespace
+
+int g_attn_pipe = 1;                           // debug switch (adsr_debug_set_attn_pipe): 0 = heads one after the other
 
 // Static plan of the fused kernel for one block shape.  Returns 0 = not covered (use the separate kernels),
 // 1 = qkv + attention fused (out = attention rows [M, nH * hdp], proj by the row-tile GEMM), 2 = whole attention half.
@@ -864,6 +1019,9 @@ int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj) {
     // be issued as soon as S is (they no longer overwrite P) instead of after P V
     p.col_acc = (p.fuse_proj && p.cp + 2 * hdp + 128 + 3 * hdp <= 512) ? p.cp + 2 * hdp + 128 : -1;
     p.early_setup = p.col_acc >= 0 ? 1 : 0;
+    // ... and then the heads are pipelined: the conversion of head h + 1 runs under P V of head h (second v panel), the
+    // normalisation of head h under S of head h + 1
+    p.pipe = (p.col_acc >= 0 && g_attn_pipe != 0) ? 1 : 0;
     // a [3 hdp x 64] qkv slab is one ring slot and one issue step (every step costs ~400 cycles of wait / commit bookkeeping on
     // top of its MMAs, so steps are kept as large as the MMA N limit of 256 allows); 3 hdp > 256: two N pieces
     const int n3 = 3 * hdp;
@@ -883,7 +1041,7 @@ int swin_attn_plan(SwinAttnParams& p, int C, int nH, int hdp, int allow_proj) {
         p.p_slot_bytes = (p.pp_rows[0] * 128 + 1023) / 1024 * 1024;
         p.p_slots = p.n_pp;                                            // the ring holds one head's proj weights: fetched a head ahead
     }
-    const int avail = kSmemLimit - p.ks * kPanelBytes - 2 * p.pan * kPanelBytes - fixed_smem_bytes(nH, hdp, p.cp) - p.p_slots * p.p_slot_bytes;
+    const int avail = kSmemLimit - p.ks * kPanelBytes - (2 + p.pipe) * p.pan * kPanelBytes - fixed_smem_bytes(nH, hdp, p.cp) - p.p_slots * p.p_slot_bytes;
     p.w_slots = avail / p.w_slot_bytes;
     if (p.w_slots > kMaxSlots) p.w_slots = kMaxSlots;
     if (p.w_slots < 2) return 0;
@@ -903,7 +1061,7 @@ int launch_swin_attn(SwinAttnParams& p, int num_sms, cudaStream_t stream) {
     p.box_r = p.shift == 0 ? 8 : 4;
     const int st = encode_tmap_nhwc_box_bf16(&p.tmap_x, p.x, p.B, p.H, p.W, p.C, p.ldx, p.box_r);
     if (st != ADSR_OK) return st;
-    const int smem_bytes = p.ks * kPanelBytes + 2 * p.pan * kPanelBytes + p.w_slots * p.w_slot_bytes + p.p_slots * p.p_slot_bytes +
+    const int smem_bytes = p.ks * kPanelBytes + (2 + p.pipe) * p.pan * kPanelBytes + p.w_slots * p.w_slot_bytes + p.p_slots * p.p_slot_bytes +
                            fixed_smem_bytes(p.nH, p.hdp, p.cp);
     if (smem_bytes > kSmemLimit) return ADSR_ERR_BAD_SHAPE;
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;

@@ -6,6 +6,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 PKG = "anomaly-detection-super-resolution_b200"
 ops = importlib.import_module(PKG + ".ops"); pack = importlib.import_module(PKG + ".pack")
 dev = "cuda"
+if os.environ.get("PIPE"):      # PIPE=0: heads one after the other in the fused kernel (A/B of the pipelined head order)
+    import ctypes
+    _abi = importlib.import_module(PKG + "._abi"); _f = _abi.lib().adsr_debug_set_attn_pipe; _f.restype = None; _f.argtypes = [ctypes.c_int]
+    _f(int(os.environ["PIPE"]))
 B = int(os.environ.get("B", 256)); H = W = 32
 M = B * H * W
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -37,5 +37,7 @@ for it in range(3):
     print("  mma tile end: proj start %s  proj issued %s  next qkv issued %s" % tuple(rel(v) for v in t[0, it, 8, :3]))
     for h in range(heads):
         print(f"  head {h} mma: " + "  ".join(f"{names[0][k]} {rel(t[0, it, h, k])}" for k in range(5)))
+        if int(t[2, it, h, 4]) > 0:
+            print(f"  head {h} qkv issuer (x-loader warp): wait {rel(t[2, it, h, 3])}  go {rel(t[2, it, h, 4])}  all issued {rel(t[2, it, h, 5])}")
         print(f"  head {h} epi: " + "  ".join(f"{names[1][k]} {rel(t[1, it, h, k])}" for k in range(7)))
     print("  epi: wait proj_full %s  seen %s  proj epi done %s" % tuple(rel(v) for v in t[1, it, 8, :3]))
