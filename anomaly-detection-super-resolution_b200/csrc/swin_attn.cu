@@ -208,17 +208,19 @@ __global__ void __launch_bounds__(kThreads, 1) swin_attn_kernel(const __grid_con
             tr_ev<TRACE>(p.trace, 2, it, 8, 2);
             if (FUSE && p.pipe) {
                 // pipelined heads: this warp also issues the q|k|v MMAs of the tile it has just requested (accumulator columns of
-                // their own; head g may start once the conversion warps have read head g - 1 out of them)
+                // their own; head g may start once the conversion warps have read head g - 1 out of them).  The same split for the
+                // two-region attention-only plans (S / P V no longer polled between q|k|v steps) gained 1 %: not kept.
                 mbar_wait(&bars->x_full, static_cast<uint32_t>(it) & 1);
                 const uint64_t x_desc = umma_desc_k_sw128(smem_u32(x_buf));
                 const uint64_t ring_desc = umma_desc_k_sw128(smem_u32(ring));
                 const uint32_t slot_units = static_cast<uint32_t>(p.w_slot_bytes >> 4);
-                const uint32_t acc = tmem + static_cast<uint32_t>(p.col_acc);
                 for (int h = 0; h < p.nH; ++h) {
                     const int g = it * p.nH + h;
+                    const uint32_t acc = tmem + static_cast<uint32_t>(p.col_acc);
                     // head g may start once the conversion warps have read head g - 1 out of the accumulator columns.  (Gating on "S of head
                     // g - 1 issued / completed" instead, so that these bulk MMAs queue behind the latency-critical S, was measured slower:
                     // 221 / 218 vs 209 us -- they then sit in front of P V.)
+                    // (this warp is never two phases behind: qkv_ready of head g needs the q|k|v it is about to issue)
                     if (g > 0) mbar_wait(&bars->qkv_ready, static_cast<uint32_t>(g - 1) & 1);
                     tr_ev<TRACE>(p.trace, 2, it, h, 4);
                     // (K slab, N piece) steps of 4 MMAs: one batch of 12 in a single elected region was measured at ~280 cycles per MMA

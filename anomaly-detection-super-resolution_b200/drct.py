@@ -30,6 +30,12 @@ from .pack import PackedWeight, round_up
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # src/drct.py:774
 _FUSED_ADJUST = os.environ.get("ADSR_FUSED_ADJUST", "1") != "0"  # A/B switch: 0 = adjust convs as separate GEMMs
 _FOLD_ADJUST5 = os.environ.get("ADSR_FOLD_ADJUST5", "1") != "0"  # A/B switch: 0 = adjust5 + the RDG residual as a row-tile GEMM
+if os.environ.get("ADSR_ATTN_PIPE", "1") == "0":                # A/B switch: 0 = the fused attention kernel takes its heads one after the other
+    import ctypes as _ct
+    from . import _abi as _abi_dbg
+    _f = _abi_dbg.lib().adsr_debug_set_attn_pipe
+    _f.restype, _f.argtypes = None, [_ct.c_int]
+    _f(0)
 _ALT_TILE_ORDER = os.environ.get("ADSR_ALT_TILE_ORDER", "1") != "0"  # A/B switch: 0 = every kernel walks its row tiles front to back
 _FUSED_ATTN = os.environ.get("ADSR_FUSED_ATTN", "1") != "0"
 _PREFER_ATTN2 = os.environ.get("ADSR_PREFER_ATTN2", "0") != "0"  # A/B switch: 1 = swin_attn2 (+ proj GEMM) wherever it covers the block shape    # A/B switch for profiling: 0 = separate qkv / attention / proj kernels
