@@ -177,11 +177,13 @@ __global__ void __launch_bounds__(kThreads, 1) swin_mlp_kernel(const __grid_cons
             const uint64_t b_desc = umma_desc_k_sw128(smem_u32(wadj_s));
             const uint32_t idesc = umma_idesc_bf16_m128(32u);
             const uint32_t d = tmem + static_cast<uint32_t>(p.piece_col[0] + 32 * acc2_buf(it));
-            for (int s = 0; s < p.ks1; ++s) {
-                const int ksteps = min(4, p.k1steps - 4 * s);
-                for (int j = 0; j < ksteps; ++j)
-                    umma_bf16(d, a_desc + static_cast<uint64_t>(s * (kPanelBytes >> 4)) + 2 * j,
-                              b_desc + static_cast<uint64_t>(s * (kAdjSlabBytes >> 4)) + 2 * j, idesc, (s > 0 || j > 0) ? 1u : 0u);
+            for (int s = 0; s < p.ks1; ++s) {                          // straight-line groups of 4: MMAs issued from a rolled inner loop
+                const int ksteps = min(4, p.k1steps - 4 * s);           // cost the issuing thread 100-280 cycles each
+                const uint64_t ad = a_desc + static_cast<uint64_t>(s * (kPanelBytes >> 4)), bd = b_desc + static_cast<uint64_t>(s * (kAdjSlabBytes >> 4));
+                umma_bf16(d, ad, bd, idesc, s > 0 ? 1u : 0u);
+                if (ksteps > 1) umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                if (ksteps > 2) umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                if (ksteps > 3) umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
             }
         }
         __syncwarp();
