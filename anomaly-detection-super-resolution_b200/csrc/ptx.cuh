@@ -121,6 +121,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         : "memory");
 }
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
+// shared memory -> TMEM copy of one [128 rows x 32 bytes] operand slice (descriptor as for an MMA operand; executes in issue order
+// with tcgen05.mma): stages an A operand that many MMAs reuse
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
